@@ -1,0 +1,180 @@
+/*
+ * nfi_render.h -- C ABI of the B200 (sm_100a) fused tri-plane volume renderer.
+ *
+ * Drop-in boundary for ONE hot path of google-research/nerf-from-image: the
+ * per-ray render.  The reference has no FFI of its own
+ * (it is 100 % Python/PyTorch); the seam it offers is the Python call
+ *     render(target_model, height, width, tform_cam2world, focal_length,
+ *            center, bbox, model_input, depth_samples_per_ray, ...)
+ * at /root/reference/run.py:176-191, reached only from
+ * ParallelModel.forward (run.py:597-611).  The entry points below are what a
+ * ctypes binding of that seam calls; nerf_from_image_b200/render.py is that
+ * binding and INTEGRATION.md shows the reference-side stub.
+ *
+ * Conventions
+ *   - plain C types only; every pointer in nfi_render_params /
+ *     nfi_render_grads is a DEVICE pointer to fp32 data owned by the caller
+ *     (the *_host entry points take HOST pointers instead and do the copies);
+ *   - `stream` is a cudaStream_t passed as void*; kernels are only enqueued,
+ *     never synchronised (the *_host entry points synchronise before return);
+ *   - the library keeps no mutable global state and is re-entrant: the
+ *     reference's nn.DataParallel calls render() from one Python thread per
+ *     GPU (run.py:636-644), and ctypes drops the GIL around each call;
+ *   - return value 0 = success; anything else is an error whose text
+ *     nfi_last_error() returns (thread-local).  The Python binding turns it
+ *     into an exception, matching the reference's assert/raise behaviour
+ *     (models/generator.py:412-421).
+ */
+#ifndef NFI_RENDER_H_
+#define NFI_RENDER_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NFI_ABI_VERSION 1
+
+#if defined(__GNUC__)
+#define NFI_API __attribute__((visibility("default")))
+#else
+#define NFI_API
+#endif
+
+#define NFI_PLANE_CHANNELS 32 /* TriplanarDecoder(32, .)  models/generator.py:383 */
+#define NFI_HIDDEN 64         /* hidden_dim             models/generator.py:293 */
+#define NFI_MAX_ATTENTION 15  /* decoder outputs 1+A, padded to <= 16 */
+
+/* what the 5th output of render() carries (run.py:227-257,337-338) */
+enum nfi_extra_mode {
+  NFI_EXTRA_NONE = 0,
+  NFI_EXTRA_COORDS = 1,    /* compute_coords:    sum_i w_i * x_i      [B,H,W,3] */
+  NFI_EXTRA_SEMANTICS = 2  /* compute_semantics: sum_i w_i * probs_i  [B,H,W,A] */
+};
+
+/* where the two random draws of the path come from */
+enum nfi_noise_mode {
+  NFI_NOISE_DETERMINISTIC = 0, /* randomize=False: no jitter, u = linspace(0,1,S) */
+  NFI_NOISE_EXPLICIT = 1       /* noise_t / noise_u tensors (torch.rand_like at
+                                  lib/nerf_utils.py:112, torch.rand at :201) */
+};
+
+/* which implementation of the decoder MLP the kernels use */
+enum nfi_mlp_mode {
+  NFI_MLP_AUTO = 0,
+  NFI_MLP_FP32_SIMT = 1, /* fp32 FFMA on CUDA cores                      */
+  NFI_MLP_TC_3XTF32 = 2  /* tcgen05.mma kind::tf32, hi/lo split (3 MMAs) */
+};
+
+typedef struct nfi_render_params {
+  /* ---- shapes ---- */
+  int32_t batch;       /* B */
+  int32_t height;      /* H  (render(height, ...)) */
+  int32_t width;       /* W */
+  int32_t num_samples; /* S = depth_samples_per_ray: S coarse (+ S fine) */
+  int32_t plane_res;   /* R: planes are [B,3,R,R,32] channel-last */
+  int32_t n_attention; /* A: palette entries (args.attention_values); 0 = the
+                          decoder emits 3 colour logits -> wide sigmoid */
+  /* ---- flags (dataset_config / args read by render(), run.py:200-348) ---- */
+  float scene_range;
+  int32_t white_background;
+  int32_t use_sdf;       /* 1: Laplace-CDF density, 0: softplus(d-1) */
+  int32_t fine_sampling; /* args.fine_sampling: hierarchical pass on/off */
+  int32_t noise_mode;    /* enum nfi_noise_mode */
+  int32_t extra_mode;    /* enum nfi_extra_mode */
+  int32_t compute_normals; /* analytic grad of the SDF, normalised, composited
+                              with detached weights (generator.py:614-623) */
+  int32_t mlp_mode;      /* enum nfi_mlp_mode */
+  /* ---- radiance field (models/generator.py:288-331,587-681) ---- */
+  const float *planes; /* [B,3,R,R,32] channel-last, see nfi_planes_to_channel_last */
+  const float *w1;     /* [64,32]  EFFECTIVE weight (EqualizedLinear gain applied) */
+  const float *b1;     /* [64] */
+  const float *w2;     /* [1+A,64] (or [4,64] when A == 0) */
+  const float *b2;     /* [1+A] */
+  const float *palette; /* [B,A,3] attention values, NULL when A == 0 */
+  const float *beta;    /* [1] Generator.beta  (device scalar; NULL if !use_sdf) */
+  const float *alpha;   /* [1] Generator.alpha */
+  /* ---- cameras (lib/nerf_utils.py:28-91) ---- */
+  const float *c2w;    /* [B,4,4] tform_cam2world */
+  const float *focal;  /* [B] or NULL = orthographic model */
+  const float *center; /* [B,2] or NULL */
+  const float *bbox;   /* [B,2,2] (row 0 start, row 1 range) or NULL */
+  /* ---- noise (NFI_NOISE_EXPLICIT) ---- */
+  const float *noise_t; /* [B,H,W,S] in [0,1) */
+  const float *noise_u; /* [B*H*W,S] in [0,1); only read when fine_sampling */
+  /* ---- outputs ---- */
+  float *rgb;     /* [B,H,W,3] */
+  float *depth;   /* [B,H,W]   */
+  float *mask;    /* [B,H,W]   */
+  float *extra;   /* [B,H,W,3] or [B,H,W,A] or NULL (extra_mode) */
+  float *normals; /* [B,H,W,3] or NULL */
+  float *z_fine;  /* [B*H*W,S] sorted fine depths, kept for the backward pass;
+                     NULL = do not save */
+  /* ---- scratch ---- */
+  void *workspace;        /* >= nfi_render_workspace_bytes(params) */
+  size_t workspace_bytes;
+} nfi_render_params;
+
+/* Upstream gradients in, parameter gradients out (all device pointers).
+ * Every grad_* output is ACCUMULATED into (+=); the caller zero-fills.  A NULL
+ * output pointer skips that gradient (e.g. frozen decoder weights during
+ * inversion, run.py:628-629 `model_ema.requires_grad_(False)`). */
+typedef struct nfi_render_grads {
+  const float *g_rgb;   /* [B,H,W,3] dL/d rgb */
+  const float *g_mask;  /* [B,H,W] or NULL */
+  const float *g_extra; /* like `extra` or NULL */
+  const float *out_rgb;  /* forward outputs, needed for the suffix sums */
+  const float *out_mask;
+  const float *out_extra;
+  float *grad_planes;  /* [B,3,R,R,32] channel-last */
+  float *grad_w1;      /* [64,32] */
+  float *grad_b1;      /* [64] */
+  float *grad_w2;      /* [1+A,64] */
+  float *grad_b2;      /* [1+A] */
+  float *grad_palette; /* [B,A,3] */
+  float *grad_beta;    /* [1] */
+  float *grad_alpha;   /* [1] */
+  float *grad_origins; /* [B,H,W,3] dL/d ray origin       (chain to c2w in the binding) */
+  float *grad_dirs;    /* [B,H,W,3] dL/d unit ray direction */
+} nfi_render_grads;
+
+/* library / build identification */
+NFI_API int nfi_abi_version(void);
+NFI_API const char *nfi_build_info(void); /* "sm_100a ..." */
+NFI_API const char *nfi_last_error(void);
+
+/* Scratch the forward / backward kernels need for `params` (bytes). */
+NFI_API size_t nfi_render_workspace_bytes(const nfi_render_params *params);
+
+/* Planes arrive from SynthesisNetwork as [B,96,R,R] = three [B,32,R,R]
+ * channel-first planes xy/xz/yz (models/generator.py:475-477,500-502).  The
+ * render kernels gather channel-last texels (one 128-byte line per tap).
+ * `batch_stride` is the element stride between images of each source plane. */
+NFI_API int nfi_planes_to_channel_last(const float *xy, const float *xz, const float *yz,
+                               int64_t batch_stride, int32_t batch, int32_t plane_res,
+                               float *dst, void *stream);
+/* inverse re-layout for the plane gradient: [B,3,R,R,32] -> [B,3,32,R,R] */
+NFI_API int nfi_planes_from_channel_last(const float *src, int32_t batch, int32_t plane_res,
+                                 float *dst, void *stream);
+
+/* render() forward: run.py:176-350 from the planes on (rays, near/far, coarse
+ * samples, field, importance resampling, sorted merge, compositing). */
+NFI_API int nfi_render_forward(const nfi_render_params *params, void *stream);
+
+/* autograd of the above: recomputes the samples. */
+NFI_API int nfi_render_backward(const nfi_render_params *params, const nfi_render_grads *grads,
+                        void *stream);
+
+/* Same as nfi_render_forward but every pointer in `params` (inputs and
+ * outputs; `workspace` ignored) is a HOST pointer; `planes` is the
+ * channel-FIRST [B,3,32,R,R] array the reference produces.  Copies in, runs,
+ * copies rgb/depth/mask/extra/normals out and synchronises.  This is the
+ * end-to-end entry the bench's `e2e` figure is measured through. */
+NFI_API int nfi_render_forward_host(const nfi_render_params *params, int32_t device);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NFI_RENDER_H_ */

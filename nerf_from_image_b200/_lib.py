@@ -1,0 +1,124 @@
+"""ctypes binding of libnfi_render.so (the C ABI declared in include/nfi_render.h).
+
+The library is built in-tree by ``nerf_from_image_b200/csrc/build.sh`` (or
+``__graft_entry__.build()``).  There is no fallback: if the shared object is
+missing or a launch fails, the caller gets an exception.
+"""
+
+import ctypes
+import os
+import subprocess
+import threading
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, 'csrc', 'libnfi_render.so')
+
+c_float_p = ctypes.POINTER(ctypes.c_float)
+
+EXTRA_NONE, EXTRA_COORDS, EXTRA_SEMANTICS = 0, 1, 2
+NOISE_DETERMINISTIC, NOISE_EXPLICIT = 0, 1
+MLP_AUTO, MLP_FP32_SIMT, MLP_TC_3XTF32 = 0, 1, 2
+
+
+class RenderParams(ctypes.Structure):
+    """struct nfi_render_params -- field order must match the header."""
+    _fields_ = [
+        ('batch', ctypes.c_int32), ('height', ctypes.c_int32),
+        ('width', ctypes.c_int32), ('num_samples', ctypes.c_int32),
+        ('plane_res', ctypes.c_int32), ('n_attention', ctypes.c_int32),
+        ('scene_range', ctypes.c_float),
+        ('white_background', ctypes.c_int32), ('use_sdf', ctypes.c_int32),
+        ('fine_sampling', ctypes.c_int32), ('noise_mode', ctypes.c_int32),
+        ('extra_mode', ctypes.c_int32), ('compute_normals', ctypes.c_int32),
+        ('mlp_mode', ctypes.c_int32),
+        ('planes', ctypes.c_void_p), ('w1', ctypes.c_void_p),
+        ('b1', ctypes.c_void_p), ('w2', ctypes.c_void_p),
+        ('b2', ctypes.c_void_p), ('palette', ctypes.c_void_p),
+        ('beta', ctypes.c_void_p), ('alpha', ctypes.c_void_p),
+        ('c2w', ctypes.c_void_p), ('focal', ctypes.c_void_p),
+        ('center', ctypes.c_void_p), ('bbox', ctypes.c_void_p),
+        ('noise_t', ctypes.c_void_p), ('noise_u', ctypes.c_void_p),
+        ('rgb', ctypes.c_void_p), ('depth', ctypes.c_void_p),
+        ('mask', ctypes.c_void_p), ('extra', ctypes.c_void_p),
+        ('normals', ctypes.c_void_p), ('z_fine', ctypes.c_void_p),
+        ('workspace', ctypes.c_void_p), ('workspace_bytes', ctypes.c_size_t),
+    ]
+
+
+class RenderGrads(ctypes.Structure):
+    """struct nfi_render_grads."""
+    _fields_ = [(n, ctypes.c_void_p) for n in (
+        'g_rgb', 'g_mask', 'g_extra', 'out_rgb', 'out_mask', 'out_extra',
+        'grad_planes', 'grad_w1', 'grad_b1', 'grad_w2', 'grad_b2',
+        'grad_palette', 'grad_beta', 'grad_alpha', 'grad_origins',
+        'grad_dirs')]
+
+
+# every symbol include/nfi_render.h declares (tests/test_abi.py checks the
+# header against this table and the table against the built library)
+EXPORTS = {
+    'nfi_abi_version': (ctypes.c_int, []),
+    'nfi_build_info': (ctypes.c_char_p, []),
+    'nfi_last_error': (ctypes.c_char_p, []),
+    'nfi_render_workspace_bytes': (ctypes.c_size_t,
+                                   [ctypes.POINTER(RenderParams)]),
+    'nfi_planes_to_channel_last': (ctypes.c_int, [
+        ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64,
+        ctypes.c_int32, ctypes.c_int32, ctypes.c_void_p, ctypes.c_void_p]),
+    'nfi_planes_from_channel_last': (ctypes.c_int, [
+        ctypes.c_void_p, ctypes.c_int32, ctypes.c_int32, ctypes.c_void_p,
+        ctypes.c_void_p]),
+    'nfi_render_forward': (ctypes.c_int, [ctypes.POINTER(RenderParams),
+                                          ctypes.c_void_p]),
+    'nfi_render_backward': (ctypes.c_int, [ctypes.POINTER(RenderParams),
+                                           ctypes.POINTER(RenderGrads),
+                                           ctypes.c_void_p]),
+    'nfi_render_forward_host': (ctypes.c_int, [ctypes.POINTER(RenderParams),
+                                               ctypes.c_int32]),
+}
+
+_lib = None
+_lock = threading.Lock()
+
+
+class NfiError(RuntimeError):
+    pass
+
+
+def build(verbose=False):
+    """Compiles the library in-tree (nvcc, sm_100a)."""
+    script = os.path.join(_HERE, 'csrc', 'build.sh')
+    res = subprocess.run(['bash', script], capture_output=True, text=True)
+    if verbose or res.returncode != 0:
+        print(res.stdout)
+        print(res.stderr)
+    if res.returncode != 0:
+        raise NfiError('building libnfi_render.so failed')
+    return LIB_PATH
+
+
+def load():
+    """Loads libnfi_render.so; raises if it has not been built."""
+    global _lib
+    with _lock:
+        if _lib is None:
+            if not os.path.isfile(LIB_PATH):
+                raise NfiError(
+                    'libnfi_render.so is missing (%s): run '
+                    'nerf_from_image_b200/csrc/build.sh or '
+                    '__graft_entry__.build(); there is no fallback path.'
+                    % LIB_PATH)
+            lib = ctypes.CDLL(LIB_PATH)
+            for name, (restype, argtypes) in EXPORTS.items():
+                fn = getattr(lib, name)
+                fn.restype = restype
+                fn.argtypes = argtypes
+            if lib.nfi_abi_version() != 1:
+                raise NfiError('libnfi_render.so ABI version mismatch')
+            _lib = lib
+    return _lib
+
+
+def check(rc):
+    if rc != 0:
+        raise NfiError(load().nfi_last_error().decode() or 'nfi error %d' % rc)

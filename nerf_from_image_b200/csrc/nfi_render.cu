@@ -1,0 +1,297 @@
+// C-ABI entry points of libnfi_render.so (see include/nfi_render.h).
+//
+// Build: nvcc -gencode arch=compute_100a,code=sm_100a --fmad=false -lineinfo
+//        (nerf_from_image_b200/csrc/build.sh).  No torch, no CPU fallback: on a
+//        machine without an sm_100 device every launch returns an error.
+#include <cuda_runtime.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "nfi_backward.cuh"
+#include "nfi_forward.cuh"
+#include "nfi_render.h"
+
+#define NFI_STR_(x) #x
+#define NFI_STR(x) NFI_STR_(x)
+
+namespace {
+
+thread_local char g_err[512] = "";
+
+int fail(const char* fmt, const char* detail = "") {
+  snprintf(g_err, sizeof(g_err), fmt, detail);
+  return 1;
+}
+
+#define NFI_CUDA(expr)                                                      \
+  do {                                                                      \
+    cudaError_t e__ = (expr);                                               \
+    if (e__ != cudaSuccess) {                                               \
+      snprintf(g_err, sizeof(g_err), "%s failed: %s", #expr,                \
+               cudaGetErrorString(e__));                                    \
+      return 2;                                                             \
+    }                                                                       \
+  } while (0)
+
+int nout_pad_of(const nfi_render_params* p) {
+  const int nout = 1 + (p->n_attention > 0 ? p->n_attention : 3);
+  return nout <= 4 ? 4 : (nout <= 12 ? 12 : 16);
+}
+
+int check_params(const nfi_render_params* p) {
+  if (p == nullptr) return fail("params is NULL");
+  if (p->batch <= 0 || p->height <= 0 || p->width <= 0) return fail("empty render");
+  if (p->num_samples < 4 || p->num_samples > 512)
+    return fail("depth_samples_per_ray must be in [4, 512]");
+  if (p->plane_res < 2) return fail("plane_res must be >= 2");
+  if (p->n_attention < 0 || p->n_attention > NFI_MAX_ATTENTION)
+    return fail("attention_values must be in [0, 15]");
+  if (!(p->scene_range > 0.f)) return fail("scene_range must be positive");
+  if (!p->planes || !p->w1 || !p->b1 || !p->w2 || !p->b2 || !p->c2w)
+    return fail("planes / decoder weights / tform_cam2world must be given");
+  if (p->n_attention > 0 && !p->palette) return fail("palette missing (attention_values > 0)");
+  if (p->use_sdf && (!p->beta || !p->alpha)) return fail("use_sdf needs beta and alpha");
+  if (p->noise_mode == NFI_NOISE_EXPLICIT) {
+    if (!p->noise_t) return fail("noise_t missing (randomize=True)");
+    if (p->fine_sampling && !p->noise_u) return fail("noise_u missing (fine_sampling)");
+  } else if (p->noise_mode != NFI_NOISE_DETERMINISTIC) {
+    return fail("unknown noise_mode");
+  }
+  if (p->extra_mode == NFI_EXTRA_SEMANTICS && p->n_attention <= 0)
+    return fail("compute_semantics needs attention_values > 0");  // run.py:232
+  if (p->extra_mode < 0 || p->extra_mode > 2) return fail("unknown extra_mode");
+  if (p->extra_mode != NFI_EXTRA_NONE && !p->extra) return fail("extra output buffer missing");
+  if (p->compute_normals) return fail("compute_normals is not implemented in this build");
+  if (!p->rgb || !p->depth || !p->mask) return fail("output buffers missing");
+  return 0;
+}
+
+size_t num_ctas(const nfi_render_params* p) {
+  const size_t tx = (p->width + nfi::kTileW - 1) / nfi::kTileW;
+  const size_t ty = (p->height + nfi::kTileH - 1) / nfi::kTileH;
+  return tx * ty * (size_t)p->batch;
+}
+
+int ne_store_of(const nfi_render_params* p) {
+  return p->extra_mode == NFI_EXTRA_SEMANTICS ? nout_pad_of(p) - 1 : 0;
+}
+
+template <typename K>
+int launch(K kernel, const nfi_render_params& p, size_t smem_bytes, cudaStream_t st) {
+  if (smem_bytes > 227 * 1024)
+    return fail("depth_samples_per_ray too large for the shared-memory columns");
+  NFI_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                (int)smem_bytes));
+  kernel<<<(unsigned)num_ctas(&p), nfi::kThreads, smem_bytes, st>>>(p);
+  NFI_CUDA(cudaGetLastError());
+  return 0;
+}
+
+template <int NP, int EX>
+int launch_fwd_fine(const nfi_render_params& p, size_t smem, cudaStream_t st) {
+  if (p.fine_sampling) return launch(nfi::render_forward_simt<NP, EX, true>, p, smem, st);
+  return launch(nfi::render_forward_simt<NP, EX, false>, p, smem, st);
+}
+
+template <int NP>
+int launch_fwd_extra(const nfi_render_params& p, size_t smem, cudaStream_t st) {
+  switch (p.extra_mode) {
+    case NFI_EXTRA_COORDS: return launch_fwd_fine<NP, 1>(p, smem, st);
+    case NFI_EXTRA_SEMANTICS: return launch_fwd_fine<NP, 2>(p, smem, st);
+    default: return launch_fwd_fine<NP, 0>(p, smem, st);
+  }
+}
+
+// ---------------------------------------------------------------- re-layout
+// [B,32,R,R] x3 (channel-first)  ->  [B,3,R,R,32] (channel-last), and back.
+// 32 channels x 32 pixels per block through a padded shared tile: both the
+// reads (along pixels) and the writes (along channels) are 128-byte lines.
+__global__ void __launch_bounds__(256)
+planes_to_cl_kernel(const float* __restrict__ xy, const float* __restrict__ xz,
+                    const float* __restrict__ yz, long long batch_stride, int RR,
+                    float* __restrict__ dst) {
+  __shared__ float tile[32][33];
+  const int b = blockIdx.z, pl = blockIdx.y;
+  const float* src = (pl == 0 ? xy : (pl == 1 ? xz : yz)) + (long long)b * batch_stride;
+  const int pix0 = blockIdx.x * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
+  for (int c = ty; c < 32; c += 8) {
+    const int pix = pix0 + tx;
+    tile[c][tx] = (pix < RR) ? src[(long long)c * RR + pix] : 0.f;
+  }
+  __syncthreads();
+  float* out = dst + ((long long)(b * 3 + pl) * RR) * 32;
+  for (int q = ty; q < 32; q += 8) {
+    const int pix = pix0 + q;
+    if (pix < RR) out[(long long)pix * 32 + tx] = tile[tx][q];
+  }
+}
+
+__global__ void __launch_bounds__(256)
+planes_from_cl_kernel(const float* __restrict__ src, int RR, float* __restrict__ dst) {
+  __shared__ float tile[32][33];
+  const int b = blockIdx.z, pl = blockIdx.y;
+  const float* in = src + ((long long)(b * 3 + pl) * RR) * 32;
+  float* out = dst + ((long long)(b * 3 + pl) * 32) * RR;
+  const int pix0 = blockIdx.x * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  for (int q = ty; q < 32; q += 8) {
+    const int pix = pix0 + q;
+    tile[q][tx] = (pix < RR) ? in[(long long)pix * 32 + tx] : 0.f;
+  }
+  __syncthreads();
+  for (int c = ty; c < 32; c += 8) {
+    const int pix = pix0 + tx;
+    if (pix < RR) out[(long long)c * RR + pix] = tile[tx][c];
+  }
+}
+
+}  // namespace
+
+extern "C" {
+
+int nfi_abi_version(void) { return NFI_ABI_VERSION; }
+
+const char* nfi_build_info(void) {
+  return "libnfi_render sm_100a (compute_100a) nvcc " NFI_STR(__CUDACC_VER_MAJOR__) "." NFI_STR(
+      __CUDACC_VER_MINOR__) " fmad=false";
+}
+
+const char* nfi_last_error(void) { return g_err; }
+
+size_t nfi_render_workspace_bytes(const nfi_render_params* p) {
+  if (p == nullptr) return 0;
+  size_t fwd = 0;
+  if (p->fine_sampling)
+    fwd = num_ctas(p) * nfi::fwd_scratch_floats_per_cta(p->num_samples, ne_store_of(p)) *
+          sizeof(float);
+  return fwd + 256;
+}
+
+int nfi_planes_to_channel_last(const float* xy, const float* xz, const float* yz,
+                               int64_t batch_stride, int32_t batch, int32_t plane_res, float* dst,
+                               void* stream) {
+  if (!xy || !xz || !yz || !dst || batch <= 0 || plane_res <= 0) return fail("bad re-layout args");
+  const int RR = plane_res * plane_res;
+  dim3 grid((RR + 31) / 32, 3, batch);
+  planes_to_cl_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(xy, xz, yz, batch_stride, RR, dst);
+  NFI_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int nfi_planes_from_channel_last(const float* src, int32_t batch, int32_t plane_res, float* dst,
+                                 void* stream) {
+  if (!src || !dst || batch <= 0 || plane_res <= 0) return fail("bad re-layout args");
+  const int RR = plane_res * plane_res;
+  dim3 grid((RR + 31) / 32, 3, batch);
+  planes_from_cl_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(src, RR, dst);
+  NFI_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int nfi_render_forward(const nfi_render_params* params, void* stream) {
+  if (int rc = check_params(params)) return rc;
+  const nfi_render_params& p = *params;
+  if (p.fine_sampling) {
+    if (!p.workspace || p.workspace_bytes < nfi_render_workspace_bytes(params))
+      return fail("workspace too small (see nfi_render_workspace_bytes)");
+  }
+  const int np = nout_pad_of(params);
+  const size_t smem = nfi::fwd_smem_floats(np, p.num_samples, p.fine_sampling != 0) * sizeof(float);
+  cudaStream_t st = (cudaStream_t)stream;
+  switch (np) {
+    case 4: return launch_fwd_extra<4>(p, smem, st);
+    case 12: return launch_fwd_extra<12>(p, smem, st);
+    default: return launch_fwd_extra<16>(p, smem, st);
+  }
+}
+
+int nfi_render_backward(const nfi_render_params* params, const nfi_render_grads* grads,
+                        void* stream) {
+  if (int rc = check_params(params)) return rc;
+  if (grads == nullptr || grads->g_rgb == nullptr) return fail("grads->g_rgb missing");
+  return nfi::launch_backward(*params, *grads, (cudaStream_t)stream, g_err, sizeof(g_err));
+}
+
+int nfi_render_forward_host(const nfi_render_params* hp, int32_t device) {
+  if (hp == nullptr) return fail("params is NULL");
+  NFI_CUDA(cudaSetDevice(device));
+  cudaStream_t st;
+  NFI_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+  cudaMemPool_t pool;
+  NFI_CUDA(cudaDeviceGetDefaultMemPool(&pool, device));
+  uint64_t keep = UINT64_MAX;
+  NFI_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
+
+  nfi_render_params d = *hp;
+  const size_t B = hp->batch, H = hp->height, W = hp->width, S = hp->num_samples;
+  const size_t R = hp->plane_res, A = hp->n_attention;
+  const size_t nout = 1 + (A > 0 ? A : 3);
+  const size_t n_rays = B * H * W;
+  void* to_free[32];
+  int n_free = 0;
+  int rc = 0;
+  auto dalloc = [&](size_t bytes) -> float* {
+    void* q = nullptr;
+    if (cudaMallocAsync(&q, bytes ? bytes : 4, st) != cudaSuccess) return nullptr;
+    to_free[n_free++] = q;
+    return (float*)q;
+  };
+  auto up = [&](const float* h, size_t n) -> const float* {
+    if (h == nullptr) return nullptr;
+    float* q = dalloc(n * sizeof(float));
+    if (q) cudaMemcpyAsync(q, h, n * sizeof(float), cudaMemcpyHostToDevice, st);
+    return q;
+  };
+  const size_t plane_elems = B * 3 * R * R * 32;
+  const float* planes_cf = up(hp->planes, plane_elems);
+  float* planes_cl = dalloc(plane_elems * sizeof(float));
+  d.w1 = up(hp->w1, 64 * 32);
+  d.b1 = up(hp->b1, 64);
+  d.w2 = up(hp->w2, nout * 64);
+  d.b2 = up(hp->b2, nout);
+  d.palette = up(hp->palette, B * A * 3);
+  d.beta = up(hp->beta, 1);
+  d.alpha = up(hp->alpha, 1);
+  d.c2w = up(hp->c2w, B * 16);
+  d.focal = up(hp->focal, B);
+  d.center = up(hp->center, B * 2);
+  d.bbox = up(hp->bbox, B * 4);
+  d.noise_t = up(hp->noise_t, n_rays * S);
+  d.noise_u = hp->fine_sampling ? up(hp->noise_u, n_rays * S) : nullptr;
+  const size_t ne = hp->extra_mode == NFI_EXTRA_COORDS ? 3 : (hp->extra_mode ? A : 0);
+  d.rgb = dalloc(n_rays * 3 * sizeof(float));
+  d.depth = dalloc(n_rays * sizeof(float));
+  d.mask = dalloc(n_rays * sizeof(float));
+  d.extra = ne ? dalloc(n_rays * ne * sizeof(float)) : nullptr;
+  d.normals = nullptr;
+  d.z_fine = nullptr;
+  d.planes = planes_cl;
+  d.workspace_bytes = nfi_render_workspace_bytes(&d);
+  d.workspace = dalloc(d.workspace_bytes);
+  if (!planes_cf || !planes_cl || !d.rgb || !d.depth || !d.mask || !d.workspace) {
+    rc = fail("device allocation failed");
+  } else {
+    rc = nfi_planes_to_channel_last(planes_cf, planes_cf + 32 * R * R, planes_cf + 64 * R * R,
+                                    (int64_t)(96 * R * R), (int32_t)B, (int32_t)R, planes_cl, st);
+    if (!rc) rc = nfi_render_forward(&d, st);
+    if (!rc) {
+      cudaMemcpyAsync(hp->rgb, d.rgb, n_rays * 3 * sizeof(float), cudaMemcpyDeviceToHost, st);
+      cudaMemcpyAsync(hp->depth, d.depth, n_rays * sizeof(float), cudaMemcpyDeviceToHost, st);
+      cudaMemcpyAsync(hp->mask, d.mask, n_rays * sizeof(float), cudaMemcpyDeviceToHost, st);
+      if (ne && hp->extra)
+        cudaMemcpyAsync(hp->extra, d.extra, n_rays * ne * sizeof(float), cudaMemcpyDeviceToHost,
+                        st);
+    }
+  }
+  for (int i = 0; i < n_free; ++i) cudaFreeAsync(to_free[i], st);
+  cudaError_t e = cudaStreamSynchronize(st);
+  cudaStreamDestroy(st);
+  if (!rc && e != cudaSuccess) {
+    snprintf(g_err, sizeof(g_err), "render failed: %s", cudaGetErrorString(e));
+    rc = 2;
+  }
+  return rc;
+}
+
+}  // extern "C"

@@ -1,0 +1,127 @@
+"""Seeded synthetic scenes and cameras for tests, smoke and bench.
+
+No datasets or checkpoints exist offline, so the render path is exercised on
+an analytic stand-in for a trained generator: tri-planes
+whose channel 0 carries a quadratic that the 2-layer decoder turns into a
+sphere-like signed distance (so the Laplace-CDF density of
+/root/reference/models/generator.py:629-636 has a real surface, a mask
+coverage well away from 0 and 1, and an empty margin near the cube faces),
+and smooth low-frequency content in the other 31 channels that drives the
+softmax-over-palette colour of :668-679.  Cameras follow the reference's
+conventions: OpenGL axes (camera looks down -z, lib/nerf_utils.py:60),
+look-at-origin poses, focal in [1.0, 1.6] for the perspective sets and
+``c2w[3,3] = 1/scale`` for the orthographic CUB model (:66-89).
+"""
+
+import math
+
+import torch
+import torch.nn.functional as F
+
+HIDDEN = 64
+PLANE_CHANNELS = 32
+
+# per-dataset constants of /root/reference/data/loaders.py:23-87
+DATASET_CONFIGS = {
+    'p3d_car': dict(scene_range=1.4, white_background=False, ortho=False,
+                    radius=3.0, object_radius=0.7),
+    'cub': dict(scene_range=2.0, white_background=False, ortho=True,
+                radius=3.0, object_radius=0.45),
+    'shapenet_chairs': dict(scene_range=0.55, white_background=True,
+                            ortho=False, radius=1.6, object_radius=0.8),
+}
+
+
+def make_scene(seed, batch, plane_res=256, attention_values=10,
+               scene_range=1.4, white_background=False, object_radius=0.7,
+               device='cpu', channels=PLANE_CHANNELS):
+    """Returns a dict: planes [B,3,C,R,R], w1 [64,C], b1 [64], w2 [1+A,64],
+    b2 [1+A] (EFFECTIVE weights, EqualizedLinear gains already applied),
+    palette [B,A,3] | None, beta [1], alpha [1], scene_range, white_background.
+    """
+    gen = torch.Generator().manual_seed(seed)
+    B, C, R = batch, channels, plane_res
+    A = attention_values
+    n_out = 1 + (A if A > 0 else 3)
+    low = max(4, R // 8)
+    noise = torch.randn(B * 3, C, low, low, generator=gen)
+    shape_noise = torch.randn(B * 3, 1, 4, 4, generator=gen)
+    w1 = torch.randn(HIDDEN, C, generator=gen) / math.sqrt(C)
+    b1 = 0.1 * torch.randn(HIDDEN, generator=gen)
+    w2 = torch.randn(n_out, HIDDEN, generator=gen) / math.sqrt(HIDDEN)
+    b2 = 0.1 * torch.randn(n_out, generator=gen)
+    palette = None
+    if A > 0:
+        palette = torch.rand(B, A, 3, generator=gen) * 2 - 1
+
+    a, c = 4.0, 6.0
+    rho = object_radius
+    g = scene_range / (2 * rho)
+    w1[0].zero_()
+    w1[0, 0] = a
+    b1[0] = c
+    w2[0] = 0.01 * torch.randn(HIDDEN, generator=gen)
+    w2[0, 0] = 3 * g / a
+    b2[0] = -(3 * g / a) * c - g * rho * rho
+
+    noise = noise.to(device)
+    shape_noise = shape_noise.to(device)
+    planes = 0.5 * F.interpolate(noise, size=(R, R), mode='bilinear',
+                                 align_corners=True)
+    lin = torch.linspace(-1, 1, R, device=device)
+    quad = 0.5 * (lin[None, :] ** 2 + lin[:, None] ** 2)
+    planes[:, 0] = quad[None] + 0.03 * F.interpolate(
+        shape_noise, size=(R, R), mode='bicubic', align_corners=True)[:, 0]
+    planes = planes.view(B, 3, C, R, R).contiguous()
+
+    to = lambda t: t.to(device) if t is not None else None
+    return dict(planes=planes, w1=to(w1), b1=to(b1), w2=to(w2), b2=to(b2),
+                palette=to(palette), beta=torch.tensor([0.1], device=device),
+                alpha=torch.tensor([1.0], device=device),
+                scene_range=float(scene_range),
+                white_background=bool(white_background))
+
+
+def make_cameras(seed, batch, ortho=False, radius=3.0, with_bbox=False,
+                 with_center=False, device='cpu'):
+    """Look-at-origin cameras: dict(c2w [B,4,4], focal [B]|None, center, bbox)."""
+    gen = torch.Generator().manual_seed(seed + 7919)
+    az = torch.rand(batch, generator=gen) * 2 * math.pi
+    el = torch.rand(batch, generator=gen) * 0.8 - 0.3
+    back = torch.stack((torch.cos(el) * torch.sin(az), torch.sin(el),
+                        torch.cos(el) * torch.cos(az)), dim=-1)
+    up = torch.tensor([0., 1., 0.]).expand(batch, 3)
+    right = F.normalize(torch.linalg.cross(up, back), dim=-1)
+    true_up = torch.linalg.cross(back, right)
+    c2w = torch.zeros(batch, 4, 4)
+    c2w[:, :3, 0] = right
+    c2w[:, :3, 1] = true_up
+    c2w[:, :3, 2] = back
+    c2w[:, :3, 3] = back * radius
+    c2w[:, 3, 3] = 1.0
+    focal = None
+    if ortho:
+        scale = 0.9 + 0.2 * torch.rand(batch, generator=gen)
+        c2w[:, 3, 3] = 1.0 / scale
+    else:
+        focal = 1.0 + 0.6 * torch.rand(batch, generator=gen)
+    bbox = None
+    if with_bbox:
+        start = -1.0 + 0.3 * torch.rand(batch, 1, 2, generator=gen)
+        rng = 1.6 + 0.4 * torch.rand(batch, 1, 2, generator=gen)
+        bbox = torch.cat((start, rng), dim=1)
+    center = None
+    if with_center and not ortho:
+        center = 0.45 + 0.1 * torch.rand(batch, 2, generator=gen)
+    to = lambda t: t.to(device) if t is not None else None
+    return dict(c2w=to(c2w), focal=to(focal), center=to(center), bbox=to(bbox))
+
+
+def make_noise(seed, batch, height, width, num_samples, fine=True,
+               device='cpu'):
+    """Explicit stratified jitter [B,H,W,S] and inverse-CDF uniforms [B*H*W,S]."""
+    gen = torch.Generator().manual_seed(seed + 104729)
+    noise_t = torch.rand(batch, height, width, num_samples, generator=gen)
+    noise_u = torch.rand(batch * height * width, num_samples,
+                         generator=gen) if fine else None
+    return noise_t.to(device), (noise_u.to(device) if fine else None)

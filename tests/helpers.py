@@ -1,0 +1,58 @@
+"""Shared helpers for the parity tests (oracle side and CUDA side)."""
+import torch
+
+from nerf_from_image_b200 import synthetic
+from oracle import render_oracle as O
+
+CASES = {
+    # name: (dataset, camera kwargs, scene kwargs)
+    'p3d_bbox': ('p3d_car', dict(with_bbox=True), {}),
+    'p3d_plain': ('p3d_car', dict(), {}),
+    'cub_ortho': ('cub', dict(), {}),
+    'cub_ortho_bbox': ('cub', dict(with_bbox=True), {}),
+    'chairs_white_center': ('shapenet_chairs', dict(with_center=True), {}),
+}
+
+
+def make_case(name, seed=1, batch=2, plane_res=32, attention_values=10, device='cpu'):
+    ds, cam_kw, sc_kw = CASES[name]
+    cfg = synthetic.DATASET_CONFIGS[ds]
+    scene = synthetic.make_scene(seed, batch, plane_res=plane_res,
+                                 attention_values=attention_values,
+                                 scene_range=cfg['scene_range'],
+                                 white_background=cfg['white_background'],
+                                 object_radius=cfg['object_radius'], device=device, **sc_kw)
+    cams = synthetic.make_cameras(seed, batch, ortho=cfg['ortho'], radius=cfg['radius'],
+                                  device=device, **cam_kw)
+    return scene, cams
+
+
+def to_device(d, device):
+    return {k: (v.to(device) if torch.is_tensor(v) else v) for k, v in d.items()}
+
+
+def run_oracle(scene, cams, H, W, S, noise_t, noise_u, **kw):
+    return O.render_oracle(scene['planes'], scene['w1'], scene['b1'], scene['w2'],
+                           scene['b2'], scene['palette'], scene['beta'], scene['alpha'],
+                           cams['c2w'], cams['focal'], cams['center'], cams['bbox'],
+                           H, W, S, noise_t, noise_u, scene_range=scene['scene_range'],
+                           white_background=scene['white_background'], **kw)
+
+
+def run_cuda(scene, cams, H, W, S, noise_t, noise_u, use_sdf=True, fine_sampling=True,
+             extra_mode=0, cam_grad=True, device='cuda'):
+    from nerf_from_image_b200.fused import RenderConfig, fused_render
+    sc = to_device(scene, device)
+    cm = to_device(cams, device)
+    A = sc['palette'].shape[1] if sc['palette'] is not None else 0
+    cfg = RenderConfig(scene_range=sc['scene_range'], white_background=sc['white_background'],
+                       use_sdf=use_sdf, fine_sampling=fine_sampling, attention_values=A)
+    nt = noise_t.to(device) if noise_t is not None else None
+    nu = noise_u.to(device) if noise_u is not None else None
+    return fused_render(sc['planes'], sc['w1'], sc['b1'], sc['w2'], sc['b2'], sc['palette'],
+                        sc['beta'], sc['alpha'], cm['c2w'], cm['focal'], cm['center'],
+                        cm['bbox'], cfg, H, W, S, nt, nu, extra_mode, cam_grad)
+
+
+def rel_l2(a, b):
+    return ((a - b).norm() / b.norm().clamp_min(1e-12)).item()

@@ -1,0 +1,58 @@
+"""The C-ABI library builds, loads and exports what include/nfi_render.h declares
+(no compute calls: this file runs without a GPU)."""
+import ctypes
+import os
+import re
+
+from nerf_from_image_b200 import _lib
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HEADER = os.path.join(ROOT, 'include', 'nfi_render.h')
+
+
+def header_functions():
+    src = open(HEADER).read()
+    return re.findall(r'NFI_API\s+[\w\s\*]+?\b(nfi_\w+)\s*\(', src)
+
+
+def test_header_and_binding_agree():
+    names = header_functions()
+    assert len(names) >= 9
+    assert sorted(names) == sorted(_lib.EXPORTS)
+
+
+def test_library_exports_every_declared_symbol():
+    lib = _lib.load()
+    for name in header_functions():
+        assert hasattr(lib, name), name
+    assert lib.nfi_abi_version() == 1
+    assert b'sm_100a' in lib.nfi_build_info()
+
+
+def test_struct_layout_matches_header():
+    """Field order / count of the ctypes mirrors vs the C structs."""
+    src = open(HEADER).read()
+    for cname, cls in (('nfi_render_params', _lib.RenderParams),
+                       ('nfi_render_grads', _lib.RenderGrads)):
+        body = re.search(r'typedef struct %s \{(.*?)\} %s;' % (cname, cname), src, re.S).group(1)
+        body = re.sub(r'/\*.*?\*/', '', body, flags=re.S)
+        fields = [re.search(r'(\w+)\s*$', d.strip()).group(1)
+                  for d in body.split(';') if d.strip()]
+        assert fields == [f[0] for f in cls._fields_], cname
+
+
+def test_errors_are_reported_without_a_gpu():
+    lib = _lib.load()
+    p = _lib.RenderParams()
+    assert lib.nfi_render_forward(ctypes.byref(p), None) != 0
+    assert len(lib.nfi_last_error()) > 0
+    assert lib.nfi_render_workspace_bytes(None) == 0
+
+
+def test_no_cpu_fallback():
+    import pytest
+    import torch
+    from tests import helpers as Hh
+    scene, cams = Hh.make_case('p3d_plain', batch=1, plane_res=8)
+    with pytest.raises(_lib.NfiError):
+        Hh.run_cuda(scene, cams, 8, 8, 8, None, None, device='cpu')
