@@ -1,0 +1,349 @@
+#!/usr/bin/env python
+"""Benchmark of the fused tri-plane render (BASELINE.json metric: rays/s at
+128x128, 64 coarse + 64 fine samples per ray).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+
+One "step" = one pass of the hot path over one batch of config 2
+(p3d_car geometry, batch 32 per GPU): planes [32,3,32,256,256] fp32 as the
+synthesis network leaves them -> channel-last re-layout -> fused forward render
+-> rgb/depth/mask.  Inputs (805 MB of planes + 268 MB of noise per GPU) are far
+larger than the 126 MB L2, so consecutive steps cannot be served from cache.
+
+  value      rays/s with inputs resident in HBM (CUDA events, max over ranks)
+  e2e        same metric through the C-ABI host entry point
+             nfi_render_forward_host with PINNED HOST buffers: H2D of every
+             input and D2H of rgb/depth/mask inside the timed region
+  roofline   dominant kernel (render_forward_*) against the algorithmic
+             tensor-FLOP bound of SURVEY.md section 8d
+  cpu_baseline   the oracle port (oracle/render_oracle.py, same torch ops as the
+             reference) on this box's host cores, bounded sample, rank 0, N=1
+
+--impl reference times only the CPU oracle port (the reference's own CPU
+PyTorch path cannot travel to the GPU box) on the same config.
+"""
+import argparse
+import ctypes
+import json
+import math
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = 'rays_per_sec_128x128_64+64spp'
+UNIT = 'rays/s'
+CFG = dict(batch=32, height=128, width=128, samples=64, plane_res=256, attention_values=10,
+           dataset='p3d_car')
+FLOPS_PER_POINT = 2 * 32 * 64 + 2 * 64 * 11 + 2 * 10 * 3  # 5,564
+
+
+def peaks():
+    path = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.isfile(path):
+        p = json.load(open(path))
+        return dict(hbm_gbs=p['hbm_gbs'], tflops=p.get('bf16_tflops_sustained', p['bf16_tflops']),
+                    source='measured (MEASURED_PEAKS.json, bf16 sustained)')
+    return dict(hbm_gbs=6650.0, tflops=1590.0, source='fallback (B200_PROFILING.md)')
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons during the timed region."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.rows, self.stop_flag = index, [], False
+
+    def run(self):
+        q = ('clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,'
+             'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,'
+             'clocks_event_reasons.sw_power_cap')
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(['nvidia-smi', '-i', str(self.index), '--query-gpu=' + q,
+                                      '--format=csv,noheader,nounits'], capture_output=True,
+                                     text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([x.strip() for x in out.split(',')])
+            except Exception:
+                pass
+            time.sleep(0.1)
+
+    def summary(self):
+        self.stop_flag = True
+        self.join(timeout=6)
+        if not self.rows:
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=['unsampled'])
+        sm = sorted(int(r[0]) for r in self.rows if r[0].isdigit())
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        reasons = [n for i, n in enumerate(names)
+                   if any(r[2 + i].lower().startswith('active') for r in self.rows)]
+        return dict(sm_mhz=sm[len(sm) // 2] if sm else None,
+                    sm_max_mhz=int(self.rows[0][1]) if self.rows[0][1].isdigit() else None,
+                    reasons=reasons, samples=len(self.rows))
+
+
+def cpu_oracle_rate(n_images, threads=None, grad=False):
+    """Times the oracle port on the host cores; returns (rays/s, seconds, outputs, inputs)."""
+    from nerf_from_image_b200 import synthetic
+    from oracle import render_oracle as O
+    threads = threads or os.cpu_count()
+    torch.set_num_threads(threads)
+    ds = synthetic.DATASET_CONFIGS[CFG['dataset']]
+    scene = synthetic.make_scene(1234, n_images, plane_res=CFG['plane_res'],
+                                 attention_values=CFG['attention_values'],
+                                 scene_range=ds['scene_range'],
+                                 white_background=ds['white_background'])
+    cams = synthetic.make_cameras(1234, n_images, radius=ds['radius'])
+    nt, nu = synthetic.make_noise(1234, n_images, CFG['height'], CFG['width'], CFG['samples'])
+    t0 = time.perf_counter()
+    with torch.no_grad():
+        out = O.render_oracle(scene['planes'], scene['w1'], scene['b1'], scene['w2'],
+                              scene['b2'], scene['palette'], scene['beta'], scene['alpha'],
+                              cams['c2w'], cams['focal'], None, None, CFG['height'],
+                              CFG['width'], CFG['samples'], nt, nu,
+                              scene_range=scene['scene_range'],
+                              white_background=scene['white_background'])
+    dt = time.perf_counter() - t0
+    rays = n_images * CFG['height'] * CFG['width']
+    return rays / dt, dt, out, (scene, cams, nt, nu)
+
+
+def run_reference(args):
+    """--impl reference: the CPU path of the reference (oracle port), bounded sample."""
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return
+    n_img = 1
+    threads = os.cpu_count()
+    for _ in range(args.warmup):
+        cpu_oracle_rate(n_img, threads)
+    times = []
+    for _ in range(args.steps):
+        _, dt, _, _ = cpu_oracle_rate(n_img, threads)
+        times.append(dt)
+    rays = n_img * CFG['height'] * CFG['width']
+    total = sum(times)
+    value = rays * len(times) / total
+    line = {
+        'impl': 'reference', 'metric': METRIC, 'value': value, 'unit': UNIT,
+        'n_gpus': args.gpus, 'steps': args.steps, 'warmup': args.warmup,
+        'ms_per_step': 1e3 * total / len(times), 'higher_is_better': True, 'scaling': 'weak',
+        'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+        'config': {'workload': 'p3d_car render 128x128, 64+64 samples/ray, 256^2 tri-planes '
+                               '(config 2 geometry), CPU sample of %d image(s) per step' % n_img},
+        'cpu_baseline': {'value': value, 'unit': UNIT, 'cores': threads, 'kind': 'port',
+                         'sample': '%d image(s) of the 32-image batch per step, torch CPU fp32, '
+                                   'no_grad' % n_img},
+        'e2e': {'value': value, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+        'gpu_launches': 0,
+    }
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=10)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
+    ap.add_argument('--batch', type=int, default=CFG['batch'])
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-e2e', action='store_true')
+    ap.add_argument('--e2e-steps', type=int, default=3)
+    ap.add_argument('--mlp-mode', type=int, default=0)
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == 'b200' else args.warmup
+    if args.impl == 'reference':
+        return run_reference(args)
+
+    import torch.distributed as dist
+    from nerf_from_image_b200 import _lib, fused, synthetic
+
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    rank = int(os.environ.get('RANK', '0'))
+    local_rank = int(os.environ.get('LOCAL_RANK', '0'))
+    if not torch.cuda.is_available():
+        raise SystemExit('bench.py needs a CUDA device: the fused renderer has no CPU path')
+    torch.cuda.set_device(local_rank)
+    dev = torch.device('cuda', local_rank)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=dev)
+    lib = _lib.load()
+
+    B, H, W, S = args.batch, CFG['height'], CFG['width'], CFG['samples']
+    ds = synthetic.DATASET_CONFIGS[CFG['dataset']]
+    # every rank renders its own 32 images (weak scaling; images are independent)
+    scene = synthetic.make_scene(1234 + rank, B, plane_res=CFG['plane_res'],
+                                 attention_values=CFG['attention_values'],
+                                 scene_range=ds['scene_range'],
+                                 white_background=ds['white_background'], device=dev)
+    cams = synthetic.make_cameras(1234 + rank, B, radius=ds['radius'], device=dev)
+    nt, nu = synthetic.make_noise(1234 + rank, B, H, W, S, device=dev)
+    cfg = fused.RenderConfig(scene_range=scene['scene_range'],
+                             white_background=scene['white_background'],
+                             attention_values=CFG['attention_values'], mlp_mode=args.mlp_mode)
+    gathered = [torch.empty(B, H, W, 5, device=dev) for _ in range(world)] if world > 1 else None
+
+    kernel_events = []
+
+    def step(time_kernel=False):
+        with torch.no_grad():
+            if time_kernel:
+                fused.KERNEL_EVENTS = kernel_events
+            rgb, depth, mask, _ = fused.fused_render(
+                scene['planes'], scene['w1'], scene['b1'], scene['w2'], scene['b2'],
+                scene['palette'], scene['beta'], scene['alpha'], cams['c2w'], cams['focal'],
+                None, None, cfg, H, W, S, nt, nu)
+            fused.KERNEL_EVENTS = None
+            if world > 1:
+                # the path's one exchange step: packed [rgb, depth, mask] tiles to every rank
+                packed = torch.cat((rgb, depth.unsqueeze(-1), mask.unsqueeze(-1)), dim=-1)
+                dist.all_gather(gathered, packed)
+        return rgb, depth, mask
+
+    for _ in range(args.warmup):
+        out = step()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    torch.cuda.synchronize()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for _ in range(args.steps):
+        out = step(time_kernel=True)
+    ev1.record()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    clocks = sampler.summary() if rank == 0 else None
+    ms_total = ev0.elapsed_time(ev1)
+    if world > 1:
+        t = torch.tensor([ms_total], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_total = t.item()
+    ms_step = ms_total / args.steps
+    rays_step = world * B * H * W
+    value = rays_step / (ms_step * 1e-3)
+    k_ms = sum(a.elapsed_time(b) for a, b in kernel_events) / max(1, len(kernel_events))
+
+    # ------------------------------------------------------------ e2e (host buffers)
+    e2e = None
+    if not args.no_e2e:
+        host = {}
+        pin = lambda t: t.detach().cpu().contiguous().pin_memory()
+        for k in ('planes', 'w1', 'b1', 'w2', 'b2', 'palette', 'beta', 'alpha'):
+            host[k] = pin(scene[k])
+        host['c2w'], host['focal'] = pin(cams['c2w']), pin(cams['focal'])
+        host['noise_t'], host['noise_u'] = pin(nt), pin(nu)
+        host['rgb'] = torch.empty(B, H, W, 3).pin_memory()
+        host['depth'] = torch.empty(B, H, W).pin_memory()
+        host['mask'] = torch.empty(B, H, W).pin_memory()
+        p = _lib.RenderParams()
+        p.batch, p.height, p.width, p.num_samples = B, H, W, S
+        p.plane_res, p.n_attention = CFG['plane_res'], CFG['attention_values']
+        p.scene_range = scene['scene_range']
+        p.white_background = int(scene['white_background'])
+        p.use_sdf, p.fine_sampling, p.noise_mode = 1, 1, _lib.NOISE_EXPLICIT
+        p.mlp_mode = args.mlp_mode
+        for k in ('planes', 'w1', 'b1', 'w2', 'b2', 'palette', 'beta', 'alpha', 'c2w', 'focal',
+                  'noise_t', 'noise_u', 'rgb', 'depth', 'mask'):
+            setattr(p, k, ctypes.c_void_p(host[k].data_ptr()))
+        h2d = sum(host[k].numel() * 4 for k in ('planes', 'w1', 'b1', 'w2', 'b2', 'palette',
+                                                  'beta', 'alpha', 'c2w', 'focal', 'noise_t',
+                                                  'noise_u'))
+        d2h = sum(host[k].numel() * 4 for k in ('rgb', 'depth', 'mask'))
+        _lib.check(lib.nfi_render_forward_host(ctypes.byref(p), local_rank))  # warm-up
+        if world > 1:
+            dist.barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.e2e_steps):
+            _lib.check(lib.nfi_render_forward_host(ctypes.byref(p), local_rank))
+        dt = (time.perf_counter() - t0) / args.e2e_steps
+        if world > 1:
+            t = torch.tensor([dt], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dt = t.item()
+        e2e_err = (host['rgb'] - out[0].cpu()).abs().max().item()
+        e2e = {'value': rays_step / dt, 'unit': UNIT, 'h2d_bytes_per_step': h2d,
+               'd2h_bytes_per_step': d2h, 'ms_per_step': dt * 1e3,
+               'max_abs_diff_vs_device_path': e2e_err,
+               'api': 'nfi_render_forward_host (C ABI, pinned host buffers)'}
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    pk = peaks()
+    flops_launch = float(B * H * W) * (2 * S) * FLOPS_PER_POINT
+    hbm_bytes_launch = float(B) * 3 * 32 * CFG['plane_res'] ** 2 * 4 + B * H * W * 20.0
+    achieved_tf = flops_launch / (k_ms * 1e-3) / 1e12 if k_ms > 0 else 0.0
+    roofline = {
+        'bound': 'tensor', 'achieved': achieved_tf, 'peak': pk['tflops'], 'unit': 'TFLOP/s',
+        'frac': achieved_tf / pk['tflops'], 'traffic': TRAFFIC_BYTES_PER_LAUNCH,
+        'kernel': 'render_forward (dominant kernel of the step)', 'kernel_ms': k_ms,
+        'kernel_share_of_step': k_ms / ms_step if ms_step > 0 else None,
+        'algorithmic_flops_per_launch': flops_launch,
+        'algorithmic_hbm_bytes_per_launch': hbm_bytes_launch,
+        'hbm_achieved_gbs': hbm_bytes_launch / (k_ms * 1e-3) / 1e9 if k_ms > 0 else 0.0,
+        'hbm_peak_gbs': pk['hbm_gbs'], 'peak_source': pk['source'],
+    }
+
+    cpu_baseline = None
+    parity = None
+    if world == 1 and not args.no_cpu_baseline:
+        n_img = 2
+        cores = os.cpu_count()
+        rate, dt, ref, (sc_c, cm_c, nt_c, nu_c) = cpu_oracle_rate(n_img, cores)
+        cpu_baseline = {'value': rate, 'unit': UNIT, 'cores': cores, 'kind': 'port',
+                        'sample': '%d of the 32 images (same geometry), %.1f s, torch CPU fp32 '
+                                  'no_grad' % (n_img, dt)}
+        # parity of the CUDA path on exactly those images
+        sc_g = {k: (v.to(dev) if torch.is_tensor(v) else v) for k, v in sc_c.items()}
+        with torch.no_grad():
+            rgb_g, dep_g, msk_g, _ = fused.fused_render(
+                sc_g['planes'], sc_g['w1'], sc_g['b1'], sc_g['w2'], sc_g['b2'], sc_g['palette'],
+                sc_g['beta'], sc_g['alpha'], cm_c['c2w'].to(dev), cm_c['focal'].to(dev), None,
+                None, cfg, H, W, S, nt_c.to(dev), nu_c.to(dev))
+        from oracle.render_oracle import psnr, rel_l2
+        parity = {'rgb_rel_l2': rel_l2(rgb_g.cpu(), ref['rgb']),
+                  'rgb_psnr_db': psnr(rgb_g.cpu(), ref['rgb']),
+                  'mask_rel_l2': rel_l2(msk_g.cpu(), ref['mask']),
+                  'depth_rel_l2': rel_l2(dep_g.cpu(), ref['depth']),
+                  'against': 'CPU oracle, identical injected noise, %d images' % n_img}
+
+    line = {
+        'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps,
+        'warmup': args.warmup, 'ms_per_step': ms_step, 'higher_is_better': True,
+        'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+        'config': {'workload': 'config 2: p3d_car render 128x128, 64 coarse + 64 fine '
+                               'samples/ray, batch %d per GPU, 256^2x32ch fp32 tri-planes given '
+                               '(channel-first) -> rgb/depth/mask' % B,
+                   'global_batch': world * B, 'parallelism': 'images sharded over %d GPU(s)'
+                   % world + (', all_gather of [rgb,depth,mask] tiles' if world > 1 else ''),
+                   'cache': 'inputs (1.07 GB per GPU) larger than L2; no flush needed',
+                   'randomize': True},
+        'clocks': clocks, 'e2e': e2e, 'gpu_launches': 2 * args.steps,
+        'roofline': roofline, 'cpu_baseline': cpu_baseline, 'parity': parity,
+    }
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+# dram__bytes_read.sum + dram__bytes_write.sum of the render kernel from the
+# committed `ncu --set full` capture (profiles/), per launch; None until captured.
+TRAFFIC_BYTES_PER_LAUNCH = None
+
+if __name__ == '__main__':
+    main()

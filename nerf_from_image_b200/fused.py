@@ -28,6 +28,11 @@ class RenderConfig:
     mlp_mode: int = _lib.MLP_AUTO
 
 
+# bench.py sets this to a list to collect (start, end) CUDA events around the
+# render kernel launch (events on the launching stream); None = no timing.
+KERNEL_EVENTS = None
+
+
 def _ptr(t):
     return ctypes.c_void_p(t.data_ptr()) if t is not None else None
 
@@ -171,7 +176,14 @@ class FusedTriplaneRender(torch.autograd.Function):
             ws_bytes = lib.nfi_render_workspace_bytes(ctypes.byref(p))
             ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
             p.workspace, p.workspace_bytes = _ptr(ws), ws_bytes
+            if KERNEL_EVENTS is not None:
+                e0 = torch.cuda.Event(enable_timing=True)
+                e1 = torch.cuda.Event(enable_timing=True)
+                e0.record()
             _lib.check(lib.nfi_render_forward(ctypes.byref(p), stream))
+            if KERNEL_EVENTS is not None:
+                e1.record()
+                KERNEL_EVENTS.append((e0, e1))
         if needs_grad:
             ctx.cfg, ctx.dims, ctx.extra_mode = cfg, (height, width, S), extra_mode
             ctx.cam_grad = cam_grad

