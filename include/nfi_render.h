@@ -163,6 +163,15 @@ NFI_API int nfi_planes_from_channel_last(const float *src, int32_t batch, int32_
  * samples, field, importance resampling, sorted merge, compositing). */
 NFI_API int nfi_render_forward(const nfi_render_params *params, void *stream);
 
+/* TriplanarDecoder.net on given features (models/generator.py:294-299,329-331):
+ * features [N,32] -> [N,1+A] (density-or-distance first, colour logits after).
+ * The tensor-core mode runs the same tiles / descriptors / epilogue as the
+ * render kernel; `workspace` must hold 32 KiB (ignored in SIMT mode). */
+NFI_API int nfi_decoder_forward(const float *features, int64_t n_points, const float *w1,
+                                const float *b1, const float *w2, const float *b2,
+                                int32_t n_attention, float *out, int32_t mlp_mode,
+                                void *workspace, void *stream);
+
 /* autograd of the above: recomputes the samples. */
 NFI_API int nfi_render_backward(const nfi_render_params *params, const nfi_render_grads *grads,
                         void *stream);

@@ -70,6 +70,10 @@ EXPORTS = {
         ctypes.c_void_p]),
     'nfi_render_forward': (ctypes.c_int, [ctypes.POINTER(RenderParams),
                                           ctypes.c_void_p]),
+    'nfi_decoder_forward': (ctypes.c_int, [
+        ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p, ctypes.c_void_p,
+        ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int32, ctypes.c_void_p,
+        ctypes.c_int32, ctypes.c_void_p, ctypes.c_void_p]),
     'nfi_render_backward': (ctypes.c_int, [ctypes.POINTER(RenderParams),
                                            ctypes.POINTER(RenderGrads),
                                            ctypes.c_void_p]),

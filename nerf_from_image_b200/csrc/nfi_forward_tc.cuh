@@ -1,0 +1,557 @@
+// Forward render kernel, tensor-core variant (NFI_MLP_TC_3XTF32).
+//
+// CTA = 512 threads = 4 independent "tile groups" of 128 threads; a group owns
+// one 16x8 pixel tile (thread = ray, exactly as in nfi_forward.cuh) and the four
+// groups of a CTA cover a 32x16 pixel block of one image.  One CTA per SM:
+// 16 resident warps, ~150 KB of shared memory, all 512 TMEM columns.
+//
+// Per sample step and group:
+//   1. every thread places its point and computes its 3x(offset, fx, fy) taps;
+//   2. the group's four warps gather features cooperatively (8 lanes x float4
+//      = one 128-byte channel-last texel per tap) and write them, split into
+//      TF32 hi/lo parts, straight into the group's A tiles in the UMMA
+//      SWIZZLE_128B K-major layout -- features never exist anywhere else;
+//   3. one thread issues 12 tcgen05.mma (3xTF32, M=128 N=64 K=32) into the
+//      group's 64 TMEM columns and commits to the group's mbarrier;
+//   4. every thread reads its own TMEM lane (tcgen05.ld), applies bias +
+//      softplus and runs layer 2 (64 -> 1+A) in exact fp32 with weights
+//      broadcast from shared memory, then density / softmax-palette colour /
+//      alpha compositing in registers.
+// Decoder weights arrive pre-split and pre-swizzled ("weight image", built by
+// prep_weight_image) through ONE TMA bulk copy per CTA.
+//
+// Hierarchical sampling (run.py:259-335): coarse (t, w, sigma, rgb) go to an
+// L2-resident scratch slab; the per-ray sort of the S uniforms and the
+// inverse-CDF walk use the group's (idle) A-tile memory as S x 128 columns;
+// the S sorted fine depths are then parked in the group's other 64 TMEM
+// columns, from where pass 2 reads them one column per step.
+#pragma once
+#include "nfi_common.cuh"
+#include "nfi_forward.cuh"
+#include "nfi_tc.cuh"
+
+namespace nfi {
+
+constexpr int kGroups = 4;
+constexpr int kTcThreads = kGroups * kThreads;  // 512
+constexpr int kW2Pad = 16;
+
+// weight image (bytes)
+constexpr int kWiW1Hi = 0;
+constexpr int kWiW1Lo = 8192;
+constexpr int kWiW2t = 16384;             // [64][16] fp32
+constexpr int kWiB1 = kWiW2t + 64 * kW2Pad * 4;   // 20480
+constexpr int kWiB2 = kWiB1 + 256;        // 20736
+constexpr int kWiBytes = kWiB2 + 64;      // 20800
+// shared memory map (bytes from the 1024-aligned base)
+constexpr int kSmA = 21504;               // 21 * 1024
+constexpr int kSmAGroup = 32768;          // A_hi (16 KB) + A_lo (16 KB)
+constexpr int kSmPal = kSmA + kGroups * kSmAGroup;  // 152576
+constexpr int kSmBars = kSmPal + 48 * 4;  // 5 mbarriers
+constexpr int kSmTmemPtr = kSmBars + 8 * 8;
+constexpr int kSmTcBytes = kSmTmemPtr + 16 + 1024;  // + alignment slack
+
+// scratch per group-tile: float4 srgb[S][128], float t[S][128], float w[S][128]
+__host__ __device__ inline size_t tc_scratch_floats_per_group(int S) {
+  return (size_t)S * kThreads * 6;
+}
+
+// Builds the weight image: W1 split into TF32 hi/lo and laid out as the UMMA
+// B operand ([64 rows = hidden unit][32 k] fp32, K-major, SWIZZLE_128B), W2
+// transposed/padded, biases.
+__global__ void prep_weight_image(const float* __restrict__ w1, const float* __restrict__ b1,
+                                  const float* __restrict__ w2, const float* __restrict__ b2,
+                                  int nout, unsigned char* __restrict__ img) {
+  for (int i = threadIdx.x; i < kHid * kC; i += blockDim.x) {
+    const int j = i / kC, k = i % kC;  // W1[j][k]
+    const float w = w1[i];
+    const float hi = tc::tf32_hi(w);
+    const uint32_t off = tc::sw128_offset(j, k >> 2) + (k & 3) * 4;
+    *reinterpret_cast<float*>(img + kWiW1Hi + off) = hi;
+    *reinterpret_cast<float*>(img + kWiW1Lo + off) = w - hi;
+  }
+  float* w2t = reinterpret_cast<float*>(img + kWiW2t);
+  for (int i = threadIdx.x; i < kHid * kW2Pad; i += blockDim.x) {
+    const int j = i / kW2Pad, o = i % kW2Pad;
+    w2t[i] = (o < nout) ? w2[o * kHid + j] : 0.f;
+  }
+  float* b1i = reinterpret_cast<float*>(img + kWiB1);
+  float* b2i = reinterpret_cast<float*>(img + kWiB2);
+  for (int i = threadIdx.x; i < kHid; i += blockDim.x) b1i[i] = b1[i];
+  for (int i = threadIdx.x; i < kW2Pad; i += blockDim.x) b2i[i] = (i < nout) ? b2[i] : 0.f;
+}
+
+struct PackedTaps {
+  uint32_t o[3];  // texel offset of the nw tap | dx << 30 | dy << 31
+  float fx[3], fy[3];
+};
+
+__device__ __forceinline__ void pack_taps(float gx, float gy, int R, uint32_t& o, float& fx,
+                                          float& fy) {
+  const float m = (float)(R - 1);
+  float ix = (gx + 1.f) * 0.5f * m;
+  float iy = (gy + 1.f) * 0.5f * m;
+  ix = fminf(m, fmaxf(ix, 0.f));
+  iy = fminf(m, fmaxf(iy, 0.f));
+  const float x0 = floorf(ix), y0 = floorf(iy);
+  fx = ix - x0;
+  fy = iy - y0;
+  const int xi = (int)x0, yi = (int)y0;
+  o = (uint32_t)(yi * R + xi) | ((xi + 1 < R) ? (1u << 30) : 0u) | ((yi + 1 < R) ? (1u << 31) : 0u);
+}
+
+__device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) {
+  return __ffma2_rn(a, b, c);
+}
+
+// interpolates one plane's 4 taps for this lane's 4 channels, accumulating into acc
+__device__ __forceinline__ void plane_taps_acc(const float4* __restrict__ plane, uint32_t o,
+                                               float fx, float fy, int R, float4& acc,
+                                               bool first) {
+  const uint32_t o00 = o & 0x3FFFFFFFu;
+  const uint32_t dx = (o >> 30) & 1u, dy = (o >> 31) ? (uint32_t)R : 0u;
+  const float gx0 = 1.f - fx, gy0 = 1.f - fy;
+  const float w00 = gx0 * gy0, w01 = fx * gy0, w10 = gx0 * fy, w11 = fx * fy;
+  const float4 a = ldg4(plane + (size_t)o00 * (kC / 4));
+  const float4 b = ldg4(plane + (size_t)(o00 + dx) * (kC / 4));
+  const float4 c = ldg4(plane + (size_t)(o00 + dy) * (kC / 4));
+  const float4 d = ldg4(plane + (size_t)(o00 + dy + dx) * (kC / 4));
+  float2 lo = first ? make_float2(0.f, 0.f) : make_float2(acc.x, acc.y);
+  float2 hi = first ? make_float2(0.f, 0.f) : make_float2(acc.z, acc.w);
+  lo = ffma2(make_float2(a.x, a.y), make_float2(w00, w00), lo);
+  hi = ffma2(make_float2(a.z, a.w), make_float2(w00, w00), hi);
+  lo = ffma2(make_float2(b.x, b.y), make_float2(w01, w01), lo);
+  hi = ffma2(make_float2(b.z, b.w), make_float2(w01, w01), hi);
+  lo = ffma2(make_float2(c.x, c.y), make_float2(w10, w10), lo);
+  hi = ffma2(make_float2(c.z, c.w), make_float2(w10, w10), hi);
+  lo = ffma2(make_float2(d.x, d.y), make_float2(w11, w11), lo);
+  hi = ffma2(make_float2(d.z, d.w), make_float2(w11, w11), hi);
+  acc = make_float4(lo.x, lo.y, hi.x, hi.y);
+}
+
+// Cooperative gather of this warp's 32 points into rows [row0, row0+32) of the
+// group's A_hi / A_lo tiles (byte pointers, SWIZZLE_128B layout).
+__device__ __forceinline__ void gather_to_tiles(const float* __restrict__ planes_b, int R,
+                                                const PackedTaps& tp, unsigned char* a_hi,
+                                                unsigned char* a_lo, int row0, int lane) {
+  const int q = lane >> 3, k = lane & 7;
+  const size_t plane_stride4 = (size_t)R * R * (kC / 4);
+  const float4* base = reinterpret_cast<const float4*>(planes_b) + k;
+#pragma unroll 2
+  for (int g = 0; g < 8; ++g) {
+    const int src = 4 * g + q;
+    float4 acc;
+#pragma unroll
+    for (int pl = 0; pl < 3; ++pl) {
+      const uint32_t o = __shfl_sync(kFull, tp.o[pl], src);
+      const float fx = __shfl_sync(kFull, tp.fx[pl], src);
+      const float fy = __shfl_sync(kFull, tp.fy[pl], src);
+      plane_taps_acc(base + pl * plane_stride4, o, fx, fy, R, acc, pl == 0);
+    }
+    const float third = 0.33333334f;  // mean of the three planes (generator.py:328)
+    const float4 f = make_float4(acc.x * third, acc.y * third, acc.z * third, acc.w * third);
+    const float4 fh = make_float4(tc::tf32_hi(f.x), tc::tf32_hi(f.y), tc::tf32_hi(f.z),
+                                  tc::tf32_hi(f.w));
+    const float4 fl = make_float4(f.x - fh.x, f.y - fh.y, f.z - fh.z, f.w - fh.w);
+    const uint32_t off = tc::sw128_offset(row0 + src, k);
+    *reinterpret_cast<float4*>(a_hi + off) = fh;
+    *reinterpret_cast<float4*>(a_lo + off) = fl;
+  }
+}
+
+// bias + softplus + layer 2 on this thread's TMEM lane (64 hidden units)
+template <int NOUT_PAD>
+__device__ __forceinline__ void tile_epilogue(uint32_t d_lane_addr, const float* __restrict__ b1s,
+                                              const float* __restrict__ w2t /*[64][16]*/,
+                                              const float* __restrict__ b2s,
+                                              float (&out)[NOUT_PAD]) {
+#pragma unroll
+  for (int o = 0; o < NOUT_PAD; ++o) out[o] = b2s[o];
+#pragma unroll 1
+  for (int c = 0; c < 4; ++c) {
+    float v[16];
+    tc::tmem_ld16(d_lane_addr + 16 * c, v);
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      const int j = 16 * c + i;
+      const float x = v[i] + b1s[j];
+      // softplus(x) = max(x,0) + ln2 * lg2(1 + 2^(-|x| log2 e))
+      const float e = exp2f(-fabsf(x) * 1.4426950408889634f);
+      const float a = fmaf(__log2f(1.f + e), 0.6931471805599453f, fmaxf(x, 0.f));
+      const float4* wr = reinterpret_cast<const float4*>(w2t + j * kW2Pad);
+#pragma unroll
+      for (int o4 = 0; o4 < NOUT_PAD / 4; ++o4) {
+        const float4 w = wr[o4];
+        out[4 * o4 + 0] = fmaf(w.x, a, out[4 * o4 + 0]);
+        out[4 * o4 + 1] = fmaf(w.y, a, out[4 * o4 + 1]);
+        out[4 * o4 + 2] = fmaf(w.z, a, out[4 * o4 + 2]);
+        out[4 * o4 + 3] = fmaf(w.w, a, out[4 * o4 + 3]);
+      }
+    }
+  }
+}
+
+struct TcShared {
+  unsigned char* base;   // 1024-aligned
+  const float* w2t;
+  const float* b1;
+  const float* b2;
+  float* pal;
+  uint64_t* bars;        // [0..3] group MMA barriers, [4] weights
+  uint32_t* tmem_ptr;
+};
+
+__device__ __forceinline__ TcShared tc_shared_map(unsigned char* raw) {
+  TcShared s;
+  s.base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(raw) + 1023) &
+                                            ~(uintptr_t)1023);
+  s.w2t = reinterpret_cast<const float*>(s.base + kWiW2t);
+  s.b1 = reinterpret_cast<const float*>(s.base + kWiB1);
+  s.b2 = reinterpret_cast<const float*>(s.base + kWiB2);
+  s.pal = reinterpret_cast<float*>(s.base + kSmPal);
+  s.bars = reinterpret_cast<uint64_t*>(s.base + kSmBars);
+  s.tmem_ptr = reinterpret_cast<uint32_t*>(s.base + kSmTmemPtr);
+  return s;
+}
+
+// common prologue: barriers, TMEM, weight image via TMA bulk copy
+__device__ __forceinline__ uint32_t tc_prologue(const TcShared& sm, const unsigned char* wimg,
+                                                int tid) {
+  if (tid == 0) {
+    for (int i = 0; i < kGroups; ++i) tc::mbar_init(&sm.bars[i], 1);
+    tc::mbar_init(&sm.bars[4], 1);
+    tc::fence_mbar_init();
+  }
+  if (tid < 32) tc::tmem_alloc(sm.tmem_ptr, 512);
+  tc::tc_fence_before();
+  __syncthreads();
+  tc::tc_fence_after();
+  const uint32_t tmem_base = *sm.tmem_ptr;
+  if (tid == 0) {
+    tc::mbar_expect_tx(&sm.bars[4], kWiBytes);
+    tc::tma_bulk_g2s(sm.base, wimg, kWiBytes, &sm.bars[4]);
+  }
+  tc::mbar_wait(&sm.bars[4], 0);
+  return tmem_base;
+}
+
+__device__ __forceinline__ void tc_epilogue_free(const TcShared& sm, uint32_t tmem_base, int tid) {
+  tc::tc_fence_before();
+  __syncthreads();
+  if (tid < 32) tc::tmem_dealloc(tmem_base, 512);
+}
+
+// ---------------------------------------------------------------------------
+// Stand-alone decoder: features [N,32] -> decoder outputs [N,nout]
+// (TriplanarDecoder.net, models/generator.py:294-299,329-331).  Same tiles,
+// descriptors, barriers and epilogue as the render kernel.
+// ---------------------------------------------------------------------------
+template <int NOUT_PAD>
+__global__ void __launch_bounds__(kTcThreads, 1)
+decoder_forward_tc(const float* __restrict__ feats, long long n_points, int nout,
+                   const unsigned char* __restrict__ wimg, float* __restrict__ outp) {
+  extern __shared__ unsigned char smem_raw[];
+  const TcShared sm = tc_shared_map(smem_raw);
+  const int tid = threadIdx.x, g = tid >> 7, gt = tid & 127, lane = tid & 31, wig = gt >> 5;
+  const uint32_t tmem_base = tc_prologue(sm, wimg, tid);
+  unsigned char* a_hi = sm.base + kSmA + g * kSmAGroup;
+  unsigned char* a_lo = a_hi + 16384;
+  const uint32_t d_tmem = tmem_base + g * 128;
+  const uint32_t d_lane = d_tmem + ((uint32_t)(32 * wig) << 16);
+  const long long n_tiles = (n_points + 127) / 128;
+  uint32_t phase = 0;
+  for (long long tile = (long long)blockIdx.x * kGroups + g; tile < n_tiles;
+       tile += (long long)gridDim.x * kGroups) {
+    // thread gt stages row gt: 8 chunks of 16 bytes
+    const long long row = tile * 128 + gt;
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+      float4 f = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (row < n_points) f = *reinterpret_cast<const float4*>(feats + row * kC + 4 * c);
+      const float4 fh = make_float4(tc::tf32_hi(f.x), tc::tf32_hi(f.y), tc::tf32_hi(f.z),
+                                    tc::tf32_hi(f.w));
+      const float4 fl = make_float4(f.x - fh.x, f.y - fh.y, f.z - fh.z, f.w - fh.w);
+      const uint32_t off = tc::sw128_offset(gt, c);
+      *reinterpret_cast<float4*>(a_hi + off) = fh;
+      *reinterpret_cast<float4*>(a_lo + off) = fl;
+    }
+    tc::fence_async_smem();
+    tc::tc_fence_before();
+    tc::bar_sync(1 + g, kThreads);
+    if (gt == 0) {
+      tc::tc_fence_after();
+      tc::issue_layer1(d_tmem, tc::smem_u32(a_hi), tc::smem_u32(a_lo),
+                       tc::smem_u32(sm.base + kWiW1Hi), tc::smem_u32(sm.base + kWiW1Lo));
+      tc::umma_commit(&sm.bars[g]);
+    }
+    tc::mbar_wait(&sm.bars[g], phase);
+    phase ^= 1;
+    tc::tc_fence_after();
+    float out[NOUT_PAD];
+    tile_epilogue<NOUT_PAD>(d_lane, sm.b1, sm.w2t, sm.b2, out);
+    if (row < n_points)
+      for (int o = 0; o < NOUT_PAD; ++o)
+        if (o < nout) outp[row * nout + o] = out[o];
+  }
+  tc_epilogue_free(sm, tmem_base, tid);
+}
+
+// ---------------------------------------------------------------------------
+// render, tensor-core variant.  EXTRA: 0 none, 1 coords.
+// ---------------------------------------------------------------------------
+template <int NOUT_PAD, int EXTRA, bool FINE>
+__global__ void __launch_bounds__(kTcThreads, 1)
+render_forward_tc(const nfi_render_params p, const unsigned char* __restrict__ wimg,
+                  float* __restrict__ scratch) {
+  constexpr int NE = (EXTRA == 1) ? 3 : 0;
+  extern __shared__ unsigned char smem_raw[];
+  const TcShared sm = tc_shared_map(smem_raw);
+  const int tid = threadIdx.x, g = tid >> 7, gt = tid & 127, lane = tid & 31, wig = gt >> 5;
+  const int S = p.num_samples;
+  const uint32_t tmem_base = tc_prologue(sm, wimg, tid);
+
+  // CTA -> 2x2 block of 16x8 tiles of one image
+  const int tiles_x = (p.width + kTileW - 1) / kTileW;
+  const int tiles_y = (p.height + kTileH - 1) / kTileH;
+  const int ctx_n = (tiles_x + 1) / 2, cty_n = (tiles_y + 1) / 2;
+  const int cta = blockIdx.x;
+  const int b = cta / (ctx_n * cty_n);
+  const int crem = cta % (ctx_n * cty_n);
+  const int tile_x = 2 * (crem % ctx_n) + (g & 1);
+  const int tile_y = 2 * (crem / ctx_n) + (g >> 1);
+  const bool group_active = (tile_x < tiles_x) && (tile_y < tiles_y);
+
+  if (tid < 48)
+    sm.pal[tid] = (p.n_attention > 0 && tid < p.n_attention * 3)
+                      ? p.palette[(size_t)b * p.n_attention * 3 + tid]
+                      : 0.f;
+  __syncthreads();
+
+  if (group_active) {
+    int px, py;
+    tile_pixel(tile_x, tile_y, wig, lane, px, py);
+    const bool valid = (px < p.width) && (py < p.height);
+    px = min(px, p.width - 1);
+    py = min(py, p.height - 1);
+    const size_t ray = ((size_t)b * p.height + py) * p.width + px;
+    Ray r;
+    setup_ray(p, b, py, px, r);
+    FieldConst fc;
+    fc.A = p.n_attention;
+    fc.use_sdf = p.use_sdf;
+    fc.inv_beta = p.use_sdf ? 1.f / p.beta[0] : 0.f;
+    fc.inv_alpha = p.use_sdf ? 1.f / p.alpha[0] : 0.f;
+    const float inv_range = 1.f / p.scene_range;
+    const int R = p.plane_res;
+    const float* planes_b = p.planes + (size_t)b * 3 * R * R * kC;
+    const bool explicit_noise = (p.noise_mode == NFI_NOISE_EXPLICIT);
+
+    unsigned char* a_hi = sm.base + kSmA + g * kSmAGroup;
+    unsigned char* a_lo = a_hi + 16384;
+    const uint32_t a_hi_s = tc::smem_u32(a_hi), a_lo_s = tc::smem_u32(a_lo);
+    const uint32_t w_hi_s = tc::smem_u32(sm.base + kWiW1Hi), w_lo_s = tc::smem_u32(sm.base + kWiW1Lo);
+    const uint32_t d_tmem = tmem_base + g * 128;
+    const uint32_t d_lane = d_tmem + ((uint32_t)(32 * wig) << 16);
+    const uint32_t zf_lane = d_lane + 64;
+    uint32_t phase = 0;
+
+    const size_t group_slot = (size_t)blockIdx.x * kGroups + g;
+    float* slab = scratch + group_slot * tc_scratch_floats_per_group(S);
+    float4* sc_srgb = reinterpret_cast<float4*>(slab);
+    float* sc_t = slab + (size_t)4 * S * kThreads;
+    float* sc_w = sc_t + (size_t)S * kThreads;
+
+    Compositor<NE> comp;
+    comp.init();
+
+    auto eval = [&](float t, float& sigma, float& cr, float& cg, float& cb, float* ex) {
+      const float wx = r.ox + r.dx * t, wy = r.oy + r.dy * t, wz = r.oz + r.dz * t;
+      const float x0 = wx * inv_range, x1 = wy * inv_range, x2 = wz * inv_range;
+      const float keep =
+          (fabsf(x0) > 1.f || fabsf(x1) > 1.f || fabsf(x2) > 1.f) ? 0.f : 1.f;
+      PackedTaps tp;
+      pack_taps(x0, x1, R, tp.o[0], tp.fx[0], tp.fy[0]);
+      pack_taps(x0, x2, R, tp.o[1], tp.fx[1], tp.fy[1]);
+      pack_taps(x1, x2, R, tp.o[2], tp.fx[2], tp.fy[2]);
+      gather_to_tiles(planes_b, R, tp, a_hi, a_lo, 32 * wig, lane);
+      tc::fence_async_smem();
+      tc::tc_fence_before();
+      tc::bar_sync(1 + g, kThreads);
+      if (gt == 0) {
+        tc::tc_fence_after();
+        tc::issue_layer1(d_tmem, a_hi_s, a_lo_s, w_hi_s, w_lo_s);
+        tc::umma_commit(&sm.bars[g]);
+      }
+      tc::mbar_wait(&sm.bars[g], phase);
+      phase ^= 1;
+      tc::tc_fence_after();
+      float out[NOUT_PAD];
+      tile_epilogue<NOUT_PAD>(d_lane, sm.b1, sm.w2t, sm.b2, out);
+      float probs[NOUT_PAD];
+      field_head<NOUT_PAD>(out, fc, sm.pal, keep, sigma, cr, cg, cb, probs);
+      if (EXTRA == 1) {
+        ex[0] = wx;
+        ex[1] = wy;
+        ex[2] = wz;
+      }
+    };
+
+    // ---------------- coarse pass ----------------
+    float wT = 1.f, prev_t = 0.f, prev_s = 0.f;
+    const float span = r.tfar - r.tnear;
+    for (int s = 0; s < S; ++s) {
+      float t = lerp_torch(r.tnear, r.tfar, (float)s / (float)S);
+      if (explicit_noise) t = t + p.noise_t[ray * S + s] * (span / (float)S);
+      float sigma, cr, cg, cb;
+      float ex[NE > 0 ? NE : 1];
+      eval(t, sigma, cr, cg, cb, ex);
+      if (FINE) {
+        sc_srgb[s * kThreads + gt] = make_float4(sigma, cr, cg, cb);
+        sc_t[s * kThreads + gt] = t;
+        if (s > 0) {
+          const float delta = (t - prev_t) * r.dn;
+          const float a = 1.f - expf(-prev_s * delta);
+          sc_w[(s - 1) * kThreads + gt] = a * wT;
+          wT = wT * ((1.f - a) + 1e-10f);
+        }
+        prev_t = t;
+        prev_s = sigma;
+      } else {
+        comp.push(t, sigma, cr, cg, cb, ex, r.dn);
+      }
+    }
+
+    if (FINE) {
+      sc_w[(S - 1) * kThreads + gt] = 0.f;
+      // the A tiles are idle until pass 2: use them as S x 128 float columns
+      float* col = reinterpret_cast<float*>(a_hi) + gt;
+      // smoothed pdf (run.py:266-272, lib/nerf_utils.py:189-192): first the sum
+      float sum = 0.f;
+      {
+        float wa = sc_w[gt], wb = sc_w[kThreads + gt], wc;
+        for (int m = 0; m + 2 < S; ++m) {
+          wc = sc_w[(m + 2) * kThreads + gt];
+          sum += ((fmaxf(wa, wb) + fmaxf(wb, wc)) * 0.5f + 0.01f) + 1e-5f;
+          wa = wb;
+          wb = wc;
+        }
+      }
+      // the S uniforms, ascending (thread-private column: bank = thread)
+      if (explicit_noise) {
+        for (int k = 0; k < S; ++k) {
+          const float u = p.noise_u[ray * S + k];
+          int i = k - 1;
+          while (i >= 0 && col[i * kThreads] > u) {
+            col[(i + 1) * kThreads] = col[i * kThreads];
+            --i;
+          }
+          col[(i + 1) * kThreads] = u;
+        }
+      } else {
+        for (int k = 0; k < S; ++k) col[k * kThreads] = linspace01(k, S);
+      }
+      // inverse CDF: walk the CDF bins once, consuming the sorted uniforms
+      {
+        int k = 0;
+        float c_prev = 0.f;
+        float wa = sc_w[gt], wb = sc_w[kThreads + gt], wc;
+        float t_lo = sc_t[gt], t_mid = sc_t[kThreads + gt];
+        float z0 = 0.5f * (t_mid + t_lo);  // bins[0]
+        for (int i = 1; i + 1 < S; ++i) {  // cdf[i], i = 1 .. S-2
+          wc = sc_w[(i + 1) * kThreads + gt];
+          const float pw = ((fmaxf(wa, wb) + fmaxf(wb, wc)) * 0.5f + 0.01f) + 1e-5f;
+          wa = wb;
+          wb = wc;
+          const float c_i = c_prev + pw / sum;
+          const float t_hi = sc_t[(i + 1) * kThreads + gt];
+          const float z1 = 0.5f * (t_hi + t_mid);  // bins[i]
+          float den = c_i - c_prev;
+          if (den < 1e-5f) den = 1.f;
+          while (k < S) {
+            const float u = col[k * kThreads];
+            if (!(u < c_i)) break;
+            col[k * kThreads] = z0 + (u - c_prev) / den * (z1 - z0);
+            ++k;
+          }
+          c_prev = c_i;
+          t_mid = t_hi;
+          z0 = z1;
+        }
+        while (k < S) {  // u >= cdf[S-2]: both neighbours are the last bin
+          col[k * kThreads] = z0;
+          ++k;
+        }
+      }
+      if (p.z_fine != nullptr && valid)
+        for (int k = 0; k < S; ++k) p.z_fine[ray * S + k] = col[k * kThreads];
+      __syncwarp();
+      // park the sorted fine depths in TMEM (columns 64.. of this group's lanes)
+      for (int c = 0; c < S / 16; ++c) {
+        float v[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) v[i] = col[(16 * c + i) * kThreads];
+        tc::tmem_st16(zf_lane + 16 * c, v);
+      }
+      tc::tmem_wait_st();
+      tc::tc_fence_before();
+      tc::bar_sync(1 + g, kThreads);  // columns are dead; A tiles may be rewritten
+      tc::tc_fence_after();
+
+      // ------- fine pass + sorted merge + compositing -------
+      int c = 0;
+      float ct = sc_t[gt];
+      for (int k = 0; k < S; ++k) {
+        uint32_t zr;
+        asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];"
+                     : "=r"(zr)
+                     : "r"(zf_lane + k)
+                     : "memory");
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        const float z = __uint_as_float(zr);
+        float sigma, cr, cg, cb;
+        float ex[NE > 0 ? NE : 1];
+        eval(z, sigma, cr, cg, cb, ex);
+        while (c < S && ct <= z) {
+          const float4 q = sc_srgb[c * kThreads + gt];
+          float ce[NE > 0 ? NE : 1];
+          if (EXTRA == 1) {
+            ce[0] = r.ox + r.dx * ct;
+            ce[1] = r.oy + r.dy * ct;
+            ce[2] = r.oz + r.dz * ct;
+          }
+          comp.push(ct, q.x, q.y, q.z, q.w, ce, r.dn);
+          ++c;
+          ct = (c < S) ? sc_t[c * kThreads + gt] : 0.f;
+        }
+        comp.push(z, sigma, cr, cg, cb, ex, r.dn);
+      }
+      while (c < S) {
+        const float4 q = sc_srgb[c * kThreads + gt];
+        float ce[NE > 0 ? NE : 1];
+        if (EXTRA == 1) {
+          ce[0] = r.ox + r.dx * ct;
+          ce[1] = r.oy + r.dy * ct;
+          ce[2] = r.oz + r.dz * ct;
+        }
+        comp.push(ct, q.x, q.y, q.z, q.w, ce, r.dn);
+        ++c;
+        ct = (c < S) ? sc_t[c * kThreads + gt] : 0.f;
+      }
+    }
+
+    if (valid) {
+      float bg = 0.f;
+      if (p.white_background) bg = 1.f - comp.am;
+      p.rgb[ray * 3 + 0] = comp.ar + bg;
+      p.rgb[ray * 3 + 1] = comp.ag + bg;
+      p.rgb[ray * 3 + 2] = comp.ab + bg;
+      p.depth[ray] = comp.ad;
+      p.mask[ray] = comp.am;
+      if (EXTRA == 1 && p.extra != nullptr)
+        for (int a = 0; a < 3; ++a) p.extra[ray * 3 + a] = comp.ae[a];
+    }
+  }
+  tc_epilogue_free(sm, tmem_base, tid);
+}
+
+}  // namespace nfi

@@ -9,6 +9,7 @@
 
 #include "nfi_backward.cuh"
 #include "nfi_forward.cuh"
+#include "nfi_forward_tc.cuh"
 #include "nfi_render.h"
 
 #define NFI_STR_(x) #x
@@ -72,6 +73,21 @@ size_t num_ctas(const nfi_render_params* p) {
   return tx * ty * (size_t)p->batch;
 }
 
+constexpr size_t kWeightImageBytes = 32768;  // workspace header (nfi::kWiBytes rounded up)
+
+size_t num_tc_ctas(const nfi_render_params* p) {
+  const size_t tx = (p->width + nfi::kTileW - 1) / nfi::kTileW;
+  const size_t ty = (p->height + nfi::kTileH - 1) / nfi::kTileH;
+  return ((tx + 1) / 2) * ((ty + 1) / 2) * (size_t)p->batch;
+}
+
+// Can the tensor-core kernel take this configuration?
+bool tc_supported(const nfi_render_params* p) {
+  if (p->extra_mode == NFI_EXTRA_SEMANTICS) return false;
+  if (p->fine_sampling && (p->num_samples % 16 != 0 || p->num_samples > 64)) return false;
+  return true;
+}
+
 int ne_store_of(const nfi_render_params* p) {
   return p->extra_mode == NFI_EXTRA_SEMANTICS ? nout_pad_of(p) - 1 : 0;
 }
@@ -100,6 +116,74 @@ int launch_fwd_extra(const nfi_render_params& p, size_t smem, cudaStream_t st) {
     case NFI_EXTRA_SEMANTICS: return launch_fwd_fine<NP, 2>(p, smem, st);
     default: return launch_fwd_fine<NP, 0>(p, smem, st);
   }
+}
+
+template <int NP, int EX>
+int launch_fwd_tc_fine(const nfi_render_params& p, const unsigned char* wimg, float* scratch,
+                       cudaStream_t st) {
+  const unsigned grid = (unsigned)num_tc_ctas(&p);
+  if (p.fine_sampling) {
+    auto k = nfi::render_forward_tc<NP, EX, true>;
+    NFI_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  nfi::kSmTcBytes));
+    k<<<grid, nfi::kTcThreads, nfi::kSmTcBytes, st>>>(p, wimg, scratch);
+  } else {
+    auto k = nfi::render_forward_tc<NP, EX, false>;
+    NFI_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  nfi::kSmTcBytes));
+    k<<<grid, nfi::kTcThreads, nfi::kSmTcBytes, st>>>(p, wimg, scratch);
+  }
+  NFI_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int launch_fwd_tc(const nfi_render_params& p, int np, cudaStream_t st) {
+  unsigned char* wimg = (unsigned char*)p.workspace;
+  float* scratch = (float*)(wimg + kWeightImageBytes);
+  const int nout = 1 + (p.n_attention > 0 ? p.n_attention : 3);
+  nfi::prep_weight_image<<<1, 256, 0, st>>>(p.w1, p.b1, p.w2, p.b2, nout, wimg);
+  NFI_CUDA(cudaGetLastError());
+  const bool coords = p.extra_mode == NFI_EXTRA_COORDS;
+  switch (np) {
+    case 4:
+      return coords ? launch_fwd_tc_fine<4, 1>(p, wimg, scratch, st)
+                    : launch_fwd_tc_fine<4, 0>(p, wimg, scratch, st);
+    case 12:
+      return coords ? launch_fwd_tc_fine<12, 1>(p, wimg, scratch, st)
+                    : launch_fwd_tc_fine<12, 0>(p, wimg, scratch, st);
+    default:
+      return coords ? launch_fwd_tc_fine<16, 1>(p, wimg, scratch, st)
+                    : launch_fwd_tc_fine<16, 0>(p, wimg, scratch, st);
+  }
+}
+
+// SIMT reference decoder (one point per thread), for nfi_decoder_forward
+template <int NOUT_PAD>
+__global__ void __launch_bounds__(128)
+decoder_forward_simt(const float* __restrict__ feats, long long n, int nout,
+                     const float* __restrict__ w1, const float* __restrict__ b1,
+                     const float* __restrict__ w2, const float* __restrict__ b2,
+                     float* __restrict__ outp) {
+  __shared__ __align__(16) float W1t[nfi::kC * nfi::kHid];
+  __shared__ __align__(16) float b1s[nfi::kHid];
+  __shared__ __align__(16) float W2t[nfi::kHid * NOUT_PAD];
+  __shared__ __align__(16) float b2s[NOUT_PAD];
+  for (int i = threadIdx.x; i < nfi::kC * nfi::kHid; i += 128)
+    W1t[i] = w1[(i % nfi::kHid) * nfi::kC + i / nfi::kHid];
+  for (int i = threadIdx.x; i < nfi::kHid; i += 128) b1s[i] = b1[i];
+  for (int i = threadIdx.x; i < nfi::kHid * NOUT_PAD; i += 128) {
+    const int j = i / NOUT_PAD, o = i % NOUT_PAD;
+    W2t[i] = (o < nout) ? w2[o * nfi::kHid + j] : 0.f;
+  }
+  for (int i = threadIdx.x; i < NOUT_PAD; i += 128) b2s[i] = (i < nout) ? b2[i] : 0.f;
+  __syncthreads();
+  const long long row = (long long)blockIdx.x * 128 + threadIdx.x;
+  if (row >= n) return;
+  float out[NOUT_PAD];
+  float h[nfi::kHid];
+  nfi::mlp_forward<NOUT_PAD, false>(feats + row * nfi::kC, W1t, b1s, W2t, b2s, out, h);
+  for (int o = 0; o < NOUT_PAD; ++o)
+    if (o < nout) outp[row * nout + o] = out[o];
 }
 
 // ---------------------------------------------------------------- re-layout
@@ -162,10 +246,14 @@ const char* nfi_last_error(void) { return g_err; }
 size_t nfi_render_workspace_bytes(const nfi_render_params* p) {
   if (p == nullptr) return 0;
   size_t fwd = 0;
-  if (p->fine_sampling)
+  if (p->fine_sampling) {
     fwd = num_ctas(p) * nfi::fwd_scratch_floats_per_cta(p->num_samples, ne_store_of(p)) *
           sizeof(float);
-  return fwd + 256;
+    const size_t tc = num_tc_ctas(p) * nfi::kGroups *
+                      nfi::tc_scratch_floats_per_group(p->num_samples) * sizeof(float);
+    if (tc > fwd) fwd = tc;
+  }
+  return kWeightImageBytes + fwd + 256;
 }
 
 int nfi_planes_to_channel_last(const float* xy, const float* xz, const float* yz,
@@ -192,18 +280,68 @@ int nfi_planes_from_channel_last(const float* src, int32_t batch, int32_t plane_
 int nfi_render_forward(const nfi_render_params* params, void* stream) {
   if (int rc = check_params(params)) return rc;
   const nfi_render_params& p = *params;
-  if (p.fine_sampling) {
+  const int np = nout_pad_of(params);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (p.mlp_mode == NFI_MLP_TC_3XTF32 && !tc_supported(params))
+    return fail("NFI_MLP_TC_3XTF32 needs S %% 16 == 0, S <= 64 with fine sampling, and no "
+                "semantics output; use NFI_MLP_AUTO");
+  const bool want_tc = p.mlp_mode == NFI_MLP_TC_3XTF32 ||
+                       (p.mlp_mode == NFI_MLP_AUTO && tc_supported(params));
+  if (want_tc || p.fine_sampling) {
     if (!p.workspace || p.workspace_bytes < nfi_render_workspace_bytes(params))
       return fail("workspace too small (see nfi_render_workspace_bytes)");
   }
-  const int np = nout_pad_of(params);
+  if (want_tc) return launch_fwd_tc(p, np, st);
   const size_t smem = nfi::fwd_smem_floats(np, p.num_samples, p.fine_sampling != 0) * sizeof(float);
-  cudaStream_t st = (cudaStream_t)stream;
+  nfi_render_params ps = p;  // SIMT scratch starts after the weight-image header
+  if (ps.workspace) ps.workspace = (unsigned char*)ps.workspace + kWeightImageBytes;
   switch (np) {
-    case 4: return launch_fwd_extra<4>(p, smem, st);
-    case 12: return launch_fwd_extra<12>(p, smem, st);
-    default: return launch_fwd_extra<16>(p, smem, st);
+    case 4: return launch_fwd_extra<4>(ps, smem, st);
+    case 12: return launch_fwd_extra<12>(ps, smem, st);
+    default: return launch_fwd_extra<16>(ps, smem, st);
   }
+}
+
+int nfi_decoder_forward(const float* features, int64_t n_points, const float* w1, const float* b1,
+                        const float* w2, const float* b2, int32_t n_attention, float* out,
+                        int32_t mlp_mode, void* workspace, void* stream) {
+  if (!features || !w1 || !b1 || !w2 || !b2 || !out || n_points <= 0)
+    return fail("bad decoder arguments");
+  if (n_attention < 0 || n_attention > NFI_MAX_ATTENTION) return fail("attention_values out of range");
+  const int nout = 1 + (n_attention > 0 ? n_attention : 3);
+  const int np = nout <= 4 ? 4 : (nout <= 12 ? 12 : 16);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (mlp_mode == NFI_MLP_FP32_SIMT) {
+    const unsigned grid = (unsigned)((n_points + 127) / 128);
+    if (np == 4) decoder_forward_simt<4><<<grid, 128, 0, st>>>(features, n_points, nout, w1, b1, w2, b2, out);
+    else if (np == 12) decoder_forward_simt<12><<<grid, 128, 0, st>>>(features, n_points, nout, w1, b1, w2, b2, out);
+    else decoder_forward_simt<16><<<grid, 128, 0, st>>>(features, n_points, nout, w1, b1, w2, b2, out);
+    NFI_CUDA(cudaGetLastError());
+    return 0;
+  }
+  if (!workspace) return fail("decoder (tensor-core mode) needs a 32 KiB workspace");
+  unsigned char* wimg = (unsigned char*)workspace;
+  nfi::prep_weight_image<<<1, 256, 0, st>>>(w1, b1, w2, b2, nout, wimg);
+  NFI_CUDA(cudaGetLastError());
+  const long long tiles = (n_points + 127) / 128;
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const unsigned grid = (unsigned)((tiles + nfi::kGroups - 1) / nfi::kGroups < sms
+                                       ? (tiles + nfi::kGroups - 1) / nfi::kGroups
+                                       : sms);
+#define NFI_DEC(NP)                                                                          \
+  do {                                                                                       \
+    NFI_CUDA(cudaFuncSetAttribute(nfi::decoder_forward_tc<NP>,                               \
+                                  cudaFuncAttributeMaxDynamicSharedMemorySize,               \
+                                  nfi::kSmTcBytes));                                         \
+    nfi::decoder_forward_tc<NP><<<grid, nfi::kTcThreads, nfi::kSmTcBytes, st>>>(             \
+        features, n_points, nout, wimg, out);                                                \
+  } while (0)
+  if (np == 4) NFI_DEC(4); else if (np == 12) NFI_DEC(12); else NFI_DEC(16);
+#undef NFI_DEC
+  NFI_CUDA(cudaGetLastError());
+  return 0;
 }
 
 int nfi_render_backward(const nfi_render_params* params, const nfi_render_grads* grads,

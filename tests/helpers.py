@@ -39,14 +39,18 @@ def run_oracle(scene, cams, H, W, S, noise_t, noise_u, **kw):
                            white_background=scene['white_background'], **kw)
 
 
+MLP_MODE = 0  # tests/test_parity_gpu.py switches this (0 auto, 1 SIMT, 2 tensor core)
+
+
 def run_cuda(scene, cams, H, W, S, noise_t, noise_u, use_sdf=True, fine_sampling=True,
-             extra_mode=0, cam_grad=True, device='cuda'):
+             extra_mode=0, cam_grad=True, device='cuda', mlp_mode=None):
     from nerf_from_image_b200.fused import RenderConfig, fused_render
     sc = to_device(scene, device)
     cm = to_device(cams, device)
     A = sc['palette'].shape[1] if sc['palette'] is not None else 0
     cfg = RenderConfig(scene_range=sc['scene_range'], white_background=sc['white_background'],
-                       use_sdf=use_sdf, fine_sampling=fine_sampling, attention_values=A)
+                       use_sdf=use_sdf, fine_sampling=fine_sampling, attention_values=A,
+                       mlp_mode=MLP_MODE if mlp_mode is None else mlp_mode)
     nt = noise_t.to(device) if noise_t is not None else None
     nu = noise_u.to(device) if noise_u is not None else None
     return fused_render(sc['planes'], sc['w1'], sc['b1'], sc['w2'], sc['b2'], sc['palette'],
