@@ -12,19 +12,21 @@
 //      TF32 hi/lo parts, straight into the group's A tiles in the UMMA
 //      SWIZZLE_128B K-major layout -- features never exist anywhere else;
 //   3. one thread issues 12 tcgen05.mma (3xTF32, M=128 N=64 K=32) into the
-//      group's 64 TMEM columns and commits to the group's mbarrier;
+//      group's first 64 TMEM columns and commits to the group's mbarrier;
 //   4. every thread reads its own TMEM lane (tcgen05.ld), applies bias +
-//      softplus and runs layer 2 (64 -> 1+A) in exact fp32 with weights
-//      broadcast from shared memory, then density / softmax-palette colour /
-//      alpha compositing in registers.
+//      softplus, and hands the hidden activations back to the tensor core split
+//      as H_hi (shared memory, in the space of the now idle A tiles) and H_lo
+//      (tcgen05.st over the D1 columns it just read);
+//   5. 24 more tcgen05.mma (N=16, K=64; H_lo read from TMEM, H_hi from shared
+//      memory) produce the 1+A decoder outputs in 16 further TMEM columns;
+//   6. density / softmax-palette colour / alpha compositing in registers.
 // Decoder weights arrive pre-split and pre-swizzled ("weight image", built by
 // prep_weight_image) through ONE TMA bulk copy per CTA.
 //
 // Hierarchical sampling (run.py:259-335): coarse (t, w, sigma, rgb) go to an
 // L2-resident scratch slab; the per-ray sort of the S uniforms and the
 // inverse-CDF walk use the group's (idle) A-tile memory as S x 128 columns;
-// the S sorted fine depths are then parked in the group's other 64 TMEM
-// columns, from where pass 2 reads them one column per step.
+// the S sorted fine depths then join the coarse samples in the slab.
 #pragma once
 #include "nfi_common.cuh"
 #include "nfi_forward.cuh"
@@ -37,23 +39,25 @@ constexpr int kTcThreads = kGroups * kThreads;  // 512
 constexpr int kW2Pad = 16;
 
 // weight image (bytes)
-constexpr int kWiW1Hi = 0;
+constexpr int kWiW1Hi = 0;                 // [64 x 32] SW128, 8 KB
 constexpr int kWiW1Lo = 8192;
-constexpr int kWiW2t = 16384;             // [64][16] fp32
-constexpr int kWiB1 = kWiW2t + 64 * kW2Pad * 4;   // 20480
-constexpr int kWiB2 = kWiB1 + 256;        // 20736
-constexpr int kWiBytes = kWiB2 + 64;      // 20800
+constexpr int kWiW2Hi = 16384;             // [16 x 64] as two [16 x 32] SW128 K-blocks, 4 KB
+constexpr int kWiW2Lo = 20480;
+constexpr int kWiB1 = 24576;               // 64 floats
+constexpr int kWiB2 = kWiB1 + 256;         // 16 floats
+constexpr int kWiBytes = kWiB2 + 64;       // 24896
 // shared memory map (bytes from the 1024-aligned base)
-constexpr int kSmA = 21504;               // 21 * 1024
-constexpr int kSmAGroup = 32768;          // A_hi (16 KB) + A_lo (16 KB)
-constexpr int kSmPal = kSmA + kGroups * kSmAGroup;  // 152576
-constexpr int kSmBars = kSmPal + 48 * 4;  // 5 mbarriers
+constexpr int kSmA = 25600;                // 25 * 1024
+constexpr int kSmAGroup = 32768;           // A_hi (16 KB) + A_lo (16 KB); later H_hi k-blocks 0/1
+constexpr int kSmPal = kSmA + kGroups * kSmAGroup;
+constexpr int kSmBars = kSmPal + 48 * 4;   // 5 mbarriers
 constexpr int kSmTmemPtr = kSmBars + 8 * 8;
-constexpr int kSmTcBytes = kSmTmemPtr + 16 + 1024;  // + alignment slack
+constexpr int kSmTcBytes = kSmTmemPtr + 16;
+// TMEM columns of group g: [128 g, +64) D1 then H_lo, [128 g + 64, +16) D2
 
-// scratch per group-tile: float4 srgb[S][128], float t[S][128], float w[S][128]
+// scratch per group-tile: float4 srgb[S][128], float t[S][128], w[S][128], zf[S][128]
 __host__ __device__ inline size_t tc_scratch_floats_per_group(int S) {
-  return (size_t)S * kThreads * 6;
+  return (size_t)S * kThreads * 7;
 }
 
 // Builds the weight image: W1 split into TF32 hi/lo and laid out as the UMMA
@@ -70,10 +74,13 @@ __global__ void prep_weight_image(const float* __restrict__ w1, const float* __r
     *reinterpret_cast<float*>(img + kWiW1Hi + off) = hi;
     *reinterpret_cast<float*>(img + kWiW1Lo + off) = w - hi;
   }
-  float* w2t = reinterpret_cast<float*>(img + kWiW2t);
-  for (int i = threadIdx.x; i < kHid * kW2Pad; i += blockDim.x) {
-    const int j = i / kW2Pad, o = i % kW2Pad;
-    w2t[i] = (o < nout) ? w2[o * kHid + j] : 0.f;
+  for (int i = threadIdx.x; i < kW2Pad * kHid; i += blockDim.x) {
+    const int o = i / kHid, j = i % kHid;  // W2[o][j], rows >= nout are zero
+    const float w = (o < nout) ? w2[o * kHid + j] : 0.f;
+    const float hi = tc::tf32_hi(w);
+    const uint32_t off = (j >> 5) * 2048 + tc::sw128_offset(o, (j & 31) >> 2) + (j & 3) * 4;
+    *reinterpret_cast<float*>(img + kWiW2Hi + off) = hi;
+    *reinterpret_cast<float*>(img + kWiW2Lo + off) = w - hi;
   }
   float* b1i = reinterpret_cast<float*>(img + kWiB1);
   float* b2i = reinterpret_cast<float*>(img + kWiB2);
@@ -159,41 +166,8 @@ __device__ __forceinline__ void gather_to_tiles(const float* __restrict__ planes
   }
 }
 
-// bias + softplus + layer 2 on this thread's TMEM lane (64 hidden units)
-template <int NOUT_PAD>
-__device__ __forceinline__ void tile_epilogue(uint32_t d_lane_addr, const float* __restrict__ b1s,
-                                              const float* __restrict__ w2t /*[64][16]*/,
-                                              const float* __restrict__ b2s,
-                                              float (&out)[NOUT_PAD]) {
-#pragma unroll
-  for (int o = 0; o < NOUT_PAD; ++o) out[o] = b2s[o];
-#pragma unroll 1
-  for (int c = 0; c < 4; ++c) {
-    float v[16];
-    tc::tmem_ld16(d_lane_addr + 16 * c, v);
-#pragma unroll
-    for (int i = 0; i < 16; ++i) {
-      const int j = 16 * c + i;
-      const float x = v[i] + b1s[j];
-      // softplus(x) = max(x,0) + ln2 * lg2(1 + 2^(-|x| log2 e))
-      const float e = exp2f(-fabsf(x) * 1.4426950408889634f);
-      const float a = fmaf(__log2f(1.f + e), 0.6931471805599453f, fmaxf(x, 0.f));
-      const float4* wr = reinterpret_cast<const float4*>(w2t + j * kW2Pad);
-#pragma unroll
-      for (int o4 = 0; o4 < NOUT_PAD / 4; ++o4) {
-        const float4 w = wr[o4];
-        out[4 * o4 + 0] = fmaf(w.x, a, out[4 * o4 + 0]);
-        out[4 * o4 + 1] = fmaf(w.y, a, out[4 * o4 + 1]);
-        out[4 * o4 + 2] = fmaf(w.z, a, out[4 * o4 + 2]);
-        out[4 * o4 + 3] = fmaf(w.w, a, out[4 * o4 + 3]);
-      }
-    }
-  }
-}
-
 struct TcShared {
   unsigned char* base;   // 1024-aligned
-  const float* w2t;
   const float* b1;
   const float* b2;
   float* pal;
@@ -203,21 +177,114 @@ struct TcShared {
 
 __device__ __forceinline__ TcShared tc_shared_map(unsigned char* raw) {
   TcShared s;
-  s.base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(raw) + 1023) &
-                                            ~(uintptr_t)1023);
-  s.w2t = reinterpret_cast<const float*>(s.base + kWiW2t);
-  s.b1 = reinterpret_cast<const float*>(s.base + kWiB1);
-  s.b2 = reinterpret_cast<const float*>(s.base + kWiB2);
-  s.pal = reinterpret_cast<float*>(s.base + kSmPal);
-  s.bars = reinterpret_cast<uint64_t*>(s.base + kSmBars);
-  s.tmem_ptr = reinterpret_cast<uint32_t*>(s.base + kSmTmemPtr);
+  s.base = raw;  // declared __align__(1024); checked in tc_prologue
+  s.b1 = reinterpret_cast<const float*>(raw + kWiB1);
+  s.b2 = reinterpret_cast<const float*>(raw + kWiB2);
+  s.pal = reinterpret_cast<float*>(raw + kSmPal);
+  s.bars = reinterpret_cast<uint64_t*>(raw + kSmBars);
+  s.tmem_ptr = reinterpret_cast<uint32_t*>(raw + kSmTmemPtr);
   return s;
+}
+
+// per-thread view of its tile group
+struct TcGroup {
+  int g, gt, wig;
+  unsigned char* a_hi;   // A_hi tile  / H_hi k-block 0
+  unsigned char* a_lo;   // A_lo tile  / H_hi k-block 1
+  uint32_t a_hi_s, a_lo_s, w1_hi_s, w1_lo_s, w2_hi_s, w2_lo_s;
+  uint32_t d_tmem;       // group's first TMEM column, lane 0
+  uint32_t d_lane;       // same, this warp's lane quadrant
+  uint64_t* bar;
+};
+
+__device__ __forceinline__ TcGroup tc_group(const TcShared& sm, uint32_t tmem_base, int tid) {
+  TcGroup q;
+  q.g = tid >> 7;
+  q.gt = tid & 127;
+  q.wig = q.gt >> 5;
+  q.a_hi = sm.base + kSmA + q.g * kSmAGroup;
+  q.a_lo = q.a_hi + 16384;
+  q.a_hi_s = tc::smem_u32(q.a_hi);
+  q.a_lo_s = q.a_hi_s + 16384;
+  const uint32_t base_s = tc::smem_u32(sm.base);
+  q.w1_hi_s = base_s + kWiW1Hi;
+  q.w1_lo_s = base_s + kWiW1Lo;
+  q.w2_hi_s = base_s + kWiW2Hi;
+  q.w2_lo_s = base_s + kWiW2Lo;
+  q.d_tmem = tmem_base + q.g * 128;
+  q.d_lane = q.d_tmem + ((uint32_t)(32 * q.wig) << 16);
+  q.bar = &sm.bars[q.g];
+  return q;
+}
+
+// The decoder on one 128-point tile whose features already sit (hi/lo split)
+// in the group's A tiles.  Both linear layers run on the tensor core:
+//   MMA batch 1: D1 = A * W1^T                       (12 x tcgen05.mma, N = 64)
+//   epilogue 1 : h = softplus(D1 + b1); H_hi -> shared memory (re-using the A
+//                tiles as two K-blocks), H_lo -> TMEM in place of D1
+//   MMA batch 2: D2 = H * W2^T                       (24 x tcgen05.mma, N = 16)
+//   epilogue 2 : out = D2 + b2
+template <int NOUT_PAD>
+__device__ __forceinline__ void tile_mlp(const TcGroup& q, const TcShared& sm, uint32_t& phase,
+                                         float (&out)[NOUT_PAD]) {
+  tc::fence_async_smem();
+  tc::tc_fence_before();
+  tc::bar_sync(1 + q.g, kThreads);
+  if (q.gt == 0) {
+    tc::tc_fence_after();
+    tc::issue_layer1(q.d_tmem, q.a_hi_s, q.a_lo_s, q.w1_hi_s, q.w1_lo_s);
+    tc::umma_commit(q.bar);
+  }
+  tc::mbar_wait(q.bar, phase);
+  phase ^= 1;
+  tc::tc_fence_after();
+#pragma unroll 1
+  for (int c = 0; c < 4; ++c) {
+    float v[16];
+    tc::tmem_ld16(q.d_lane + 16 * c, v);
+    unsigned char* hrow = (c < 2) ? q.a_hi : q.a_lo;
+#pragma unroll
+    for (int i4 = 0; i4 < 4; ++i4) {
+      const float4 bb = *reinterpret_cast<const float4*>(sm.b1 + 16 * c + 4 * i4);
+      const float bv[4] = {bb.x, bb.y, bb.z, bb.w};
+      float hi[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float x = v[4 * i4 + i] + bv[i];
+        // softplus(x) = max(x,0) + ln2 * lg2(1 + 2^(-|x| log2 e))   (MUFU ex2 + lg2)
+        const float e = tc::ex2_approx(-fabsf(x) * 1.4426950408889634f);
+        const float h = fmaf(tc::lg2_approx(1.f + e), 0.6931471805599453f, fmaxf(x, 0.f));
+        hi[i] = tc::tf32_hi(h);
+        v[4 * i4 + i] = h - hi[i];
+      }
+      const uint32_t off = tc::sw128_offset(q.gt, (c & 1) * 4 + i4);
+      *reinterpret_cast<float4*>(hrow + off) = make_float4(hi[0], hi[1], hi[2], hi[3]);
+    }
+    tc::tmem_st16(q.d_lane + 16 * c, v);  // H_lo over the D1 columns just read
+  }
+  tc::tmem_wait_st();
+  tc::fence_async_smem();
+  tc::tc_fence_before();
+  tc::bar_sync(1 + q.g, kThreads);
+  if (q.gt == 0) {
+    tc::tc_fence_after();
+    tc::issue_layer2(q.d_tmem + 64, q.d_tmem, q.a_hi_s, q.a_lo_s, q.w2_hi_s, q.w2_lo_s);
+    tc::umma_commit(q.bar);
+  }
+  tc::mbar_wait(q.bar, phase);
+  phase ^= 1;
+  tc::tc_fence_after();
+  float v[16];
+  tc::tmem_ld16(q.d_lane + 64, v);
+#pragma unroll
+  for (int o = 0; o < NOUT_PAD; ++o) out[o] = v[o] + sm.b2[o];
 }
 
 // common prologue: barriers, TMEM, weight image via TMA bulk copy
 __device__ __forceinline__ uint32_t tc_prologue(const TcShared& sm, const unsigned char* wimg,
                                                 int tid) {
   if (tid == 0) {
+    if (tc::smem_u32(sm.base) & 1023u) __trap();  // SWIZZLE_128B tiles need 1024-byte alignment
     for (int i = 0; i < kGroups; ++i) tc::mbar_init(&sm.bars[i], 1);
     tc::mbar_init(&sm.bars[4], 1);
     tc::fence_mbar_init();
@@ -250,20 +317,16 @@ template <int NOUT_PAD>
 __global__ void __launch_bounds__(kTcThreads, 1)
 decoder_forward_tc(const float* __restrict__ feats, long long n_points, int nout,
                    const unsigned char* __restrict__ wimg, float* __restrict__ outp) {
-  extern __shared__ unsigned char smem_raw[];
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
   const TcShared sm = tc_shared_map(smem_raw);
-  const int tid = threadIdx.x, g = tid >> 7, gt = tid & 127, lane = tid & 31, wig = gt >> 5;
+  const int tid = threadIdx.x;
   const uint32_t tmem_base = tc_prologue(sm, wimg, tid);
-  unsigned char* a_hi = sm.base + kSmA + g * kSmAGroup;
-  unsigned char* a_lo = a_hi + 16384;
-  const uint32_t d_tmem = tmem_base + g * 128;
-  const uint32_t d_lane = d_tmem + ((uint32_t)(32 * wig) << 16);
+  const TcGroup q = tc_group(sm, tmem_base, tid);
   const long long n_tiles = (n_points + 127) / 128;
   uint32_t phase = 0;
-  for (long long tile = (long long)blockIdx.x * kGroups + g; tile < n_tiles;
+  for (long long tile = (long long)blockIdx.x * kGroups + q.g; tile < n_tiles;
        tile += (long long)gridDim.x * kGroups) {
-    // thread gt stages row gt: 8 chunks of 16 bytes
-    const long long row = tile * 128 + gt;
+    const long long row = tile * 128 + q.gt;  // thread gt stages row gt: 8 x 16 bytes
 #pragma unroll
     for (int c = 0; c < 8; ++c) {
       float4 f = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -271,24 +334,12 @@ decoder_forward_tc(const float* __restrict__ feats, long long n_points, int nout
       const float4 fh = make_float4(tc::tf32_hi(f.x), tc::tf32_hi(f.y), tc::tf32_hi(f.z),
                                     tc::tf32_hi(f.w));
       const float4 fl = make_float4(f.x - fh.x, f.y - fh.y, f.z - fh.z, f.w - fh.w);
-      const uint32_t off = tc::sw128_offset(gt, c);
-      *reinterpret_cast<float4*>(a_hi + off) = fh;
-      *reinterpret_cast<float4*>(a_lo + off) = fl;
+      const uint32_t off = tc::sw128_offset(q.gt, c);
+      *reinterpret_cast<float4*>(q.a_hi + off) = fh;
+      *reinterpret_cast<float4*>(q.a_lo + off) = fl;
     }
-    tc::fence_async_smem();
-    tc::tc_fence_before();
-    tc::bar_sync(1 + g, kThreads);
-    if (gt == 0) {
-      tc::tc_fence_after();
-      tc::issue_layer1(d_tmem, tc::smem_u32(a_hi), tc::smem_u32(a_lo),
-                       tc::smem_u32(sm.base + kWiW1Hi), tc::smem_u32(sm.base + kWiW1Lo));
-      tc::umma_commit(&sm.bars[g]);
-    }
-    tc::mbar_wait(&sm.bars[g], phase);
-    phase ^= 1;
-    tc::tc_fence_after();
     float out[NOUT_PAD];
-    tile_epilogue<NOUT_PAD>(d_lane, sm.b1, sm.w2t, sm.b2, out);
+    tile_mlp<NOUT_PAD>(q, sm, phase, out);
     if (row < n_points)
       for (int o = 0; o < NOUT_PAD; ++o)
         if (o < nout) outp[row * nout + o] = out[o];
@@ -304,11 +355,13 @@ __global__ void __launch_bounds__(kTcThreads, 1)
 render_forward_tc(const nfi_render_params p, const unsigned char* __restrict__ wimg,
                   float* __restrict__ scratch) {
   constexpr int NE = (EXTRA == 1) ? 3 : 0;
-  extern __shared__ unsigned char smem_raw[];
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
   const TcShared sm = tc_shared_map(smem_raw);
-  const int tid = threadIdx.x, g = tid >> 7, gt = tid & 127, lane = tid & 31, wig = gt >> 5;
+  const int tid = threadIdx.x, lane = tid & 31;
   const int S = p.num_samples;
   const uint32_t tmem_base = tc_prologue(sm, wimg, tid);
+  const TcGroup q = tc_group(sm, tmem_base, tid);
+  const int g = q.g, gt = q.gt, wig = q.wig;
 
   // CTA -> 2x2 block of 16x8 tiles of one image
   const int tiles_x = (p.width + kTileW - 1) / kTileW;
@@ -346,13 +399,8 @@ render_forward_tc(const nfi_render_params p, const unsigned char* __restrict__ w
     const float* planes_b = p.planes + (size_t)b * 3 * R * R * kC;
     const bool explicit_noise = (p.noise_mode == NFI_NOISE_EXPLICIT);
 
-    unsigned char* a_hi = sm.base + kSmA + g * kSmAGroup;
-    unsigned char* a_lo = a_hi + 16384;
-    const uint32_t a_hi_s = tc::smem_u32(a_hi), a_lo_s = tc::smem_u32(a_lo);
-    const uint32_t w_hi_s = tc::smem_u32(sm.base + kWiW1Hi), w_lo_s = tc::smem_u32(sm.base + kWiW1Lo);
-    const uint32_t d_tmem = tmem_base + g * 128;
-    const uint32_t d_lane = d_tmem + ((uint32_t)(32 * wig) << 16);
-    const uint32_t zf_lane = d_lane + 64;
+    unsigned char* a_hi = q.a_hi;
+    unsigned char* a_lo = q.a_lo;
     uint32_t phase = 0;
 
     const size_t group_slot = (size_t)blockIdx.x * kGroups + g;
@@ -360,6 +408,7 @@ render_forward_tc(const nfi_render_params p, const unsigned char* __restrict__ w
     float4* sc_srgb = reinterpret_cast<float4*>(slab);
     float* sc_t = slab + (size_t)4 * S * kThreads;
     float* sc_w = sc_t + (size_t)S * kThreads;
+    float* sc_zf = sc_w + (size_t)S * kThreads;
 
     Compositor<NE> comp;
     comp.init();
@@ -374,19 +423,8 @@ render_forward_tc(const nfi_render_params p, const unsigned char* __restrict__ w
       pack_taps(x0, x2, R, tp.o[1], tp.fx[1], tp.fy[1]);
       pack_taps(x1, x2, R, tp.o[2], tp.fx[2], tp.fy[2]);
       gather_to_tiles(planes_b, R, tp, a_hi, a_lo, 32 * wig, lane);
-      tc::fence_async_smem();
-      tc::tc_fence_before();
-      tc::bar_sync(1 + g, kThreads);
-      if (gt == 0) {
-        tc::tc_fence_after();
-        tc::issue_layer1(d_tmem, a_hi_s, a_lo_s, w_hi_s, w_lo_s);
-        tc::umma_commit(&sm.bars[g]);
-      }
-      tc::mbar_wait(&sm.bars[g], phase);
-      phase ^= 1;
-      tc::tc_fence_after();
       float out[NOUT_PAD];
-      tile_epilogue<NOUT_PAD>(d_lane, sm.b1, sm.w2t, sm.b2, out);
+      tile_mlp<NOUT_PAD>(q, sm, phase, out);
       float probs[NOUT_PAD];
       field_head<NOUT_PAD>(out, fc, sm.pal, keep, sigma, cr, cg, cb, probs);
       if (EXTRA == 1) {
@@ -484,30 +522,16 @@ render_forward_tc(const nfi_render_params p, const unsigned char* __restrict__ w
       }
       if (p.z_fine != nullptr && valid)
         for (int k = 0; k < S; ++k) p.z_fine[ray * S + k] = col[k * kThreads];
+      // park the sorted fine depths next to the coarse samples (coalesced)
+      for (int k = 0; k < S; ++k) sc_zf[k * kThreads + gt] = col[k * kThreads];
       __syncwarp();
-      // park the sorted fine depths in TMEM (columns 64.. of this group's lanes)
-      for (int c = 0; c < S / 16; ++c) {
-        float v[16];
-#pragma unroll
-        for (int i = 0; i < 16; ++i) v[i] = col[(16 * c + i) * kThreads];
-        tc::tmem_st16(zf_lane + 16 * c, v);
-      }
-      tc::tmem_wait_st();
-      tc::tc_fence_before();
       tc::bar_sync(1 + g, kThreads);  // columns are dead; A tiles may be rewritten
-      tc::tc_fence_after();
 
       // ------- fine pass + sorted merge + compositing -------
       int c = 0;
       float ct = sc_t[gt];
       for (int k = 0; k < S; ++k) {
-        uint32_t zr;
-        asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];"
-                     : "=r"(zr)
-                     : "r"(zf_lane + k)
-                     : "memory");
-        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-        const float z = __uint_as_float(zr);
+        const float z = sc_zf[k * kThreads + gt];
         float sigma, cr, cg, cb;
         float ex[NE > 0 ? NE : 1];
         eval(z, sigma, cr, cg, cb, ex);

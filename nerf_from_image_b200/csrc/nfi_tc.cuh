@@ -154,6 +154,19 @@ __device__ __forceinline__ void umma_tf32_ss(uint32_t d_tmem, uint64_t a_desc, u
       "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// D[tmem] (+)= A[tmem] * B[smem]^T : A read from TMEM (lane = row, one 32-bit
+// column per K element), no output lane disabled.
+__device__ __forceinline__ void umma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc,
+                                             uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, {%5, %5, %5, %5}, p;\n"
+      "}\n" ::"r"(d_tmem),
+      "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate), "r"(0u)
+      : "memory");
+}
 // All MMAs issued so far by this thread arrive on `bar` when they complete.
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::
@@ -187,6 +200,44 @@ __device__ __forceinline__ void issue_layer1(uint32_t d_tmem, uint32_t a_hi, uin
       acc = 1;
     }
   }
+}
+
+// Layer 2 (64 -> 16 padded outputs), 3xTF32 with the hidden activations split
+// as H = H_hi + H_lo: H_hi lives in shared memory (two [128 x 32] K-blocks in
+// the space of the layer-1 A tiles), H_lo lives in TMEM where D1 was.
+//   D2 = H_lo*W2_hi (TS) + H_hi*W2_lo (SS) + H_hi*W2_hi (SS)
+// w2_hi / w2_lo: [16 x 64] fp32 as two [16 x 32] K-blocks of 2048 bytes.
+__device__ __forceinline__ void issue_layer2(uint32_t d2_tmem, uint32_t hlo_tmem, uint32_t hhi_k0,
+                                             uint32_t hhi_k1, uint32_t w2_hi, uint32_t w2_lo) {
+  constexpr uint32_t idesc = umma_idesc_tf32(128, 16);
+  uint32_t acc = 0;
+#pragma unroll
+  for (int ks = 0; ks < 8; ++ks) {  // K = 64 = 8 x 8
+    const uint32_t wb = w2_hi + (ks >> 2) * 2048 + (ks & 3) * 32;
+    umma_tf32_ts(d2_tmem, hlo_tmem + 8 * ks, umma_desc_sw128(wb), idesc, acc);
+    acc = 1;
+  }
+#pragma unroll
+  for (int term = 0; term < 2; ++term) {
+    const uint32_t w = (term == 0) ? w2_lo : w2_hi;
+#pragma unroll
+    for (int ks = 0; ks < 8; ++ks) {
+      const uint32_t a = ((ks >> 2) ? hhi_k1 : hhi_k0) + (ks & 3) * 32;
+      const uint32_t wb = w + (ks >> 2) * 2048 + (ks & 3) * 32;
+      umma_tf32_ss(d2_tmem, umma_desc_sw128(a), umma_desc_sw128(wb), idesc, 1);
+    }
+  }
+}
+
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float lg2_approx(float x) {
+  float y;
+  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
 }
 
 }  // namespace tc
