@@ -54,39 +54,83 @@ def peaks():
 
 
 class ClockSampler(threading.Thread):
-    """nvidia-smi clocks / throttle reasons during the timed region."""
+    """SM clock and throttle reasons sampled DURING the timed region (NVML, every
+    ~10 ms; falls back to nvidia-smi if pynvml is missing)."""
 
     def __init__(self, index):
         super().__init__(daemon=True)
         self.index, self.rows, self.stop_flag = index, [], False
+        self.max_mhz = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nvml = pynvml
+            self.handle = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nvml = None
 
     def run(self):
-        q = ('clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,'
-             'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,'
-             'clocks_event_reasons.sw_power_cap')
         while not self.stop_flag:
             try:
-                out = subprocess.run(['nvidia-smi', '-i', str(self.index), '--query-gpu=' + q,
-                                      '--format=csv,noheader,nounits'], capture_output=True,
-                                     text=True, timeout=5).stdout.strip()
-                if out:
-                    self.rows.append([x.strip() for x in out.split(',')])
+                if self.nvml is not None:
+                    n = self.nvml
+                    mhz = n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM)
+                    bits = n.nvmlDeviceGetCurrentClocksEventReasons(self.handle)
+                    self.rows.append((mhz, bits))
+                    time.sleep(0.01)
+                else:
+                    q = 'clocks.sm,clocks.max.sm,clocks_event_reasons.active'
+                    out = subprocess.run(['nvidia-smi', '-i', str(self.index), '--query-gpu=' + q,
+                                          '--format=csv,noheader,nounits'], capture_output=True,
+                                         text=True, timeout=5).stdout.strip().split(',')
+                    self.max_mhz = int(out[1])
+                    self.rows.append((int(out[0]), int(out[2], 16)))
             except Exception:
-                pass
-            time.sleep(0.1)
+                time.sleep(0.05)
 
     def summary(self):
         self.stop_flag = True
         self.join(timeout=6)
         if not self.rows:
-            return dict(sm_mhz=None, sm_max_mhz=None, reasons=['unsampled'])
-        sm = sorted(int(r[0]) for r in self.rows if r[0].isdigit())
-        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
-        reasons = [n for i, n in enumerate(names)
-                   if any(r[2 + i].lower().startswith('active') for r in self.rows)]
-        return dict(sm_mhz=sm[len(sm) // 2] if sm else None,
-                    sm_max_mhz=int(self.rows[0][1]) if self.rows[0][1].isdigit() else None,
-                    reasons=reasons, samples=len(self.rows))
+            return dict(sm_mhz=None, sm_max_mhz=self.max_mhz, reasons=['unsampled'])
+        sm = sorted(r[0] for r in self.rows)
+        # NVML clocks-event-reason bits
+        names = {0x8: 'hw_slowdown', 0x40: 'hw_thermal_slowdown', 0x20: 'sw_thermal_slowdown',
+                 0x4: 'sw_power_cap'}
+        seen = 0
+        for _, bits in self.rows:
+            seen |= bits
+        return dict(sm_mhz=sm[len(sm) // 2], sm_max_mhz=self.max_mhz,
+                    reasons=[n for b, n in names.items() if seen & b], samples=len(self.rows))
+
+
+def best_cpu_threads():
+    """The reference's CPU path is plain PyTorch; its intra-op scaling saturates
+    well before all cores of a big host, so probe a few thread counts on a small
+    sample of the same workload and keep the fastest (reported as `cores`)."""
+    from nerf_from_image_b200 import synthetic
+    from oracle import render_oracle as O
+    ds = synthetic.DATASET_CONFIGS[CFG['dataset']]
+    scene = synthetic.make_scene(7, 1, plane_res=64, scene_range=ds['scene_range'])
+    cams = synthetic.make_cameras(7, 1, radius=ds['radius'])
+    nt, nu = synthetic.make_noise(7, 1, 32, 32, 32)
+    total = os.cpu_count() or 1
+    best, best_t = total, None
+    for th in sorted({t for t in (8, 16, 32, 64, total) if t <= total}):
+        torch.set_num_threads(th)
+        ts = []
+        for _ in range(3):
+            t0 = time.perf_counter()
+            with torch.no_grad():
+                O.render_oracle(scene['planes'], scene['w1'], scene['b1'], scene['w2'],
+                                scene['b2'], scene['palette'], scene['beta'], scene['alpha'],
+                                cams['c2w'], cams['focal'], None, None, 32, 32, 32, nt, nu,
+                                scene_range=scene['scene_range'])
+            ts.append(time.perf_counter() - t0)
+        if best_t is None or min(ts) < best_t:
+            best, best_t = th, min(ts)
+    return best
 
 
 def cpu_oracle_rate(n_images, threads=None, grad=False):
@@ -121,7 +165,7 @@ def run_reference(args):
     if rank != 0:
         return
     n_img = 1
-    threads = os.cpu_count()
+    threads = best_cpu_threads()
     for _ in range(args.warmup):
         cpu_oracle_rate(n_img, threads)
     times = []
@@ -138,7 +182,7 @@ def run_reference(args):
         'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
         'config': {'workload': 'p3d_car render 128x128, 64+64 samples/ray, 256^2 tri-planes '
                                '(config 2 geometry), CPU sample of %d image(s) per step' % n_img},
-        'cpu_baseline': {'value': value, 'unit': UNIT, 'cores': threads, 'kind': 'port',
+        'cpu_baseline': {'value': value, 'unit': UNIT, 'cores': threads, 'host_cores': os.cpu_count(), 'kind': 'port',
                          'sample': '%d image(s) of the 32-image batch per step, torch CPU fp32, '
                                    'no_grad' % n_img},
         'e2e': {'value': value, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
@@ -150,7 +194,7 @@ def run_reference(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
-    ap.add_argument('--steps', type=int, default=10)
+    ap.add_argument('--steps', type=int, default=20)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
     ap.add_argument('--batch', type=int, default=CFG['batch'])
@@ -164,7 +208,7 @@ def main():
         return run_reference(args)
 
     import torch.distributed as dist
-    from nerf_from_image_b200 import _lib, fused, synthetic
+    from nerf_from_image_b200 import _lib, fused, parallel, synthetic
 
     world = int(os.environ.get('WORLD_SIZE', '1'))
     rank = int(os.environ.get('RANK', '0'))
@@ -189,7 +233,6 @@ def main():
     cfg = fused.RenderConfig(scene_range=scene['scene_range'],
                              white_background=scene['white_background'],
                              attention_values=CFG['attention_values'], mlp_mode=args.mlp_mode)
-    gathered = [torch.empty(B, H, W, 5, device=dev) for _ in range(world)] if world > 1 else None
 
     kernel_events = []
 
@@ -204,8 +247,7 @@ def main():
             fused.KERNEL_EVENTS = None
             if world > 1:
                 # the path's one exchange step: packed [rgb, depth, mask] tiles to every rank
-                packed = torch.cat((rgb, depth.unsqueeze(-1), mask.unsqueeze(-1)), dim=-1)
-                dist.all_gather(gathered, packed)
+                rgb, depth, mask = parallel.all_gather_outputs(rgb, depth, mask, world * B)
         return rgb, depth, mask
 
     for _ in range(args.warmup):
@@ -303,9 +345,9 @@ def main():
     parity = None
     if world == 1 and not args.no_cpu_baseline:
         n_img = 2
-        cores = os.cpu_count()
+        cores = best_cpu_threads()
         rate, dt, ref, (sc_c, cm_c, nt_c, nu_c) = cpu_oracle_rate(n_img, cores)
-        cpu_baseline = {'value': rate, 'unit': UNIT, 'cores': cores, 'kind': 'port',
+        cpu_baseline = {'value': rate, 'unit': UNIT, 'cores': cores, 'host_cores': os.cpu_count(), 'kind': 'port',
                         'sample': '%d of the 32 images (same geometry), %.1f s, torch CPU fp32 '
                                   'no_grad' % (n_img, dt)}
         # parity of the CUDA path on exactly those images
