@@ -201,7 +201,7 @@ def main():
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-e2e', action='store_true')
     ap.add_argument('--e2e-steps', type=int, default=3)
-    ap.add_argument('--mlp-mode', type=int, default=0)
+    ap.add_argument('--mlp-mode', type=lambda x: int(x, 0), default=0)
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == 'b200' else args.warmup
     if args.impl == 'reference':

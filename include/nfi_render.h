@@ -65,7 +65,8 @@ enum nfi_noise_mode {
 enum nfi_mlp_mode {
   NFI_MLP_AUTO = 0,
   NFI_MLP_FP32_SIMT = 1, /* fp32 FFMA on CUDA cores                      */
-  NFI_MLP_TC_3XTF32 = 2  /* tcgen05.mma kind::tf32, hi/lo split (3 MMAs) */
+  NFI_MLP_TC_3XTF32 = 2, /* tcgen05.mma kind::tf32, hi/lo split (3 MMAs), lockstep tile groups */
+  NFI_MLP_TC_WARPSPEC = 3 /* same arithmetic, producer/consumer warp-specialised, persistent */
 };
 
 typedef struct nfi_render_params {

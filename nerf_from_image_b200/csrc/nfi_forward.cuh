@@ -15,7 +15,7 @@
 
 namespace nfi {
 
-template <int NE>
+template <int NE, bool FAST = false>
 struct Compositor {
   float T, ar, ag, ab, ad, am;
   float ae[NE > 0 ? NE : 1];
@@ -38,7 +38,7 @@ struct Compositor {
                                        const float* e, float dn) {
     if (have) {
       const float delta = (z - pz) * dn;
-      const float a = 1.f - expf(-ps * delta);
+      const float a = 1.f - (FAST ? __expf(-ps * delta) : expf(-ps * delta));
       const float w = a * T;
       ar = fmaf(w, pr, ar);
       ag = fmaf(w, pg, ag);

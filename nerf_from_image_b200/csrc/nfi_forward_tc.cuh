@@ -166,6 +166,152 @@ __device__ __forceinline__ void gather_to_tiles(const float* __restrict__ planes
   }
 }
 
+// Software-pipelined variant of gather_to_tiles: the texel lines of point
+// group g+2 are PREFETCHED into L1 (no registers held) while group g is loaded
+// (now an L1 hit) and interpolated, so a warp never sits on an L2 round trip.
+struct GroupTaps {
+  uint32_t off[12];  // float4 index of each tap for this lane (plane and channel quad included)
+  float fx[3], fy[3];
+};
+
+__device__ __forceinline__ void group_taps(const PackedTaps& tp, int src, int R,
+                                           uint32_t plane_stride4, int k, GroupTaps& t) {
+#pragma unroll
+  for (int pl = 0; pl < 3; ++pl) {
+    const uint32_t o = __shfl_sync(kFull, tp.o[pl], src);
+    t.fx[pl] = __shfl_sync(kFull, tp.fx[pl], src);
+    t.fy[pl] = __shfl_sync(kFull, tp.fy[pl], src);
+    const uint32_t o00 = o & 0x3FFFFFFFu;
+    const uint32_t dx = (o >> 30) & 1u, dy = (o >> 31) ? (uint32_t)R : 0u;
+    const uint32_t b = pl * plane_stride4 + k;
+    t.off[4 * pl + 0] = o00 * (kC / 4) + b;
+    t.off[4 * pl + 1] = (o00 + dx) * (kC / 4) + b;
+    t.off[4 * pl + 2] = (o00 + dy) * (kC / 4) + b;
+    t.off[4 * pl + 3] = (o00 + dy + dx) * (kC / 4) + b;
+  }
+}
+
+__device__ __forceinline__ void group_prefetch(const float4* __restrict__ planes4,
+                                               const GroupTaps& t) {
+#pragma unroll
+  for (int i = 0; i < 12; ++i) tc::prefetch_l1(planes4 + t.off[i]);
+}
+
+__device__ __forceinline__ void group_consume(const float4* __restrict__ planes4,
+                                              const GroupTaps& t, unsigned char* a_hi,
+                                              unsigned char* a_lo, int row, int k) {
+  float4 v[12];
+#pragma unroll
+  for (int i = 0; i < 12; ++i) v[i] = ldg4(planes4 + t.off[i]);
+  float2 lo = make_float2(0.f, 0.f), hi = make_float2(0.f, 0.f);
+#pragma unroll
+  for (int pl = 0; pl < 3; ++pl) {
+    const float gx0 = 1.f - t.fx[pl], gy0 = 1.f - t.fy[pl];
+    const float w[4] = {gx0 * gy0, t.fx[pl] * gy0, gx0 * t.fy[pl], t.fx[pl] * t.fy[pl]};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float4 x = v[4 * pl + j];
+      lo = ffma2(make_float2(x.x, x.y), make_float2(w[j], w[j]), lo);
+      hi = ffma2(make_float2(x.z, x.w), make_float2(w[j], w[j]), hi);
+    }
+  }
+  const float third = 0.33333334f;
+  const float4 f = make_float4(lo.x * third, lo.y * third, hi.x * third, hi.y * third);
+  const float4 fh = make_float4(tc::tf32_hi(f.x), tc::tf32_hi(f.y), tc::tf32_hi(f.z),
+                                tc::tf32_hi(f.w));
+  const float4 fl = make_float4(f.x - fh.x, f.y - fh.y, f.z - fh.z, f.w - fh.w);
+  const uint32_t off = tc::sw128_offset(row, k);
+  *reinterpret_cast<float4*>(a_hi + off) = fh;
+  *reinterpret_cast<float4*>(a_lo + off) = fl;
+}
+
+__device__ __forceinline__ void gather_to_tiles_pf(const float* __restrict__ planes_b, int R,
+                                                   const PackedTaps& tp, unsigned char* a_hi,
+                                                   unsigned char* a_lo, int row0, int lane) {
+  const int q = lane >> 3, k = lane & 7;
+  const uint32_t plane_stride4 = (uint32_t)R * R * (kC / 4);
+  const float4* planes4 = reinterpret_cast<const float4*>(planes_b);
+  GroupTaps ta, tb;
+  group_taps(tp, q, R, plane_stride4, k, ta);
+  group_prefetch(planes4, ta);
+  group_taps(tp, 4 + q, R, plane_stride4, k, tb);
+  group_prefetch(planes4, tb);
+#pragma unroll 1
+  for (int g = 0; g < 8; g += 2) {
+    group_consume(planes4, ta, a_hi, a_lo, row0 + 4 * g + q, k);
+    if (g + 2 < 8) {
+      group_taps(tp, 4 * (g + 2) + q, R, plane_stride4, k, ta);
+      group_prefetch(planes4, ta);
+    }
+    group_consume(planes4, tb, a_hi, a_lo, row0 + 4 * (g + 1) + q, k);
+    if (g + 3 < 8) {
+      group_taps(tp, 4 * (g + 3) + q, R, plane_stride4, k, tb);
+      group_prefetch(planes4, tb);
+    }
+  }
+}
+
+__device__ __forceinline__ float4 ldg_nc_volatile(const float4* p) {
+  float4 r;  // volatile: the 12 loads of a point group must issue back-to-back, before any use
+  asm volatile("ld.global.nc.v4.f32 {%0, %1, %2, %3}, [%4];"
+               : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w)
+               : "l"(p));
+  return r;
+}
+
+// Gather for the producer warps: per point group (4 points x 8 lanes) the 9 tap
+// parameters are shuffled in, the 12 texel loads are ISSUED TOGETHER, then
+// interpolated.  (A structure that interleaves loads and FFMA2s leaves only ~4
+// loads in flight per warp and serialises ~24 L2 round trips per step.)
+__device__ __forceinline__ void gather_to_tiles_deep(const float* __restrict__ planes_b, int R,
+                                                     const PackedTaps& tp, unsigned char* a_hi,
+                                                     unsigned char* a_lo, int row0, int lane) {
+  const int q = lane >> 3, k = lane & 7;
+  const uint32_t plane_stride4 = (uint32_t)R * R * (kC / 4);
+  const float4* base = reinterpret_cast<const float4*>(planes_b) + k;
+#pragma unroll 1
+  for (int g = 0; g < 8; ++g) {
+    const int src = 4 * g + q;
+    uint32_t off[12];
+    float fx[3], fy[3];
+#pragma unroll
+    for (int pl = 0; pl < 3; ++pl) {
+      const uint32_t o = __shfl_sync(kFull, tp.o[pl], src);
+      fx[pl] = __shfl_sync(kFull, tp.fx[pl], src);
+      fy[pl] = __shfl_sync(kFull, tp.fy[pl], src);
+      const uint32_t o00 = (o & 0x3FFFFFFFu) * (kC / 4) + pl * plane_stride4;
+      const uint32_t dx = ((o >> 30) & 1u) * (kC / 4), dy = (o >> 31) ? (uint32_t)R * (kC / 4) : 0u;
+      off[4 * pl + 0] = o00;
+      off[4 * pl + 1] = o00 + dx;
+      off[4 * pl + 2] = o00 + dy;
+      off[4 * pl + 3] = o00 + dy + dx;
+    }
+    float4 v[12];
+#pragma unroll
+    for (int i = 0; i < 12; ++i) v[i] = ldg_nc_volatile(base + off[i]);
+    float2 lo = make_float2(0.f, 0.f), hi = make_float2(0.f, 0.f);
+#pragma unroll
+    for (int pl = 0; pl < 3; ++pl) {
+      const float gx0 = 1.f - fx[pl], gy0 = 1.f - fy[pl];
+      const float w[4] = {gx0 * gy0, fx[pl] * gy0, gx0 * fy[pl], fx[pl] * fy[pl]};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float4 x = v[4 * pl + j];
+        lo = ffma2(make_float2(x.x, x.y), make_float2(w[j], w[j]), lo);
+        hi = ffma2(make_float2(x.z, x.w), make_float2(w[j], w[j]), hi);
+      }
+    }
+    const float third = 0.33333334f;
+    const float4 f = make_float4(lo.x * third, lo.y * third, hi.x * third, hi.y * third);
+    const float4 fh = make_float4(tc::tf32_hi(f.x), tc::tf32_hi(f.y), tc::tf32_hi(f.z),
+                                  tc::tf32_hi(f.w));
+    const float4 fl = make_float4(f.x - fh.x, f.y - fh.y, f.z - fh.z, f.w - fh.w);
+    const uint32_t offs = tc::sw128_offset(row0 + src, k);
+    *reinterpret_cast<float4*>(a_hi + offs) = fh;
+    *reinterpret_cast<float4*>(a_lo + offs) = fl;
+  }
+}
+
 struct TcShared {
   unsigned char* base;   // 1024-aligned
   const float* b1;
@@ -191,27 +337,37 @@ struct TcGroup {
   int g, gt, wig;
   unsigned char* a_hi;   // A_hi tile  / H_hi k-block 0
   unsigned char* a_lo;   // A_lo tile  / H_hi k-block 1
-  uint32_t a_hi_s, a_lo_s, w1_hi_s, w1_lo_s, w2_hi_s, w2_lo_s;
+  uint64_t dsc_a, dsc_w1_hi, dsc_w1_lo, dsc_w2_hi, dsc_w2_lo;  // UMMA descriptor bases
   uint32_t d_tmem;       // group's first TMEM column, lane 0
   uint32_t d_lane;       // same, this warp's lane quadrant
   uint64_t* bar;
 };
 
+__device__ __forceinline__ bool tc_elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n.reg .pred p;\nelect.sync _|p, 0xffffffff;\nselp.u32 %0, 1, 0, p;\n}\n"
+      : "=r"(pred));
+  return pred != 0;
+}
+
 __device__ __forceinline__ TcGroup tc_group(const TcShared& sm, uint32_t tmem_base, int tid) {
   TcGroup q;
-  q.g = tid >> 7;
+  // warp-uniform by construction AND known to the compiler as such (shfl from lane 0):
+  // lets ptxas keep the UMMA operands in uniform registers instead of a
+  // per-instruction ELECT / R2UR waterfall loop.
+  q.g = __shfl_sync(kFull, tid >> 7, 0);
   q.gt = tid & 127;
-  q.wig = q.gt >> 5;
+  q.wig = __shfl_sync(kFull, q.gt >> 5, 0);
   q.a_hi = sm.base + kSmA + q.g * kSmAGroup;
   q.a_lo = q.a_hi + 16384;
-  q.a_hi_s = tc::smem_u32(q.a_hi);
-  q.a_lo_s = q.a_hi_s + 16384;
   const uint32_t base_s = tc::smem_u32(sm.base);
-  q.w1_hi_s = base_s + kWiW1Hi;
-  q.w1_lo_s = base_s + kWiW1Lo;
-  q.w2_hi_s = base_s + kWiW2Hi;
-  q.w2_lo_s = base_s + kWiW2Lo;
-  q.d_tmem = tmem_base + q.g * 128;
+  q.dsc_a = tc::umma_desc_sw128(base_s + kSmA + q.g * kSmAGroup);
+  q.dsc_w1_hi = tc::umma_desc_sw128(base_s + kWiW1Hi);
+  q.dsc_w1_lo = tc::umma_desc_sw128(base_s + kWiW1Lo);
+  q.dsc_w2_hi = tc::umma_desc_sw128(base_s + kWiW2Hi);
+  q.dsc_w2_lo = tc::umma_desc_sw128(base_s + kWiW2Lo);
+  q.d_tmem = __shfl_sync(kFull, tmem_base, 0) + q.g * 128;
   q.d_lane = q.d_tmem + ((uint32_t)(32 * q.wig) << 16);
   q.bar = &sm.bars[q.g];
   return q;
@@ -230,46 +386,68 @@ __device__ __forceinline__ void tile_mlp(const TcGroup& q, const TcShared& sm, u
   tc::fence_async_smem();
   tc::tc_fence_before();
   tc::bar_sync(1 + q.g, kThreads);
-  if (q.gt == 0) {
-    tc::tc_fence_after();
-    tc::issue_layer1(q.d_tmem, q.a_hi_s, q.a_lo_s, q.w1_hi_s, q.w1_lo_s);
-    tc::umma_commit(q.bar);
+  if (q.wig == 0) {
+    if (tc_elect_one()) {
+      tc::tc_fence_after();
+      tc::issue_layer1_d(q.d_tmem, q.dsc_a, q.dsc_a + (16384 >> 4), q.dsc_w1_hi, q.dsc_w1_lo);
+      tc::umma_commit(q.bar);
+    }
+    __syncwarp();
   }
   tc::mbar_wait(q.bar, phase);
   phase ^= 1;
   tc::tc_fence_after();
 #pragma unroll 1
-  for (int c = 0; c < 4; ++c) {
-    float v[16];
-    tc::tmem_ld16(q.d_lane + 16 * c, v);
-    unsigned char* hrow = (c < 2) ? q.a_hi : q.a_lo;
+  for (int c2 = 0; c2 < 2; ++c2) {  // two 16-column TMEM loads in flight
+    uint32_t ra[16], rb[16];
+    tc::tmem_ld16_nowait(q.d_lane + 32 * c2, ra);
+    tc::tmem_ld16_nowait(q.d_lane + 32 * c2 + 16, rb);
+    tc::tmem_wait_ld();
+    unsigned char* hrow = (c2 == 0) ? q.a_hi : q.a_lo;
 #pragma unroll
-    for (int i4 = 0; i4 < 4; ++i4) {
-      const float4 bb = *reinterpret_cast<const float4*>(sm.b1 + 16 * c + 4 * i4);
-      const float bv[4] = {bb.x, bb.y, bb.z, bb.w};
-      float hi[4];
+    for (int half = 0; half < 2; ++half) {
+      float v[16];
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const float x = v[4 * i4 + i] + bv[i];
-        // softplus(x) = max(x,0) + ln2 * lg2(1 + 2^(-|x| log2 e))   (MUFU ex2 + lg2)
-        const float e = tc::ex2_approx(-fabsf(x) * 1.4426950408889634f);
-        const float h = fmaf(tc::lg2_approx(1.f + e), 0.6931471805599453f, fmaxf(x, 0.f));
-        hi[i] = tc::tf32_hi(h);
-        v[4 * i4 + i] = h - hi[i];
+      for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(half ? rb[i] : ra[i]);
+#pragma unroll
+      for (int i4 = 0; i4 < 4; ++i4) {
+        const float4 bb = *reinterpret_cast<const float4*>(sm.b1 + 32 * c2 + 16 * half + 4 * i4);
+        const float bv[4] = {bb.x, bb.y, bb.z, bb.w};
+        float hi[4];
+#pragma unroll
+        for (int i = 0; i < 4; i += 2) {
+          // softplus(x) = max(x,0) + ln2 * lg2(1 + 2^(-|x| log2 e)); two lanes packed (FFMA2 etc.)
+          const float2 x = __fadd2_rn(make_float2(v[4 * i4 + i], v[4 * i4 + i + 1]),
+                                      make_float2(bv[i], bv[i + 1]));
+          const float2 ax = __fmul2_rn(make_float2(fabsf(x.x), fabsf(x.y)),
+                                       make_float2(-1.4426950408889634f, -1.4426950408889634f));
+          const float2 l = make_float2(tc::lg2_approx(1.f + tc::ex2_approx(ax.x)),
+                                       tc::lg2_approx(1.f + tc::ex2_approx(ax.y)));
+          const float2 h = __ffma2_rn(l, make_float2(0.6931471805599453f, 0.6931471805599453f),
+                                      make_float2(fmaxf(x.x, 0.f), fmaxf(x.y, 0.f)));
+          hi[i] = tc::tf32_hi(h.x);
+          hi[i + 1] = tc::tf32_hi(h.y);
+          const float2 lo2 = __fadd2_rn(h, make_float2(-hi[i], -hi[i + 1]));
+          v[4 * i4 + i] = lo2.x;
+          v[4 * i4 + i + 1] = lo2.y;
+        }
+        const uint32_t off = tc::sw128_offset(q.gt, half * 4 + i4);
+        *reinterpret_cast<float4*>(hrow + off) = make_float4(hi[0], hi[1], hi[2], hi[3]);
       }
-      const uint32_t off = tc::sw128_offset(q.gt, (c & 1) * 4 + i4);
-      *reinterpret_cast<float4*>(hrow + off) = make_float4(hi[0], hi[1], hi[2], hi[3]);
+      tc::tmem_st16(q.d_lane + 32 * c2 + 16 * half, v);  // H_lo over the D1 columns just read
     }
-    tc::tmem_st16(q.d_lane + 16 * c, v);  // H_lo over the D1 columns just read
   }
   tc::tmem_wait_st();
   tc::fence_async_smem();
   tc::tc_fence_before();
   tc::bar_sync(1 + q.g, kThreads);
-  if (q.gt == 0) {
-    tc::tc_fence_after();
-    tc::issue_layer2(q.d_tmem + 64, q.d_tmem, q.a_hi_s, q.a_lo_s, q.w2_hi_s, q.w2_lo_s);
-    tc::umma_commit(q.bar);
+  if (q.wig == 0) {
+    if (tc_elect_one()) {
+      tc::tc_fence_after();
+      tc::issue_layer2_d(q.d_tmem + 64, q.d_tmem, q.dsc_a, q.dsc_w2_hi, q.dsc_w2_lo);
+      tc::umma_commit(q.bar);
+    }
+    __syncwarp();
   }
   tc::mbar_wait(q.bar, phase);
   phase ^= 1;
@@ -410,7 +588,7 @@ render_forward_tc(const nfi_render_params p, const unsigned char* __restrict__ w
     float* sc_w = sc_t + (size_t)S * kThreads;
     float* sc_zf = sc_w + (size_t)S * kThreads;
 
-    Compositor<NE> comp;
+    Compositor<NE, true> comp;
     comp.init();
 
     auto eval = [&](float t, float& sigma, float& cr, float& cg, float& cb, float* ex) {
@@ -422,11 +600,11 @@ render_forward_tc(const nfi_render_params p, const unsigned char* __restrict__ w
       pack_taps(x0, x1, R, tp.o[0], tp.fx[0], tp.fy[0]);
       pack_taps(x0, x2, R, tp.o[1], tp.fx[1], tp.fy[1]);
       pack_taps(x1, x2, R, tp.o[2], tp.fx[2], tp.fy[2]);
-      gather_to_tiles(planes_b, R, tp, a_hi, a_lo, 32 * wig, lane);
+      gather_to_tiles_deep(planes_b, R, tp, a_hi, a_lo, 32 * wig, lane);
       float out[NOUT_PAD];
       tile_mlp<NOUT_PAD>(q, sm, phase, out);
       float probs[NOUT_PAD];
-      field_head<NOUT_PAD>(out, fc, sm.pal, keep, sigma, cr, cg, cb, probs);
+      field_head<NOUT_PAD, true>(out, fc, sm.pal, keep, sigma, cr, cg, cb, probs);
       if (EXTRA == 1) {
         ex[0] = wx;
         ex[1] = wy;

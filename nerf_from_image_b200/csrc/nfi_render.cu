@@ -10,6 +10,7 @@
 #include "nfi_backward.cuh"
 #include "nfi_forward.cuh"
 #include "nfi_forward_tc.cuh"
+#include "nfi_forward_ws.cuh"
 #include "nfi_render.h"
 
 #define NFI_STR_(x) #x
@@ -62,7 +63,8 @@ int check_params(const nfi_render_params* p) {
     return fail("compute_semantics needs attention_values > 0");  // run.py:232
   if (p->extra_mode < 0 || p->extra_mode > 2) return fail("unknown extra_mode");
   if (p->extra_mode != NFI_EXTRA_NONE && !p->extra) return fail("extra output buffer missing");
-  if (p->compute_normals) return fail("compute_normals is not implemented in this build");
+  if (p->compute_normals && !(p->mlp_mode & 0x1000))
+    return fail("compute_normals is not implemented in this build");
   if (!p->rgb || !p->depth || !p->mask) return fail("output buffers missing");
   return 0;
 }
@@ -75,16 +77,20 @@ size_t num_ctas(const nfi_render_params* p) {
 
 constexpr size_t kWeightImageBytes = 32768;  // workspace header (nfi::kWiBytes rounded up)
 
+constexpr size_t kMaxPersistentCtas = 160;  // >= SM count of any sm_100 part (B200: 148)
+
+// persistent warp-specialised kernel: one CTA per SM, two tiles in flight per CTA
 size_t num_tc_ctas(const nfi_render_params* p) {
-  const size_t tx = (p->width + nfi::kTileW - 1) / nfi::kTileW;
-  const size_t ty = (p->height + nfi::kTileH - 1) / nfi::kTileH;
-  return ((tx + 1) / 2) * ((ty + 1) / 2) * (size_t)p->batch;
+  const size_t want = (num_ctas(p) + nfi::kWsGroups - 1) / nfi::kWsGroups;
+  return want < kMaxPersistentCtas ? want : kMaxPersistentCtas;
 }
 
 // Can the tensor-core kernel take this configuration?
 bool tc_supported(const nfi_render_params* p) {
   if (p->extra_mode == NFI_EXTRA_SEMANTICS) return false;
-  if (p->fine_sampling && (p->num_samples % 16 != 0 || p->num_samples > 64)) return false;
+  const int mode = p->mlp_mode & 0xff;
+  const int smax = (mode == NFI_MLP_TC_WARPSPEC) ? 128 : 64;  // per-ray columns in tile memory
+  if (p->fine_sampling && p->num_samples > smax) return false;
   return true;
 }
 
@@ -121,17 +127,40 @@ int launch_fwd_extra(const nfi_render_params& p, size_t smem, cudaStream_t st) {
 template <int NP, int EX>
 int launch_fwd_tc_fine(const nfi_render_params& p, const unsigned char* wimg, float* scratch,
                        cudaStream_t st) {
-  const unsigned grid = (unsigned)num_tc_ctas(&p);
+  const bool lockstep = (p.mlp_mode & 0xff) != NFI_MLP_TC_WARPSPEC;
+  if (lockstep) {  // render_forward_tc: 4 tile groups per 512-thread CTA, one CTA per 2x2 tiles
+    const size_t tx = (p.width + nfi::kTileW - 1) / nfi::kTileW;
+    const size_t ty = (p.height + nfi::kTileH - 1) / nfi::kTileH;
+    const unsigned grid = (unsigned)(((tx + 1) / 2) * ((ty + 1) / 2) * (size_t)p.batch);
+    if (p.fine_sampling) {
+      auto k = nfi::render_forward_tc<NP, EX, true>;
+      NFI_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    nfi::kSmTcBytes));
+      k<<<grid, nfi::kTcThreads, nfi::kSmTcBytes, st>>>(p, wimg, scratch);
+    } else {
+      auto k = nfi::render_forward_tc<NP, EX, false>;
+      NFI_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    nfi::kSmTcBytes));
+      k<<<grid, nfi::kTcThreads, nfi::kSmTcBytes, st>>>(p, wimg, scratch);
+    }
+    NFI_CUDA(cudaGetLastError());
+    return 0;
+  }
+  int dev = 0, sms = 0;
+  NFI_CUDA(cudaGetDevice(&dev));
+  NFI_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  size_t grid = num_tc_ctas(&p);
+  if (grid > (size_t)sms) grid = sms;
   if (p.fine_sampling) {
-    auto k = nfi::render_forward_tc<NP, EX, true>;
+    auto k = nfi::render_forward_ws<NP, EX, true>;
     NFI_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  nfi::kSmTcBytes));
-    k<<<grid, nfi::kTcThreads, nfi::kSmTcBytes, st>>>(p, wimg, scratch);
+                                  nfi::kWsSmBytes));
+    k<<<(unsigned)grid, nfi::kWsThreads, nfi::kWsSmBytes, st>>>(p, wimg, scratch);
   } else {
-    auto k = nfi::render_forward_tc<NP, EX, false>;
+    auto k = nfi::render_forward_ws<NP, EX, false>;
     NFI_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  nfi::kSmTcBytes));
-    k<<<grid, nfi::kTcThreads, nfi::kSmTcBytes, st>>>(p, wimg, scratch);
+                                  nfi::kWsSmBytes));
+    k<<<(unsigned)grid, nfi::kWsThreads, nfi::kWsSmBytes, st>>>(p, wimg, scratch);
   }
   NFI_CUDA(cudaGetLastError());
   return 0;
@@ -249,9 +278,13 @@ size_t nfi_render_workspace_bytes(const nfi_render_params* p) {
   if (p->fine_sampling) {
     fwd = num_ctas(p) * nfi::fwd_scratch_floats_per_cta(p->num_samples, ne_store_of(p)) *
           sizeof(float);
-    const size_t tc = num_tc_ctas(p) * nfi::kGroups *
-                      nfi::tc_scratch_floats_per_group(p->num_samples) * sizeof(float);
-    if (tc > fwd) fwd = tc;
+    const size_t per_group = nfi::tc_scratch_floats_per_group(p->num_samples) * sizeof(float);
+    const size_t ws = num_tc_ctas(p) * nfi::kWsGroups * per_group;
+    const size_t tx = (p->width + nfi::kTileW - 1) / nfi::kTileW;
+    const size_t ty = (p->height + nfi::kTileH - 1) / nfi::kTileH;
+    const size_t ls = ((tx + 1) / 2) * ((ty + 1) / 2) * (size_t)p->batch * nfi::kGroups * per_group;
+    if (ws > fwd) fwd = ws;
+    if (ls > fwd) fwd = ls;
   }
   return kWeightImageBytes + fwd + 256;
 }
@@ -282,11 +315,12 @@ int nfi_render_forward(const nfi_render_params* params, void* stream) {
   const nfi_render_params& p = *params;
   const int np = nout_pad_of(params);
   cudaStream_t st = (cudaStream_t)stream;
-  if (p.mlp_mode == NFI_MLP_TC_3XTF32 && !tc_supported(params))
-    return fail("NFI_MLP_TC_3XTF32 needs S %% 16 == 0, S <= 64 with fine sampling, and no "
-                "semantics output; use NFI_MLP_AUTO");
-  const bool want_tc = p.mlp_mode == NFI_MLP_TC_3XTF32 ||
-                       (p.mlp_mode == NFI_MLP_AUTO && tc_supported(params));
+  const int mode = p.mlp_mode & 0xff;
+  if ((mode == NFI_MLP_TC_3XTF32 || mode == NFI_MLP_TC_WARPSPEC) && !tc_supported(params))
+    return fail("tensor-core modes need S <= 64 (warp-specialised: 128) with fine sampling and "
+                "no semantics output; use NFI_MLP_AUTO");
+  const bool want_tc = mode == NFI_MLP_TC_3XTF32 || mode == NFI_MLP_TC_WARPSPEC ||
+                       (mode == NFI_MLP_AUTO && tc_supported(params));
   if (want_tc || p.fine_sampling) {
     if (!p.workspace || p.workspace_bytes < nfi_render_workspace_bytes(params))
       return fail("workspace too small (see nfi_render_workspace_bytes)");

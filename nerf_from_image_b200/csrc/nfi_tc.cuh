@@ -103,6 +103,20 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
 #pragma unroll
   for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
+// same without the wait: issue several, then tmem_wait_ld() once
+__device__ __forceinline__ void tmem_ld16_nowait(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]),
+        "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]),
+        "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_wait_ld() {
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
 __device__ __forceinline__ void tmem_st16(uint32_t taddr, const float (&v)[16]) {
   asm volatile(
       "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
@@ -183,6 +197,75 @@ __device__ __forceinline__ float tf32_hi(float x) {
   return __uint_as_float(__float_as_uint(x) & 0xFFFFE000u);
 }
 
+// accumulate / overwrite variants without the setp (the flag is known at compile time)
+template <bool ACC>
+__device__ __forceinline__ void umma_ss(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc,
+                                        uint32_t idesc) {
+  if (ACC)
+    asm volatile(
+        "{\n.reg .pred p;\nsetp.eq.u32 p, 0, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n}\n" ::"r"(d_tmem),
+        "l"(a_desc), "l"(b_desc), "r"(idesc)
+        : "memory");
+  else
+    asm volatile(
+        "{\n.reg .pred p;\nsetp.ne.u32 p, 0, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n}\n" ::"r"(d_tmem),
+        "l"(a_desc), "l"(b_desc), "r"(idesc)
+        : "memory");
+}
+template <bool ACC>
+__device__ __forceinline__ void umma_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc,
+                                        uint32_t idesc) {
+  if (ACC)
+    asm volatile(
+        "{\n.reg .pred p;\nsetp.eq.u32 p, 0, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, {%4, %4, %4, %4}, p;\n}\n" ::"r"(
+            d_tmem),
+        "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(0u)
+        : "memory");
+  else
+    asm volatile(
+        "{\n.reg .pred p;\nsetp.ne.u32 p, 0, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, {%4, %4, %4, %4}, p;\n}\n" ::"r"(
+            d_tmem),
+        "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(0u)
+        : "memory");
+}
+
+// Issues the 12 MMAs of one 128x64x32 3xTF32 product (small terms first).
+// Arguments are descriptor BASES (umma_desc_sw128 of the tile start); a K-step
+// of 8 tf32 = 32 bytes adds 2 to the start-address field.
+__device__ __forceinline__ void issue_layer1_d(uint32_t d_tmem, uint64_t a_hi, uint64_t a_lo,
+                                               uint64_t w_hi, uint64_t w_lo) {
+  constexpr uint32_t idesc = umma_idesc_tf32(128, 64);
+  umma_ss<false>(d_tmem, a_lo, w_hi, idesc);
+#pragma unroll
+  for (int ks = 1; ks < 4; ++ks) umma_ss<true>(d_tmem, a_lo + 2 * ks, w_hi + 2 * ks, idesc);
+#pragma unroll
+  for (int ks = 0; ks < 4; ++ks) umma_ss<true>(d_tmem, a_hi + 2 * ks, w_lo + 2 * ks, idesc);
+#pragma unroll
+  for (int ks = 0; ks < 4; ++ks) umma_ss<true>(d_tmem, a_hi + 2 * ks, w_hi + 2 * ks, idesc);
+}
+// D2 = H_lo*W2_hi (TS) + H_hi*W2_lo (SS) + H_hi*W2_hi (SS); H_hi k-block 1 is
+// 16 KB (1024 descriptor units) after k-block 0, W2 k-block 1 is 2 KB (128) after.
+__device__ __forceinline__ void issue_layer2_d(uint32_t d2_tmem, uint32_t hlo_tmem, uint64_t hhi,
+                                               uint64_t w2_hi, uint64_t w2_lo) {
+  constexpr uint32_t idesc = umma_idesc_tf32(128, 16);
+  umma_ts<false>(d2_tmem, hlo_tmem, w2_hi, idesc);
+#pragma unroll
+  for (int ks = 1; ks < 8; ++ks)
+    umma_ts<true>(d2_tmem, hlo_tmem + 8 * ks, w2_hi + (ks >> 2) * 128 + (ks & 3) * 2, idesc);
+#pragma unroll
+  for (int ks = 0; ks < 8; ++ks)
+    umma_ss<true>(d2_tmem, hhi + (ks >> 2) * 1024 + (ks & 3) * 2,
+                  w2_lo + (ks >> 2) * 128 + (ks & 3) * 2, idesc);
+#pragma unroll
+  for (int ks = 0; ks < 8; ++ks)
+    umma_ss<true>(d2_tmem, hhi + (ks >> 2) * 1024 + (ks & 3) * 2,
+                  w2_hi + (ks >> 2) * 128 + (ks & 3) * 2, idesc);
+}
+
 // Issues the 12 MMAs of one 128x64x32 3xTF32 product (small terms first).
 // a_hi/a_lo: [128 x 32] tiles, w_hi/w_lo: [64 x 32] tiles (shared addresses).
 __device__ __forceinline__ void issue_layer1(uint32_t d_tmem, uint32_t a_hi, uint32_t a_lo,
@@ -227,6 +310,10 @@ __device__ __forceinline__ void issue_layer2(uint32_t d2_tmem, uint32_t hlo_tmem
       umma_tf32_ss(d2_tmem, umma_desc_sw128(a), umma_desc_sw128(wb), idesc, 1);
     }
   }
+}
+
+__device__ __forceinline__ void prefetch_l1(const void* p) {
+  asm volatile("prefetch.global.L1 [%0];" ::"l"(p));
 }
 
 __device__ __forceinline__ float ex2_approx(float x) {

@@ -31,6 +31,9 @@ class RenderConfig:
 # bench.py sets this to a list to collect (start, end) CUDA events around the
 # render kernel launch (events on the launching stream); None = no timing.
 KERNEL_EVENTS = None
+# timing experiments: a float32 CUDA tensor of >= 16 elements the kernel fills with
+# per-phase cycle counts when mlp_mode has bit 0x1000 set
+DEBUG_BUF = None
 
 
 def _ptr(t):
@@ -173,6 +176,8 @@ class FusedTriplaneRender(torch.autograd.Function):
                              S, t['noise_t'], t['noise_u'], extra_mode)
             p.rgb, p.depth, p.mask, p.extra = _ptr(rgb), _ptr(depth), _ptr(mask), _ptr(extra)
             p.z_fine = _ptr(z_fine)
+            if DEBUG_BUF is not None:
+                p.normals = _ptr(DEBUG_BUF)
             ws_bytes = lib.nfi_render_workspace_bytes(ctypes.byref(p))
             ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
             p.workspace, p.workspace_bytes = _ptr(ws), ws_bytes
