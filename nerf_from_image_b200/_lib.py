@@ -17,7 +17,7 @@ c_float_p = ctypes.POINTER(ctypes.c_float)
 
 EXTRA_NONE, EXTRA_COORDS, EXTRA_SEMANTICS = 0, 1, 2
 NOISE_DETERMINISTIC, NOISE_EXPLICIT = 0, 1
-MLP_AUTO, MLP_FP32_SIMT, MLP_TC_3XTF32, MLP_TC_WARPSPEC = 0, 1, 2, 3
+MLP_AUTO, MLP_FP32_SIMT, MLP_TC_3XTF32, MLP_TC_WARPSPEC, MLP_TC_PIPE = 0, 1, 2, 3, 4
 
 
 class RenderParams(ctypes.Structure):

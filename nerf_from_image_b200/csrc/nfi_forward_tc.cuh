@@ -65,10 +65,14 @@ __host__ __device__ inline size_t tc_scratch_floats_per_group(int S) {
 // transposed/padded, biases.
 __global__ void prep_weight_image(const float* __restrict__ w1, const float* __restrict__ b1,
                                   const float* __restrict__ w2, const float* __restrict__ b2,
-                                  int nout, unsigned char* __restrict__ img) {
+                                  int nout, unsigned char* __restrict__ img, float scale1,
+                                  float pad_b2, float scale2) {
+  // scale1: factor folded into layer 1 (W1 and b1); pad_b2: value of the padded
+  // layer-2 biases; scale2: factor folded into the colour rows (>= 1) of layer 2.  The
+  // pipelined kernel wants log2(e), -1e30, log2(e) (nfi_forward_pipe.cuh); others 1, 0, 1.
   for (int i = threadIdx.x; i < kHid * kC; i += blockDim.x) {
     const int j = i / kC, k = i % kC;  // W1[j][k]
-    const float w = w1[i];
+    const float w = w1[i] * scale1;
     const float hi = tc::tf32_hi(w);
     const uint32_t off = tc::sw128_offset(j, k >> 2) + (k & 3) * 4;
     *reinterpret_cast<float*>(img + kWiW1Hi + off) = hi;
@@ -76,7 +80,7 @@ __global__ void prep_weight_image(const float* __restrict__ w1, const float* __r
   }
   for (int i = threadIdx.x; i < kW2Pad * kHid; i += blockDim.x) {
     const int o = i / kHid, j = i % kHid;  // W2[o][j], rows >= nout are zero
-    const float w = (o < nout) ? w2[o * kHid + j] : 0.f;
+    const float w = (o < nout) ? w2[o * kHid + j] * (o >= 1 ? scale2 : 1.f) : 0.f;
     const float hi = tc::tf32_hi(w);
     const uint32_t off = (j >> 5) * 2048 + tc::sw128_offset(o, (j & 31) >> 2) + (j & 3) * 4;
     *reinterpret_cast<float*>(img + kWiW2Hi + off) = hi;
@@ -84,8 +88,9 @@ __global__ void prep_weight_image(const float* __restrict__ w1, const float* __r
   }
   float* b1i = reinterpret_cast<float*>(img + kWiB1);
   float* b2i = reinterpret_cast<float*>(img + kWiB2);
-  for (int i = threadIdx.x; i < kHid; i += blockDim.x) b1i[i] = b1[i];
-  for (int i = threadIdx.x; i < kW2Pad; i += blockDim.x) b2i[i] = (i < nout) ? b2[i] : 0.f;
+  for (int i = threadIdx.x; i < kHid; i += blockDim.x) b1i[i] = b1[i] * scale1;
+  for (int i = threadIdx.x; i < kW2Pad; i += blockDim.x)
+    b2i[i] = (i < nout) ? b2[i] * (i >= 1 ? scale2 : 1.f) : pad_b2;
 }
 
 struct PackedTaps {
@@ -289,6 +294,148 @@ __device__ __forceinline__ void gather_to_tiles_deep(const float* __restrict__ p
     float4 v[12];
 #pragma unroll
     for (int i = 0; i < 12; ++i) v[i] = ldg_nc_volatile(base + off[i]);
+    float2 lo = make_float2(0.f, 0.f), hi = make_float2(0.f, 0.f);
+#pragma unroll
+    for (int pl = 0; pl < 3; ++pl) {
+      const float gx0 = 1.f - fx[pl], gy0 = 1.f - fy[pl];
+      const float w[4] = {gx0 * gy0, fx[pl] * gy0, gx0 * fy[pl], fx[pl] * fy[pl]};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float4 x = v[4 * pl + j];
+        lo = ffma2(make_float2(x.x, x.y), make_float2(w[j], w[j]), lo);
+        hi = ffma2(make_float2(x.z, x.w), make_float2(w[j], w[j]), hi);
+      }
+    }
+    const float third = 0.33333334f;
+    const float4 f = make_float4(lo.x * third, lo.y * third, hi.x * third, hi.y * third);
+    const float4 fh = make_float4(tc::tf32_hi(f.x), tc::tf32_hi(f.y), tc::tf32_hi(f.z),
+                                  tc::tf32_hi(f.w));
+    const float4 fl = make_float4(f.x - fh.x, f.y - fh.y, f.z - fh.z, f.w - fh.w);
+    const uint32_t offs = tc::sw128_offset(row0 + src, k);
+    *reinterpret_cast<float4*>(a_hi + offs) = fh;
+    *reinterpret_cast<float4*>(a_lo + offs) = fl;
+  }
+}
+
+// Rotated variant of gather_to_tiles_deep: the 4 taps of a plane are consumed and
+// immediately RE-ISSUED for the next point group, so ~12 texel loads stay in flight
+// for the whole 32-row gather instead of ramping 12 -> 0 eight times.  Same
+// arithmetic order (planes 0,1,2; taps nw,ne,sw,se), bit-identical features.
+struct PlaneTaps {
+  float4 v[4];
+  float fx, fy;
+};
+__device__ __forceinline__ void plane_issue(const float4* __restrict__ base, const PackedTaps& tp,
+                                            int pl, int src, uint32_t plane_stride4, int R,
+                                            PlaneTaps& t) {
+  const uint32_t o = __shfl_sync(kFull, tp.o[pl], src);
+  t.fx = __shfl_sync(kFull, tp.fx[pl], src);
+  t.fy = __shfl_sync(kFull, tp.fy[pl], src);
+  const uint32_t o00 = (o & 0x3FFFFFFFu) * (kC / 4) + pl * plane_stride4;
+  const uint32_t dx = ((o >> 30) & 1u) * (kC / 4), dy = (o >> 31) ? (uint32_t)R * (kC / 4) : 0u;
+  t.v[0] = ldg_nc_volatile(base + o00);
+  t.v[1] = ldg_nc_volatile(base + o00 + dx);
+  t.v[2] = ldg_nc_volatile(base + o00 + dy);
+  t.v[3] = ldg_nc_volatile(base + o00 + dy + dx);
+}
+__device__ __forceinline__ void plane_consume(const PlaneTaps& t, float2& lo, float2& hi) {
+  const float gx0 = 1.f - t.fx, gy0 = 1.f - t.fy;
+  const float w[4] = {gx0 * gy0, t.fx * gy0, gx0 * t.fy, t.fx * t.fy};
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    lo = ffma2(make_float2(t.v[j].x, t.v[j].y), make_float2(w[j], w[j]), lo);
+    hi = ffma2(make_float2(t.v[j].z, t.v[j].w), make_float2(w[j], w[j]), hi);
+  }
+}
+__device__ __forceinline__ void gather_to_tiles_rot(const float* __restrict__ planes_b, int R,
+                                                    const PackedTaps& tp, unsigned char* a_hi,
+                                                    unsigned char* a_lo, int row0, int lane) {
+  const int q = lane >> 3, k = lane & 7;
+  const uint32_t plane_stride4 = (uint32_t)R * R * (kC / 4);
+  const float4* base = reinterpret_cast<const float4*>(planes_b) + k;
+  PlaneTaps p0, p1, p2;
+  plane_issue(base, tp, 0, q, plane_stride4, R, p0);
+  plane_issue(base, tp, 1, q, plane_stride4, R, p1);
+  plane_issue(base, tp, 2, q, plane_stride4, R, p2);
+#pragma unroll 1
+  for (int g = 0; g < 8; ++g) {
+    const int src = 4 * g + q;
+    const int nsrc = (g < 7) ? src + 4 : src;  // last round re-reads its own lines (L1 hits)
+    float2 lo = make_float2(0.f, 0.f), hi = make_float2(0.f, 0.f);
+    plane_consume(p0, lo, hi);
+    plane_issue(base, tp, 0, nsrc, plane_stride4, R, p0);
+    plane_consume(p1, lo, hi);
+    plane_issue(base, tp, 1, nsrc, plane_stride4, R, p1);
+    plane_consume(p2, lo, hi);
+    plane_issue(base, tp, 2, nsrc, plane_stride4, R, p2);
+    const float third = 0.33333334f;
+    const float4 f = make_float4(lo.x * third, lo.y * third, hi.x * third, hi.y * third);
+    const float4 fh = make_float4(tc::tf32_hi(f.x), tc::tf32_hi(f.y), tc::tf32_hi(f.z),
+                                  tc::tf32_hi(f.w));
+    const float4 fl = make_float4(f.x - fh.x, f.y - fh.y, f.z - fh.z, f.w - fh.w);
+    const uint32_t offs = tc::sw128_offset(row0 + src, k);
+    *reinterpret_cast<float4*>(a_hi + offs) = fh;
+    *reinterpret_cast<float4*>(a_lo + offs) = fl;
+  }
+}
+
+// ---------------------------------------------------------------------------
+// Lean gather (nfi_forward_pipe.cuh): same arithmetic as gather_to_tiles_deep,
+// about half the instructions.  The owner lane of a point pre-multiplies its
+// three nw-texel offsets into offsets from the image's plane base in 16-byte units
+// (plane index and the 8 units of a texel included; the two border flags ride in
+// bits 0/1 of the multiple-of-8 value), so the serving lanes only mask, add and
+// widen (one IMAD.WIDE.U32 per address: x16 + base).
+// ---------------------------------------------------------------------------
+struct ByteTaps {
+  uint32_t o[3];  // offset of the nw texel in 16-byte units | (x+1 < R) | (y+1 < R) << 1
+  float fx[3], fy[3];
+};
+__device__ __forceinline__ void byte_taps(float gx, float gy, int R, uint32_t plane_units,
+                                          uint32_t& o, float& fx, float& fy) {
+  const float m = (float)(R - 1);
+  float ix = (gx + 1.f) * 0.5f * m;
+  float iy = (gy + 1.f) * 0.5f * m;
+  ix = fminf(m, fmaxf(ix, 0.f));
+  iy = fminf(m, fmaxf(iy, 0.f));
+  const float x0 = floorf(ix), y0 = floorf(iy);
+  fx = ix - x0;
+  fy = iy - y0;
+  const int xi = (int)x0, yi = (int)y0;
+  o = plane_units + (uint32_t)(yi * R + xi) * 8u + ((xi + 1 < R) ? 1u : 0u) +
+      ((yi + 1 < R) ? 2u : 0u);
+}
+// base + 16 * off as ONE IMAD.WIDE.U32 (a plain 64-bit pointer add costs two)
+__device__ __forceinline__ const float4* texel_ptr(const unsigned char* base, uint32_t off16) {
+  uint64_t r;
+  asm("mad.wide.u32 %0, %1, 16, %2;" : "=l"(r) : "r"(off16), "l"(base));
+  return reinterpret_cast<const float4*>(r);
+}
+__device__ __forceinline__ void gather_to_tiles_lean(const unsigned char* __restrict__ planes_b,
+                                                     int R, const ByteTaps& tp,
+                                                     unsigned char* a_hi, unsigned char* a_lo,
+                                                     int row0, int lane) {
+  const int q = lane >> 3, k = lane & 7;
+  const uint32_t row_units = (uint32_t)R * 8u;
+#pragma unroll 1
+  for (int g = 0; g < 8; ++g) {
+    const int src = 4 * g + q;
+    float4 v[12];
+    float fx[3], fy[3];
+#pragma unroll
+    for (int pl = 0; pl < 3; ++pl) {
+      const uint32_t o = __shfl_sync(kFull, tp.o[pl], src);
+      fx[pl] = __shfl_sync(kFull, tp.fx[pl], src);
+      fy[pl] = __shfl_sync(kFull, tp.fy[pl], src);
+      const uint32_t a00 = (o & 0xFFFFFFF8u) | (uint32_t)k;
+      const uint32_t dx = (o & 1u) << 3;
+      const uint32_t dy = (o & 2u) ? row_units : 0u;
+      const uint32_t a10 = a00 + dy;
+      v[4 * pl + 0] = ldg_nc_volatile(texel_ptr(planes_b, a00));
+      v[4 * pl + 1] = ldg_nc_volatile(texel_ptr(planes_b, a00 + dx));
+      v[4 * pl + 2] = ldg_nc_volatile(texel_ptr(planes_b, a10));
+      v[4 * pl + 3] = ldg_nc_volatile(texel_ptr(planes_b, a10 + dx));
+    }
     float2 lo = make_float2(0.f, 0.f), hi = make_float2(0.f, 0.f);
 #pragma unroll
     for (int pl = 0; pl < 3; ++pl) {

@@ -11,6 +11,7 @@
 #include "nfi_forward.cuh"
 #include "nfi_forward_tc.cuh"
 #include "nfi_forward_ws.cuh"
+#include "nfi_forward_pipe.cuh"
 #include "nfi_render.h"
 
 #define NFI_STR_(x) #x
@@ -90,6 +91,8 @@ bool tc_supported(const nfi_render_params* p) {
   if (p->extra_mode == NFI_EXTRA_SEMANTICS) return false;
   const int mode = p->mlp_mode & 0xff;
   const int smax = (mode == NFI_MLP_TC_WARPSPEC) ? 128 : 64;  // per-ray columns in tile memory
+  if ((mode == NFI_MLP_TC_PIPE || mode == NFI_MLP_AUTO) && (p->num_samples > 64 || p->num_samples % 4))
+    return false;  // pipelined kernel: 2 samples per lane in the resampler, float4 jitter loads
   if (p->fine_sampling && p->num_samples > smax) return false;
   return true;
 }
@@ -127,7 +130,37 @@ int launch_fwd_extra(const nfi_render_params& p, size_t smem, cudaStream_t st) {
 template <int NP, int EX>
 int launch_fwd_tc_fine(const nfi_render_params& p, const unsigned char* wimg, float* scratch,
                        cudaStream_t st) {
-  const bool lockstep = (p.mlp_mode & 0xff) != NFI_MLP_TC_WARPSPEC;
+  const int mode = p.mlp_mode & 0xff;
+  if (mode == NFI_MLP_TC_PIPE || mode == NFI_MLP_AUTO) {
+    // persistent pipelined kernel: one CTA per SM, tiles strided over the grid
+    int dev = 0, sms = 0;
+    NFI_CUDA(cudaGetDevice(&dev));
+    NFI_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    size_t grid = num_ctas(&p);
+    if (grid > (size_t)sms) grid = sms;
+    if (grid > kMaxPersistentCtas) grid = kMaxPersistentCtas;
+#define NFI_PIPE(FINE, DBG)                                                                  \
+  do {                                                                                       \
+    auto k = nfi::render_forward_pipe<NP, EX, FINE, 2, DBG>;                                 \
+    NFI_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize,            \
+                                  nfi::PipeCfg<2>::kSmBytes));                               \
+    k<<<(unsigned)grid, nfi::PipeCfg<2>::kThreadsTotal, nfi::PipeCfg<2>::kSmBytes, st>>>(    \
+        p, wimg, scratch);                                                                   \
+  } while (0)
+    if constexpr (NP == 12 && EX == 0) {
+      if ((p.mlp_mode & 0x1000) && p.fine_sampling) {  // phase-timer build (tools/phase_times_pipe.py)
+        NFI_PIPE(true, true);
+        NFI_CUDA(cudaGetLastError());
+        return 0;
+      }
+    }
+    if (p.fine_sampling) NFI_PIPE(true, false);
+    else NFI_PIPE(false, false);
+#undef NFI_PIPE
+    NFI_CUDA(cudaGetLastError());
+    return 0;
+  }
+  const bool lockstep = mode != NFI_MLP_TC_WARPSPEC;
   if (lockstep) {  // render_forward_tc: 4 tile groups per 512-thread CTA, one CTA per 2x2 tiles
     const size_t tx = (p.width + nfi::kTileW - 1) / nfi::kTileW;
     const size_t ty = (p.height + nfi::kTileH - 1) / nfi::kTileH;
@@ -170,7 +203,12 @@ int launch_fwd_tc(const nfi_render_params& p, int np, cudaStream_t st) {
   unsigned char* wimg = (unsigned char*)p.workspace;
   float* scratch = (float*)(wimg + kWeightImageBytes);
   const int nout = 1 + (p.n_attention > 0 ? p.n_attention : 3);
-  nfi::prep_weight_image<<<1, 256, 0, st>>>(p.w1, p.b1, p.w2, p.b2, nout, wimg);
+  const int wmode = p.mlp_mode & 0xff;
+  const bool pipe = (wmode == NFI_MLP_TC_PIPE || wmode == NFI_MLP_AUTO);
+  nfi::prep_weight_image<<<1, 256, 0, st>>>(p.w1, p.b1, p.w2, p.b2, nout, wimg,
+                                            pipe ? nfi::kLog2e : 1.f,
+                                            (pipe && p.n_attention > 0) ? nfi::kPadLogit : 0.f,
+                                            (pipe && p.n_attention > 0) ? nfi::kLog2e : 1.f);
   NFI_CUDA(cudaGetLastError());
   const bool coords = p.extra_mode == NFI_EXTRA_COORDS;
   switch (np) {
@@ -316,10 +354,12 @@ int nfi_render_forward(const nfi_render_params* params, void* stream) {
   const int np = nout_pad_of(params);
   cudaStream_t st = (cudaStream_t)stream;
   const int mode = p.mlp_mode & 0xff;
-  if ((mode == NFI_MLP_TC_3XTF32 || mode == NFI_MLP_TC_WARPSPEC) && !tc_supported(params))
+  if ((mode == NFI_MLP_TC_3XTF32 || mode == NFI_MLP_TC_WARPSPEC || mode == NFI_MLP_TC_PIPE) &&
+      !tc_supported(params))
     return fail("tensor-core modes need S <= 64 (warp-specialised: 128) with fine sampling and "
                 "no semantics output; use NFI_MLP_AUTO");
   const bool want_tc = mode == NFI_MLP_TC_3XTF32 || mode == NFI_MLP_TC_WARPSPEC ||
+                       mode == NFI_MLP_TC_PIPE ||
                        (mode == NFI_MLP_AUTO && tc_supported(params));
   if (want_tc || p.fine_sampling) {
     if (!p.workspace || p.workspace_bytes < nfi_render_workspace_bytes(params))
@@ -355,7 +395,7 @@ int nfi_decoder_forward(const float* features, int64_t n_points, const float* w1
   }
   if (!workspace) return fail("decoder (tensor-core mode) needs a 32 KiB workspace");
   unsigned char* wimg = (unsigned char*)workspace;
-  nfi::prep_weight_image<<<1, 256, 0, st>>>(w1, b1, w2, b2, nout, wimg);
+  nfi::prep_weight_image<<<1, 256, 0, st>>>(w1, b1, w2, b2, nout, wimg, 1.f, 0.f, 1.f);
   NFI_CUDA(cudaGetLastError());
   const long long tiles = (n_points + 127) / 128;
   int dev = 0, sms = 148;
@@ -386,10 +426,15 @@ int nfi_render_backward(const nfi_render_params* params, const nfi_render_grads*
 }
 
 int nfi_render_forward_host(const nfi_render_params* hp, int32_t device) {
+  // Host buffers in, host buffers out.  The batch is cut into chunks of images
+  // (images are independent: SURVEY.md section 8e) and pipelined over two
+  // streams: while chunk c is re-laid-out and rendered, chunk c+1's planes and
+  // noise are already crossing PCIe, and chunk c-1's rgb/depth/mask go back.
   if (hp == nullptr) return fail("params is NULL");
   NFI_CUDA(cudaSetDevice(device));
-  cudaStream_t st;
+  cudaStream_t st = nullptr, cp = nullptr;
   NFI_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+  NFI_CUDA(cudaStreamCreateWithFlags(&cp, cudaStreamNonBlocking));
   cudaMemPool_t pool;
   NFI_CUDA(cudaDeviceGetDefaultMemPool(&pool, device));
   uint64_t keep = UINT64_MAX;
@@ -399,8 +444,8 @@ int nfi_render_forward_host(const nfi_render_params* hp, int32_t device) {
   const size_t B = hp->batch, H = hp->height, W = hp->width, S = hp->num_samples;
   const size_t R = hp->plane_res, A = hp->n_attention;
   const size_t nout = 1 + (A > 0 ? A : 3);
-  const size_t n_rays = B * H * W;
-  void* to_free[32];
+  const size_t rays_img = H * W, n_rays = B * rays_img;
+  void* to_free[40];
   int n_free = 0;
   int rc = 0;
   auto dalloc = [&](size_t bytes) -> float* {
@@ -409,56 +454,108 @@ int nfi_render_forward_host(const nfi_render_params* hp, int32_t device) {
     to_free[n_free++] = q;
     return (float*)q;
   };
-  auto up = [&](const float* h, size_t n) -> const float* {
+  auto up = [&](const float* h, size_t n) -> const float* {  // small tensors: compute stream
     if (h == nullptr) return nullptr;
     float* q = dalloc(n * sizeof(float));
     if (q) cudaMemcpyAsync(q, h, n * sizeof(float), cudaMemcpyHostToDevice, st);
     return q;
   };
-  const size_t plane_elems = B * 3 * R * R * 32;
-  const float* planes_cf = up(hp->planes, plane_elems);
-  float* planes_cl = dalloc(plane_elems * sizeof(float));
+  // chunk = 8 images: 128 CTAs of the lockstep kernel, ~34 MB per image on the wire
+  const size_t CB = B < 8 ? B : 8;
+  const size_t n_chunks = (B + CB - 1) / CB;
+  const size_t plane_img = 3 * R * R * 32;
+  float* planes_cf = dalloc(B * plane_img * sizeof(float));
+  float* planes_cl = dalloc(B * plane_img * sizeof(float));
+  const bool has_nt = hp->noise_mode == NFI_NOISE_EXPLICIT && hp->noise_t;
+  const bool has_nu = has_nt && hp->fine_sampling && hp->noise_u;
+  float* noise_t = has_nt ? dalloc(n_rays * S * sizeof(float)) : nullptr;
+  float* noise_u = has_nu ? dalloc(n_rays * S * sizeof(float)) : nullptr;
   d.w1 = up(hp->w1, 64 * 32);
   d.b1 = up(hp->b1, 64);
   d.w2 = up(hp->w2, nout * 64);
   d.b2 = up(hp->b2, nout);
-  d.palette = up(hp->palette, B * A * 3);
+  const float* palette = up(hp->palette, B * A * 3);
   d.beta = up(hp->beta, 1);
   d.alpha = up(hp->alpha, 1);
-  d.c2w = up(hp->c2w, B * 16);
-  d.focal = up(hp->focal, B);
-  d.center = up(hp->center, B * 2);
-  d.bbox = up(hp->bbox, B * 4);
-  d.noise_t = up(hp->noise_t, n_rays * S);
-  d.noise_u = hp->fine_sampling ? up(hp->noise_u, n_rays * S) : nullptr;
+  const float* c2w = up(hp->c2w, B * 16);
+  const float* focal = up(hp->focal, B);
+  const float* center = up(hp->center, B * 2);
+  const float* bbox = up(hp->bbox, B * 4);
   const size_t ne = hp->extra_mode == NFI_EXTRA_COORDS ? 3 : (hp->extra_mode ? A : 0);
-  d.rgb = dalloc(n_rays * 3 * sizeof(float));
-  d.depth = dalloc(n_rays * sizeof(float));
-  d.mask = dalloc(n_rays * sizeof(float));
-  d.extra = ne ? dalloc(n_rays * ne * sizeof(float)) : nullptr;
+  float* rgb = dalloc(n_rays * 3 * sizeof(float));
+  float* depth = dalloc(n_rays * sizeof(float));
+  float* mask = dalloc(n_rays * sizeof(float));
+  float* extra = ne ? dalloc(n_rays * ne * sizeof(float)) : nullptr;
   d.normals = nullptr;
   d.z_fine = nullptr;
-  d.planes = planes_cl;
+  d.batch = (int32_t)CB;
   d.workspace_bytes = nfi_render_workspace_bytes(&d);
   d.workspace = dalloc(d.workspace_bytes);
-  if (!planes_cf || !planes_cl || !d.rgb || !d.depth || !d.mask || !d.workspace) {
-    rc = fail("device allocation failed");
+  cudaEvent_t ready[64];
+  size_t n_events = 0;
+  if (!planes_cf || !planes_cl || !rgb || !depth || !mask || !d.workspace || n_chunks > 64 ||
+      (has_nt && !noise_t) || (has_nu && !noise_u)) {
+    rc = fail(n_chunks > 64 ? "batch too large for the host entry point (max 512 images)"
+                            : "device allocation failed");
   } else {
-    rc = nfi_planes_to_channel_last(planes_cf, planes_cf + 32 * R * R, planes_cf + 64 * R * R,
-                                    (int64_t)(96 * R * R), (int32_t)B, (int32_t)R, planes_cl, st);
-    if (!rc) rc = nfi_render_forward(&d, st);
-    if (!rc) {
-      cudaMemcpyAsync(hp->rgb, d.rgb, n_rays * 3 * sizeof(float), cudaMemcpyDeviceToHost, st);
-      cudaMemcpyAsync(hp->depth, d.depth, n_rays * sizeof(float), cudaMemcpyDeviceToHost, st);
-      cudaMemcpyAsync(hp->mask, d.mask, n_rays * sizeof(float), cudaMemcpyDeviceToHost, st);
-      if (ne && hp->extra)
-        cudaMemcpyAsync(hp->extra, d.extra, n_rays * ne * sizeof(float), cudaMemcpyDeviceToHost,
-                        st);
+    // the copy stream may only touch the buffers once their allocation (on st) is done
+    cudaEvent_t alloc_done;
+    NFI_CUDA(cudaEventCreateWithFlags(&alloc_done, cudaEventDisableTiming));
+    cudaEventRecord(alloc_done, st);
+    cudaStreamWaitEvent(cp, alloc_done, 0);
+    cudaEventDestroy(alloc_done);
+    for (size_t c = 0; c < n_chunks && !rc; ++c) {
+      const size_t b0 = c * CB, nb = (b0 + CB <= B) ? CB : B - b0;
+      cudaMemcpyAsync(planes_cf + b0 * plane_img, hp->planes + b0 * plane_img,
+                      nb * plane_img * sizeof(float), cudaMemcpyHostToDevice, cp);
+      if (has_nt)
+        cudaMemcpyAsync(noise_t + b0 * rays_img * S, hp->noise_t + b0 * rays_img * S,
+                        nb * rays_img * S * sizeof(float), cudaMemcpyHostToDevice, cp);
+      if (has_nu)
+        cudaMemcpyAsync(noise_u + b0 * rays_img * S, hp->noise_u + b0 * rays_img * S,
+                        nb * rays_img * S * sizeof(float), cudaMemcpyHostToDevice, cp);
+      cudaEventCreateWithFlags(&ready[c], cudaEventDisableTiming);
+      n_events = c + 1;
+      cudaEventRecord(ready[c], cp);
+      cudaStreamWaitEvent(st, ready[c], 0);
+      nfi_render_params q = d;
+      q.batch = (int32_t)nb;
+      q.planes = planes_cl + b0 * plane_img;
+      q.palette = palette ? palette + b0 * A * 3 : nullptr;
+      q.c2w = c2w + b0 * 16;
+      q.focal = focal ? focal + b0 : nullptr;
+      q.center = center ? center + b0 * 2 : nullptr;
+      q.bbox = bbox ? bbox + b0 * 4 : nullptr;
+      q.noise_t = has_nt ? noise_t + b0 * rays_img * S : nullptr;
+      q.noise_u = has_nu ? noise_u + b0 * rays_img * S : nullptr;
+      q.rgb = rgb + b0 * rays_img * 3;
+      q.depth = depth + b0 * rays_img;
+      q.mask = mask + b0 * rays_img;
+      q.extra = extra ? extra + b0 * rays_img * ne : nullptr;
+      const float* cf = planes_cf + b0 * plane_img;
+      rc = nfi_planes_to_channel_last(cf, cf + 32 * R * R, cf + 64 * R * R, (int64_t)(96 * R * R),
+                                      (int32_t)nb, (int32_t)R, planes_cl + b0 * plane_img, st);
+      if (!rc) rc = nfi_render_forward(&q, st);
+      if (!rc) {
+        cudaMemcpyAsync(hp->rgb + b0 * rays_img * 3, q.rgb, nb * rays_img * 3 * sizeof(float),
+                        cudaMemcpyDeviceToHost, st);
+        cudaMemcpyAsync(hp->depth + b0 * rays_img, q.depth, nb * rays_img * sizeof(float),
+                        cudaMemcpyDeviceToHost, st);
+        cudaMemcpyAsync(hp->mask + b0 * rays_img, q.mask, nb * rays_img * sizeof(float),
+                        cudaMemcpyDeviceToHost, st);
+        if (ne && hp->extra)
+          cudaMemcpyAsync(hp->extra + b0 * rays_img * ne, q.extra,
+                          nb * rays_img * ne * sizeof(float), cudaMemcpyDeviceToHost, st);
+      }
     }
   }
+  cudaError_t e1 = cudaStreamSynchronize(cp);
   for (int i = 0; i < n_free; ++i) cudaFreeAsync(to_free[i], st);
   cudaError_t e = cudaStreamSynchronize(st);
+  for (size_t c = 0; c < n_events; ++c) cudaEventDestroy(ready[c]);
+  cudaStreamDestroy(cp);
   cudaStreamDestroy(st);
+  if (e == cudaSuccess) e = e1;
   if (!rc && e != cudaSuccess) {
     snprintf(g_err, sizeof(g_err), "render failed: %s", cudaGetErrorString(e));
     rc = 2;

@@ -14,7 +14,7 @@ pytestmark = pytest.mark.gpu
 TOL = 2e-4
 
 
-@pytest.fixture(autouse=True, params=[1, 2, 3], ids=['simt', 'tc', 'tcws'])
+@pytest.fixture(autouse=True, params=[1, 2, 3, 4], ids=['simt', 'tc', 'tcws', 'pipe'])
 def mlp_mode(request):
     """Every test below runs with the fp32 SIMT MLP and with the tcgen05
     3xTF32 MLP (S = 16 keeps the fine pass inside the tensor-core kernel's
@@ -62,7 +62,7 @@ def test_forward_variants(cuda_lib, fine, A, use_sdf):
 
 @pytest.mark.parametrize('mode', ['coords', 'semantics'])
 def test_extra_outputs(cuda_lib, mode, mlp_mode):
-    if mode == 'semantics' and mlp_mode in (2, 3):
+    if mode == 'semantics' and mlp_mode != 1:
         pytest.skip('semantics output runs on the SIMT kernel (NFI_MLP_AUTO falls back)')
     B, H, W, S = 2, 16, 16, 16
     scene, cams = Hh.make_case('p3d_plain', batch=B)
