@@ -332,7 +332,7 @@ def main():
     achieved_tf = flops_launch / (k_ms * 1e-3) / 1e12 if k_ms > 0 else 0.0
     roofline = {
         'bound': 'tensor', 'achieved': achieved_tf, 'peak': pk['tflops'], 'unit': 'TFLOP/s',
-        'frac': achieved_tf / pk['tflops'], 'traffic': TRAFFIC_BYTES_PER_LAUNCH,
+        'frac': achieved_tf / pk['tflops'], 'traffic': TRAFFIC_BYTES_PER_IMAGE * B,
         'kernel': 'render_forward (dominant kernel of the step)', 'kernel_ms': k_ms,
         'kernel_share_of_step': k_ms / ms_step if ms_step > 0 else None,
         'algorithmic_flops_per_launch': flops_launch,
@@ -375,7 +375,9 @@ def main():
                    % world + (', all_gather of [rgb,depth,mask] tiles' if world > 1 else ''),
                    'cache': 'inputs (1.07 GB per GPU) larger than L2; no flush needed',
                    'randomize': True},
-        'clocks': clocks, 'e2e': e2e, 'gpu_launches': 2 * args.steps,
+        'clocks': clocks, 'e2e': e2e,
+        # per step: planes_to_cl_kernel, prep_weight_image, render_forward_pipe
+        'gpu_launches': 3 * args.steps,
         'roofline': roofline, 'cpu_baseline': cpu_baseline, 'parity': parity,
     }
     print(json.dumps(line))
@@ -385,7 +387,8 @@ def main():
 
 # dram__bytes_read.sum + dram__bytes_write.sum of the render kernel from the
 # committed `ncu --set full` capture (profiles/), per launch; None until captured.
-TRAFFIC_BYTES_PER_LAUNCH = None
+# (269.0 + 118.2) MB for the 8 images of profiles/r1_ncu_v5_pipe_B8.txt; a launch moves this per image
+TRAFFIC_BYTES_PER_IMAGE = (269012736 + 118194688) / 8
 
 if __name__ == '__main__':
     main()

@@ -16,8 +16,8 @@
 //     warpgroup 2   warp 8 issues every layer-1 tcgen05.mma, warp 9 every layer-2
 //                   tcgen05.mma (the ~25-50 cycles an MMA takes to issue are
 //                   nobody else's problem); warps 10-11 idle
-//     warpgroups 3+ P PRODUCER sets of 4 warps; set q gathers the steps
-//                   n = q (mod P) into ITS A stage (A_hi/A_lo, 32 KB, SWIZZLE_128B)
+//     warpgroups 3+ P PRODUCER sets of 4 warps; set q gathers the steps n = q (mod P)
+//                   into A stage n mod (P+1) (A_hi/A_lo, 32 KB, SWIZZLE_128B)
 //
 //   stage   : producers --full[q]--> MMA1 --a_free[q] (tcgen05.commit)--> producers
 //             (a stage is released as soon as the tensor core has READ it; the
@@ -50,22 +50,23 @@ constexpr int kPipeStageBytes = 32768;
 template <int P>
 struct PipeCfg {
   static constexpr int kThreadsTotal = 384 + 128 * P;
+  static constexpr int kStages = P + 1;  // one spare: a set never waits for its own MMA
   static constexpr int kSmA = 25600;
-  static constexpr int kSmPal = kSmA + P * kPipeStageBytes;
+  static constexpr int kSmPal = kSmA + kStages * kPipeStageBytes;
   static constexpr int kSmFrac = kSmPal + 48 * 4;  // s / S for s < 64 (one IEEE division each)
   static constexpr int kSmBars = kSmFrac + 64 * 4;
   // full[P], a_free[P], d1_full[3], h_ready[3], d2_full[3], slot_free[3], cw_ready, zf_ready,
   // weights
-  static constexpr int kNumBars = 2 * P + 4 * kPipeSlots + 3;
+  static constexpr int kNumBars = 2 * kStages + 4 * kPipeSlots + 3;
   static constexpr int kSmTmemPtr = kSmBars + kNumBars * 8;
   static constexpr int kSmBytes = kSmTmemPtr + 16;
   // setmaxnreg moves registers inside the CTA's launch allocation (threads x launch regs):
-  //   P = 2: 640 x 96 = 61440 = 128 x (104 + 112 + 24) + 256 x 120 (12 texel loads in flight
-  //   per producer warp need ~110 registers: 48 data + 64-bit addresses + taps + ray)
+  //   P = 3: 768 x 80 = 61440 = 128 x (88 + 80 + 24) + 384 x 96 (12 texel loads in flight per
+  //   producer warp: 48 data registers + 64-bit addresses + taps)
 #ifndef NFI_ACT_REGS
-#define NFI_ACT_REGS 104
-#define NFI_SHADE_REGS 112
-#define NFI_PROD_REGS 120
+#define NFI_ACT_REGS 88
+#define NFI_SHADE_REGS 80
+#define NFI_PROD_REGS 96
 #endif
   static constexpr int kActRegs = NFI_ACT_REGS;
   static constexpr int kShadeRegs = NFI_SHADE_REGS;
@@ -314,21 +315,26 @@ render_forward_pipe(const nfi_render_params p, const unsigned char* __restrict__
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   unsigned char* base = smem_raw;
   const int tid = threadIdx.x, lane = tid & 31;
-  // 0 activation, 1 shading, 2 MMA issuers, 3.. producer sets
-  const int wg = __shfl_sync(kFull, tid >> 7, 0);
+  // Role by warpgroup.  The arbiter favours high warp ids, so the two consumer roles --
+  // one warp each per sub-partition, nothing to hide their latency behind -- sit above the
+  // producers: hardware wg 0..P-1 producer sets, P MMA issuers, P+1 shading, P+2 activation.
+  // `wg` below is the logical role: 0 activation, 1 shading, 2 MMA issuers, 3.. producer sets.
+  const int hw_wg = __shfl_sync(kFull, tid >> 7, 0);
+  const int wg = (hw_wg < P) ? hw_wg + 3 : (P + 2 - hw_wg);
   const int gt = tid & 127;                        // row of the tile = ray = TMEM lane
   const int wig = __shfl_sync(kFull, gt >> 5, 0);  // warp in warpgroup = TMEM lane quadrant
   const int S = p.num_samples;
 
   uint64_t* bars = reinterpret_cast<uint64_t*>(base + Cfg::kSmBars);
-  uint64_t* full = bars;                         // [P]  stage gathered            (4 warps)
-  uint64_t* a_free = full + P;                   // [P]  stage read by the tensor core (commit)
-  uint64_t* d1_full = a_free + P;                // [3]  layer-1 accumulator ready (commit)
-  uint64_t* h_ready = d1_full + kPipeSlots;      // [3]  H_hi/H_lo in TMEM         (128 threads)
+  constexpr int NS = Cfg::kStages;
+  uint64_t* full = bars;                         // [NS] stage gathered            (4 warps)
+  uint64_t* a_free = full + NS;                  // [NS] stage read by the tensor core (commit)
+  uint64_t* d1_full = a_free + NS;               // [3]  layer-1 accumulator ready (commit)
+  uint64_t* h_ready = d1_full + kPipeSlots;      // [3]  H_hi/H_lo in TMEM         (4 warps)
   uint64_t* d2_full = h_ready + kPipeSlots;      // [3]  layer-2 accumulator ready (commit)
-  uint64_t* slot_free = d2_full + kPipeSlots;    // [3]  D2 read                   (128 threads)
-  uint64_t* cw_ready = slot_free + kPipeSlots;   //      coarse weights of the tile written (128)
-  uint64_t* zf_ready = cw_ready + 1;             //      fine depths of the tile written (256)
+  uint64_t* slot_free = d2_full + kPipeSlots;    // [3]  D2 read                   (4 warps)
+  uint64_t* cw_ready = slot_free + kPipeSlots;   //      coarse weights of the tile written (4 warps)
+  uint64_t* zf_ready = cw_ready + 1;             //      fine depths of the tile written (8 warps)
   uint64_t* wbar = zf_ready + 1;                 //      weight image landed
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(base + Cfg::kSmTmemPtr);
   const float* b1s = reinterpret_cast<const float*>(base + kWiB1);
@@ -339,18 +345,20 @@ render_forward_pipe(const nfi_render_params p, const unsigned char* __restrict__
 
   if (tid == 0) {
     if (tc::smem_u32(base) & 1023u) __trap();
-    for (int i = 0; i < P; ++i) {
+    for (int i = 0; i < NS; ++i) {
       tc::mbar_init(&full[i], 4);
       tc::mbar_init(&a_free[i], 1);
     }
     for (int i = 0; i < kPipeSlots; ++i) {
       tc::mbar_init(&d1_full[i], 1);
-      tc::mbar_init(&h_ready[i], kThreads);
+      // consumer barriers count WARPS: a warp-wide mbarrier.arrive is 32 serialised
+      // shared-memory atomics on one word (L1 data-pipe wavefronts the gather needs)
+      tc::mbar_init(&h_ready[i], kWarps);
       tc::mbar_init(&d2_full[i], 1);
-      tc::mbar_init(&slot_free[i], kThreads);
+      tc::mbar_init(&slot_free[i], kWarps);
     }
-    tc::mbar_init(cw_ready, kThreads);
-    tc::mbar_init(zf_ready, 2 * kThreads);
+    tc::mbar_init(cw_ready, kWarps);
+    tc::mbar_init(zf_ready, 2 * kWarps);
     tc::mbar_init(wbar, 1);
     tc::fence_mbar_init();
   }
@@ -458,7 +466,6 @@ render_forward_pipe(const nfi_render_params p, const unsigned char* __restrict__
     else
       asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(Cfg::kProducerRegs));
     const int set = wg - 3;
-    unsigned char* const stage = base + Cfg::kSmA + set * kPipeStageBytes;
     uint32_t n = 0;        // ring position at the start of the pass, identical in every role
     uint32_t tile_it = 0;  // tiles done by this CTA (parity of zf_ready)
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++tile_it) {
@@ -487,11 +494,12 @@ render_forward_pipe(const nfi_render_params p, const unsigned char* __restrict__
         };
         float nxt = fetch(s);
         for (; s < S; s += P) {
-          const uint32_t u = (n + (uint32_t)s) / P;
+          const uint32_t st = (n + (uint32_t)s) % NS, u = (n + (uint32_t)s) / NS;
+          unsigned char* const stage = base + Cfg::kSmA + st * kPipeStageBytes;
           const float cur = nxt;
           nxt = fetch(s + P);
           if (DBG && dbg_time) tprev = clock64();
-          tc::mbar_wait(&a_free[set], (u & 1) ^ 1);  // tensor core has read the previous fill
+          tc::mbar_wait(&a_free[st], (u & 1) ^ 1);  // tensor core has read the previous fill
           NFI_T(0)
           float t;
           if (pass == 0)
@@ -515,7 +523,7 @@ render_forward_pipe(const nfi_render_params p, const unsigned char* __restrict__
           NFI_T(2)
           tc::fence_async_smem();
           __syncwarp();
-          if (lane == 0) mbar_arrive(&full[set]);
+          if (lane == 0) mbar_arrive(&full[st]);
           NFI_T(3)
           if (DBG && dbg_time) tacc[9] += 1;
         }
@@ -532,24 +540,24 @@ render_forward_pipe(const nfi_render_params p, const unsigned char* __restrict__
       const uint64_t dsc_w1_hi = tc::umma_desc_sw128(base_s + kWiW1Hi);
       const uint64_t dsc_w1_lo = tc::umma_desc_sw128(base_s + kWiW1Lo);
       const uint64_t dsc_a0 = tc::umma_desc_sw128(base_s + Cfg::kSmA);
-      uint32_t set = 0, u = 0, sl = 0, v = 0;
+      uint32_t st = 0, u = 0, sl = 0, v = 0;
       for (uint32_t m = 0; m < total_steps; ++m) {
         if (DBG && dbg_time && tprev == 0) tprev = clock64();
-        tc::mbar_wait(&full[set], u & 1);
+        tc::mbar_wait(&full[st], u & 1);
         NFI_T(0)
         tc::mbar_wait(&slot_free[sl], (v & 1) ^ 1);
         NFI_T(1)
         if (elect_one()) {
           tc::tc_fence_after();
-          const uint64_t dsc_a = dsc_a0 + (uint64_t)set * (kPipeStageBytes >> 4);
+          const uint64_t dsc_a = dsc_a0 + (uint64_t)st * (kPipeStageBytes >> 4);
           tc::issue_layer1_d(tmem_base + sl * kPipeSlotCols, dsc_a, dsc_a + (16384 >> 4),
                              dsc_w1_hi, dsc_w1_lo);
           tc::umma_commit(&d1_full[sl]);
-          tc::umma_commit(&a_free[set]);
+          tc::umma_commit(&a_free[st]);
         }
         __syncwarp();
         NFI_T(2)
-        if (++set == P) { set = 0; ++u; }
+        if (++st == NS) { st = 0; ++u; }
         if (++sl == kPipeSlots) { sl = 0; ++v; }
       }
       if (DBG && dbg_time)
@@ -614,7 +622,8 @@ render_forward_pipe(const nfi_render_params p, const unsigned char* __restrict__
         tc::tmem_wait_st();
       }
       tc::tc_fence_before();
-      mbar_arrive(&h_ready[sl]);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&h_ready[sl]);
       if (++sl == kPipeSlots) { sl = 0; ++v; }
       NFI_T(1)
       if (DBG && dbg_time) tacc[9] += 1;
@@ -638,7 +647,8 @@ render_forward_pipe(const nfi_render_params p, const unsigned char* __restrict__
         NFI_T(3)
         resample_rows(16, r.tnear, r.tfar, ray, valid);
         __threadfence_block();
-        mbar_arrive(zf_ready);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(zf_ready);
         NFI_T(4)
         for (int s = 0; s < S; ++s) activate();
       }
@@ -690,7 +700,8 @@ render_forward_pipe(const nfi_render_params p, const unsigned char* __restrict__
         float o16[16];
         tc::tmem_ld16(d2, o16);
         tc::tc_fence_before();
-        mbar_arrive(&slot_free[sl]);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&slot_free[sl]);
         if (++sl == kPipeSlots) { sl = 0; ++v; }
         const float wx = r.ox + r.dx * t, wy = r.oy + r.dy * t, wz = r.oz + r.dz * t;
         const float x0 = wx * inv_range, x1 = wy * inv_range, x2 = wz * inv_range;
@@ -761,12 +772,14 @@ render_forward_pipe(const nfi_render_params p, const unsigned char* __restrict__
       if (FINE) {
         sc_w[(S - 1) * kThreads + gt] = 0.f;
         __threadfence_block();
-        mbar_arrive(cw_ready);  // the activation group may resample its half of the rows
+        __syncwarp();
+        if (lane == 0) mbar_arrive(cw_ready);  // the activation group may resample its half
         tc::mbar_wait(cw_ready, tile_it & 1);
         NFI_T(4)
         resample_rows(0, r.tnear, r.tfar, ray, valid);
         __threadfence_block();
-        mbar_arrive(zf_ready);  // (with the activation group's 128) producers may start
+        __syncwarp();
+        if (lane == 0) mbar_arrive(zf_ready);  // (with the activation group's 4) producers may start
         tc::mbar_wait(zf_ready, tile_it & 1);
         NFI_T(5)
 

@@ -141,10 +141,10 @@ int launch_fwd_tc_fine(const nfi_render_params& p, const unsigned char* wimg, fl
     if (grid > kMaxPersistentCtas) grid = kMaxPersistentCtas;
 #define NFI_PIPE(FINE, DBG)                                                                  \
   do {                                                                                       \
-    auto k = nfi::render_forward_pipe<NP, EX, FINE, 2, DBG>;                                 \
+    auto k = nfi::render_forward_pipe<NP, EX, FINE, 3, DBG>;                                 \
     NFI_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize,            \
-                                  nfi::PipeCfg<2>::kSmBytes));                               \
-    k<<<(unsigned)grid, nfi::PipeCfg<2>::kThreadsTotal, nfi::PipeCfg<2>::kSmBytes, st>>>(    \
+                                  nfi::PipeCfg<3>::kSmBytes));                               \
+    k<<<(unsigned)grid, nfi::PipeCfg<3>::kThreadsTotal, nfi::PipeCfg<3>::kSmBytes, st>>>(    \
         p, wimg, scratch);                                                                   \
   } while (0)
     if constexpr (NP == 12 && EX == 0) {
