@@ -12,6 +12,7 @@
 #include "nfi_forward_tc.cuh"
 #include "nfi_forward_ws.cuh"
 #include "nfi_forward_pipe.cuh"
+#include "nfi_backward_pipe.cuh"
 #include "nfi_render.h"
 
 #define NFI_STR_(x) #x
@@ -77,6 +78,7 @@ size_t num_ctas(const nfi_render_params* p) {
 }
 
 constexpr size_t kWeightImageBytes = 32768;  // workspace header (nfi::kWiBytes rounded up)
+constexpr size_t kBackwardWorkspaceBytes = 65536;  // forward + backward weight images
 
 constexpr size_t kMaxPersistentCtas = 160;  // >= SM count of any sm_100 part (B200: 148)
 
@@ -422,7 +424,56 @@ int nfi_render_backward(const nfi_render_params* params, const nfi_render_grads*
                         void* stream) {
   if (int rc = check_params(params)) return rc;
   if (grads == nullptr || grads->g_rgb == nullptr) return fail("grads->g_rgb missing");
-  return nfi::launch_backward(*params, *grads, (cudaStream_t)stream, g_err, sizeof(g_err));
+  const nfi_render_params& p = *params;
+  const nfi_render_grads& g = *grads;
+  cudaStream_t st = (cudaStream_t)stream;
+  // Tensor-core backward (nfi_backward_pipe.cuh): frozen decoder weights (the inversion
+  // setting, run.py:628-629), no semantics output, S within the pipelined kernels' envelope,
+  // and a workspace for the two weight images.  Everything else: render_backward_simt.
+  const int mode = p.mlp_mode & 0xff;
+  const bool wgrad = g.grad_w1 || g.grad_b1 || g.grad_w2 || g.grad_b2;
+  const bool tc_ok = !wgrad && mode != NFI_MLP_FP32_SIMT && p.extra_mode != NFI_EXTRA_SEMANTICS &&
+                     p.num_samples <= 64 && p.num_samples % 4 == 0 && p.workspace != nullptr &&
+                     p.workspace_bytes >= kBackwardWorkspaceBytes &&
+                     (!p.fine_sampling || p.z_fine != nullptr) && g.out_rgb && g.out_mask &&
+                     (!g.g_extra || g.out_extra) &&
+                     ((g.grad_origins == nullptr) == (g.grad_dirs == nullptr));
+  if (tc_ok) {
+    unsigned char* wimg = (unsigned char*)p.workspace;
+    const int nout = 1 + (p.n_attention > 0 ? p.n_attention : 3);
+    nfi::prep_weight_image<<<1, 256, 0, st>>>(p.w1, p.b1, p.w2, p.b2, nout, wimg, nfi::kLog2e,
+                                              p.n_attention > 0 ? nfi::kPadLogit : 0.f,
+                                              p.n_attention > 0 ? nfi::kLog2e : 1.f);
+    nfi::prep_weight_image_bwd<<<1, 256, 0, st>>>(p.w1, p.w2, nout, wimg + 32768);
+    NFI_CUDA(cudaGetLastError());
+    int dev = 0, sms = 0;
+    NFI_CUDA(cudaGetDevice(&dev));
+    NFI_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    size_t grid = num_ctas(&p);
+    if (grid > (size_t)sms) grid = sms;
+    const bool cam = g.grad_origins != nullptr;
+    const bool coords = p.extra_mode == NFI_EXTRA_COORDS && g.g_extra != nullptr;
+    using Cfg = nfi::BwdCfg<2>;
+#define NFI_BWD(NP, EX, CAM)                                                               \
+  do {                                                                                     \
+    auto k = nfi::render_backward_pipe<NP, EX, CAM, 2>;                                    \
+    NFI_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize,          \
+                                  Cfg::kSmBytes));                                         \
+    k<<<(unsigned)grid, Cfg::kThreadsTotal, Cfg::kSmBytes, st>>>(p, g, wimg);              \
+  } while (0)
+#define NFI_BWD_NP(NP)                                                                     \
+  do {                                                                                     \
+    if (coords) { if (cam) NFI_BWD(NP, 1, true); else NFI_BWD(NP, 1, false); }             \
+    else { if (cam) NFI_BWD(NP, 0, true); else NFI_BWD(NP, 0, false); }                    \
+  } while (0)
+    const int np = nout_pad_of(params);
+    if (np == 4) NFI_BWD_NP(4); else if (np == 12) NFI_BWD_NP(12); else NFI_BWD_NP(16);
+#undef NFI_BWD_NP
+#undef NFI_BWD
+    NFI_CUDA(cudaGetLastError());
+    return 0;
+  }
+  return nfi::launch_backward(*params, *grads, st, g_err, sizeof(g_err));
 }
 
 int nfi_render_forward_host(const nfi_render_params* hp, int32_t device) {

@@ -248,6 +248,9 @@ class FusedTriplaneRender(torch.autograd.Function):
             p.rgb, p.depth, p.mask = _ptr(rgb), _ptr(mask), _ptr(mask)  # unused
             p.extra = _ptr(extra)
             p.z_fine = _ptr(ctx.z_fine)
+            # the tensor-core backward keeps its two weight images here (64 KiB)
+            ws = torch.empty(65536, dtype=torch.uint8, device=dev)
+            p.workspace, p.workspace_bytes = _ptr(ws), 65536
             _lib.check(lib.nfi_render_backward(ctypes.byref(p), ctypes.byref(g), stream))
             gplanes = planes_from_channel_last(gp_cl) if n_planes else None
             gc2w = gfocal = gcenter = gbbox = None

@@ -137,6 +137,57 @@ def test_backward_matches_oracle_autograd(cuda_lib, case):
         assert err < 2e-3, (n, err)
 
 
+@pytest.mark.parametrize('case', ['p3d_bbox', 'cub_ortho', 'chairs_white_center'])
+def test_backward_frozen_decoder_matches_oracle_autograd(cuda_lib, case):
+    """The inversion setting (run.py:628-629: decoder frozen): gradients to the planes,
+    palette, beta / alpha and cameras only.  Under the tensor-core mlp modes this is
+    render_backward_pipe (tcgen05, 3xTF32 for all four GEMMs); under 'simt' the fp32 kernel."""
+    B, H, W, S = 2, 12, 20, 16
+    scene, cams = Hh.make_case(case, batch=B)
+    nt, nu = _noise(29, B, H, W, S)
+    names = ['planes', 'palette', 'beta', 'alpha']
+    cam_names = ['c2w'] + (['focal'] if cams['focal'] is not None else []) + \
+        (['bbox'] if cams['bbox'] is not None else []) + \
+        (['center'] if cams['center'] is not None else [])
+
+    def leaves(dev):
+        sc = {k: (v.detach().clone().to(dev).requires_grad_() if k in names else
+                  (v.to(dev) if torch.is_tensor(v) else v)) for k, v in scene.items()}
+        cm = {k: (v.detach().clone().to(dev).requires_grad_() if k in cam_names else
+                  (v.to(dev) if torch.is_tensor(v) else v)) for k, v in cams.items()}
+        return sc, cm
+
+    sc, cm = leaves('cpu')
+    ref = Hh.run_oracle(sc, cm, H, W, S, nt, nu)
+    gref = _grads((ref['rgb'], ref['mask']), [sc[n] for n in names] + [cm[n] for n in cam_names])
+    sc2, cm2 = leaves('cuda')
+    rgb, depth, mask, _ = Hh.run_cuda(sc2, cm2, H, W, S, nt, nu)
+    gcu = _grads((rgb, mask), [sc2[n] for n in names] + [cm2[n] for n in cam_names])
+    for n, a, b in zip(names + cam_names, gcu, gref):
+        assert a is not None and b is not None, n
+        err = Hh.rel_l2(a.cpu(), b)
+        assert err < 2e-3, (n, err)
+
+
+def test_backward_no_fine_sampling_frozen(cuda_lib):
+    """Coarse-only render (args.fine_sampling False) through the frozen-decoder backward."""
+    B, H, W, S = 1, 16, 16, 16
+    scene, cams = Hh.make_case('p3d_plain', batch=B)
+    nt, _ = _noise(31, B, H, W, S, fine=False)
+    outs = []
+    for dev in ('cpu', 'cuda'):
+        sc = Hh.to_device(scene, dev)
+        cm = Hh.to_device(cams, dev)
+        sc['planes'] = sc['planes'].clone().requires_grad_()
+        if dev == 'cpu':
+            r = Hh.run_oracle(sc, cm, H, W, S, nt, None, fine_sampling=False)
+            rgb, mask = r['rgb'], r['mask']
+        else:
+            rgb, _, mask, _ = Hh.run_cuda(sc, cm, H, W, S, nt, None, fine_sampling=False)
+        outs.append(_grads((rgb, mask), [sc['planes']])[0])
+    assert Hh.rel_l2(outs[1].cpu(), outs[0]) < 2e-3
+
+
 def test_backward_extras_and_frozen_weights(cuda_lib):
     """compute_coords gradient path + the inversion setting (only planes,
     palette and cameras require grad; decoder frozen)."""

@@ -5,6 +5,7 @@ for a in "$@"; do
     tests) timeout 600 python -m pytest tests -m gpu -q -x -k "pipe or golden" 2>&1 | tail -5 > gpurun_out/pytest_pipe.log; cat gpurun_out/pytest_pipe.log;;
     alltests) timeout 900 python -m pytest tests -m gpu -q -x 2>&1 | tail -5 > gpurun_out/pytest_all.log; cat gpurun_out/pytest_all.log;;
     phase) timeout 300 python tools/phase_times_pipe.py 8 > gpurun_out/phase_times.txt 2>&1; head -6 gpurun_out/phase_times.txt;;
+    bwdtests) timeout 600 python -m pytest tests -m gpu -q -x -k "backward" 2>&1 | tail -12 > gpurun_out/pytest_bwd.log; cat gpurun_out/pytest_bwd.log;;
     bwd) timeout 200 python tools/time_backward.py 8 2>&1 | tail -3 > gpurun_out/time_backward.txt; cat gpurun_out/time_backward.txt;;
     ncu_list) timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 60 --csv --log-file gpurun_out/launches.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-e2e > gpurun_out/ncu_list.log 2>&1; tail -12 gpurun_out/launches.csv | cut -c1-220;;
     ncu_full) timeout 500 ncu --set full --clock-control none --import-source on -k regex:render_forward_pipe -s 2 -c 1 -f -o gpurun_out/pipe_full python bench.py --batch 8 --steps 1 --warmup 3 --no-cpu-baseline --no-e2e > gpurun_out/ncu_full.log 2>&1; tail -2 gpurun_out/ncu_full.log | cut -c1-200;;
