@@ -200,6 +200,7 @@ def main():
     ap.add_argument('--batch', type=int, default=CFG['batch'])
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-e2e', action='store_true')
+    ap.add_argument('--no-backward', action='store_true')
     ap.add_argument('--e2e-steps', type=int, default=3)
     ap.add_argument('--mlp-mode', type=lambda x: int(x, 0), default=0)
     args = ap.parse_args()
@@ -286,7 +287,6 @@ def main():
         for k in ('planes', 'w1', 'b1', 'w2', 'b2', 'palette', 'beta', 'alpha'):
             host[k] = pin(scene[k])
         host['c2w'], host['focal'] = pin(cams['c2w']), pin(cams['focal'])
-        host['noise_t'], host['noise_u'] = pin(nt), pin(nu)
         host['rgb'] = torch.empty(B, H, W, 3).pin_memory()
         host['depth'] = torch.empty(B, H, W).pin_memory()
         host['mask'] = torch.empty(B, H, W).pin_memory()
@@ -295,14 +295,16 @@ def main():
         p.plane_res, p.n_attention = CFG['plane_res'], CFG['attention_values']
         p.scene_range = scene['scene_range']
         p.white_background = int(scene['white_background'])
-        p.use_sdf, p.fine_sampling, p.noise_mode = 1, 1, _lib.NOISE_EXPLICIT
+        # The two random draws of the path (torch.rand_like / torch.rand on the device in the
+        # reference, lib/nerf_utils.py:112,201) are generated on the device from a seed:
+        # they are not inputs that exist on the host in the reference either.
+        p.use_sdf, p.fine_sampling, p.noise_mode = 1, 1, _lib.NOISE_PHILOX
+        p.noise_seed = 1234 + rank
         p.mlp_mode = args.mlp_mode
-        for k in ('planes', 'w1', 'b1', 'w2', 'b2', 'palette', 'beta', 'alpha', 'c2w', 'focal',
-                  'noise_t', 'noise_u', 'rgb', 'depth', 'mask'):
+        in_keys = ('planes', 'w1', 'b1', 'w2', 'b2', 'palette', 'beta', 'alpha', 'c2w', 'focal')
+        for k in in_keys + ('rgb', 'depth', 'mask'):
             setattr(p, k, ctypes.c_void_p(host[k].data_ptr()))
-        h2d = sum(host[k].numel() * 4 for k in ('planes', 'w1', 'b1', 'w2', 'b2', 'palette',
-                                                  'beta', 'alpha', 'c2w', 'focal', 'noise_t',
-                                                  'noise_u'))
+        h2d = sum(host[k].numel() * 4 for k in in_keys)
         d2h = sum(host[k].numel() * 4 for k in ('rgb', 'depth', 'mask'))
         _lib.check(lib.nfi_render_forward_host(ctypes.byref(p), local_rank))  # warm-up
         if world > 1:
@@ -315,11 +317,67 @@ def main():
             t = torch.tensor([dt], device=dev)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             dt = t.item()
-        e2e_err = (host['rgb'] - out[0].cpu()).abs().max().item()
+        # same render through the device path with the same device-generated noise
+        nt2, nu2 = torch.empty_like(nt), torch.empty_like(nu)
+        st_ = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+        _lib.check(lib.nfi_fill_uniform(ctypes.c_void_p(nt2.data_ptr()), nt2.numel(),
+                                        p.noise_seed, 0, 0, st_))
+        _lib.check(lib.nfi_fill_uniform(ctypes.c_void_p(nu2.data_ptr()), nu2.numel(),
+                                        p.noise_seed, 1, 0, st_))
+        with torch.no_grad():
+            rgb_d = fused.fused_render(
+                scene['planes'], scene['w1'], scene['b1'], scene['w2'], scene['b2'],
+                scene['palette'], scene['beta'], scene['alpha'], cams['c2w'], cams['focal'],
+                None, None, cfg, H, W, S, nt2, nu2)[0]
+        e2e_err = (host['rgb'] - rgb_d[:B].cpu()).abs().max().item()
+        del nt2, nu2, rgb_d
         e2e = {'value': rays_step / dt, 'unit': UNIT, 'h2d_bytes_per_step': h2d,
                'd2h_bytes_per_step': d2h, 'ms_per_step': dt * 1e3,
                'max_abs_diff_vs_device_path': e2e_err,
-               'api': 'nfi_render_forward_host (C ABI, pinned host buffers)'}
+               'api': 'nfi_render_forward_host (C ABI, pinned host buffers; planes, decoder, '
+                      'palette, cameras H2D every step, the two uniform draws generated on the '
+                      'device from a seed (NFI_NOISE_PHILOX), rgb/depth/mask D2H)'}
+
+    # ------------------------------------------------------------ forward + backward
+    # (the inversion loop's use of the path, run.py:2202-2299: grads to planes, palette and
+    # cameras with the decoder frozen).  Reported beside the headline, not instead of it.
+    fwd_bwd = None
+    if not args.no_backward:
+        planes_g = scene['planes'].detach().clone().requires_grad_()
+        pal_g = scene['palette'].detach().clone().requires_grad_()
+        c2w_g = cams['c2w'].detach().clone().requires_grad_()
+
+        def step_bwd():
+            rgb, depth, mask, _ = fused.fused_render(
+                planes_g, scene['w1'], scene['b1'], scene['w2'], scene['b2'], pal_g,
+                scene['beta'], scene['alpha'], c2w_g, cams['focal'], None, None, cfg, H, W, S,
+                nt, nu)
+            (rgb.square().mean() + mask.mean()).backward()
+            planes_g.grad = pal_g.grad = c2w_g.grad = None
+
+        for _ in range(2):
+            step_bwd()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        b0, b1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        nb = max(2, min(5, args.steps))
+        b0.record()
+        for _ in range(nb):
+            step_bwd()
+        b1.record()
+        torch.cuda.synchronize()
+        ms_b = b0.elapsed_time(b1) / nb
+        if world > 1:
+            t = torch.tensor([ms_b], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms_b = t.item()
+        fwd_bwd = {'value': rays_step / (ms_b * 1e-3), 'unit': UNIT, 'ms_per_step': ms_b,
+                   'what': 'fused_render forward + backward through the autograd.Function '
+                           '(grads to planes, palette, tform_cam2world; decoder frozen), '
+                           'incl. both re-layouts'}
+        del planes_g, pal_g, c2w_g
+        torch.cuda.empty_cache()
 
     if rank != 0:
         if world > 1:
@@ -378,7 +436,7 @@ def main():
         'clocks': clocks, 'e2e': e2e,
         # per step: planes_to_cl_kernel, prep_weight_image, render_forward_pipe
         'gpu_launches': 3 * args.steps,
-        'roofline': roofline, 'cpu_baseline': cpu_baseline, 'parity': parity,
+        'roofline': roofline, 'fwd_bwd': fwd_bwd, 'cpu_baseline': cpu_baseline, 'parity': parity,
     }
     print(json.dumps(line))
     if world > 1:

@@ -35,7 +35,7 @@
 extern "C" {
 #endif
 
-#define NFI_ABI_VERSION 1
+#define NFI_ABI_VERSION 2
 
 #if defined(__GNUC__)
 #define NFI_API __attribute__((visibility("default")))
@@ -57,8 +57,12 @@ enum nfi_extra_mode {
 /* where the two random draws of the path come from */
 enum nfi_noise_mode {
   NFI_NOISE_DETERMINISTIC = 0, /* randomize=False: no jitter, u = linspace(0,1,S) */
-  NFI_NOISE_EXPLICIT = 1       /* noise_t / noise_u tensors (torch.rand_like at
+  NFI_NOISE_EXPLICIT = 1,      /* noise_t / noise_u tensors (torch.rand_like at
                                   lib/nerf_utils.py:112, torch.rand at :201) */
+  NFI_NOISE_PHILOX = 2         /* nfi_render_forward_host only: both draws are generated ON THE
+                                  DEVICE from noise_seed (Philox-4x32-10, as nfi_fill_uniform
+                                  with stream ids 0 / 1) -- where the reference draws them
+                                  too -- instead of crossing PCIe */
 };
 
 /* which implementation of the decoder MLP the kernels use */
@@ -118,6 +122,7 @@ typedef struct nfi_render_params {
   /* ---- scratch ---- */
   void *workspace;        /* >= nfi_render_workspace_bytes(params) */
   size_t workspace_bytes;
+  uint64_t noise_seed;    /* NFI_NOISE_PHILOX */
 } nfi_render_params;
 
 /* Upstream gradients in, parameter gradients out (all device pointers).
@@ -181,6 +186,12 @@ NFI_API int nfi_decoder_forward(const float *features, int64_t n_points, const f
  * tcgen05 (render_backward_pipe); otherwise the fp32 SIMT kernel is used. */
 NFI_API int nfi_render_backward(const nfi_render_params *params, const nfi_render_grads *grads,
                         void *stream);
+
+/* dst[i] = uniform in [0, 1) (24-bit, like torch.rand) from Philox-4x32-10 keyed by `seed`,
+ * counter (offset + i) / 4, sub-stream `stream_id`; i in [0, n), offset % 4 == 0.  The value
+ * of element `offset + i` does not depend on how a buffer is split into calls. */
+NFI_API int nfi_fill_uniform(float *dst, int64_t n, uint64_t seed, uint32_t stream_id,
+                             int64_t offset, void *stream);
 
 /* Same as nfi_render_forward but every pointer in `params` (inputs and
  * outputs; `workspace` ignored) is a HOST pointer; `planes` is the

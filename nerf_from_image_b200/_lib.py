@@ -16,7 +16,7 @@ LIB_PATH = os.path.join(_HERE, 'csrc', 'libnfi_render.so')
 c_float_p = ctypes.POINTER(ctypes.c_float)
 
 EXTRA_NONE, EXTRA_COORDS, EXTRA_SEMANTICS = 0, 1, 2
-NOISE_DETERMINISTIC, NOISE_EXPLICIT = 0, 1
+NOISE_DETERMINISTIC, NOISE_EXPLICIT, NOISE_PHILOX = 0, 1, 2
 MLP_AUTO, MLP_FP32_SIMT, MLP_TC_3XTF32, MLP_TC_WARPSPEC, MLP_TC_PIPE = 0, 1, 2, 3, 4
 
 
@@ -42,6 +42,7 @@ class RenderParams(ctypes.Structure):
         ('mask', ctypes.c_void_p), ('extra', ctypes.c_void_p),
         ('normals', ctypes.c_void_p), ('z_fine', ctypes.c_void_p),
         ('workspace', ctypes.c_void_p), ('workspace_bytes', ctypes.c_size_t),
+        ('noise_seed', ctypes.c_uint64),
     ]
 
 
@@ -79,6 +80,8 @@ EXPORTS = {
                                            ctypes.c_void_p]),
     'nfi_render_forward_host': (ctypes.c_int, [ctypes.POINTER(RenderParams),
                                                ctypes.c_int32]),
+    'nfi_fill_uniform': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int64, ctypes.c_uint64,
+                                        ctypes.c_uint32, ctypes.c_int64, ctypes.c_void_p]),
 }
 
 _lib = None
@@ -117,7 +120,7 @@ def load():
                 fn = getattr(lib, name)
                 fn.restype = restype
                 fn.argtypes = argtypes
-            if lib.nfi_abi_version() != 1:
+            if lib.nfi_abi_version() != 2:
                 raise NfiError('libnfi_render.so ABI version mismatch')
             _lib = lib
     return _lib

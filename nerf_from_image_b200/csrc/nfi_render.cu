@@ -58,6 +58,9 @@ int check_params(const nfi_render_params* p) {
   if (p->noise_mode == NFI_NOISE_EXPLICIT) {
     if (!p->noise_t) return fail("noise_t missing (randomize=True)");
     if (p->fine_sampling && !p->noise_u) return fail("noise_u missing (fine_sampling)");
+  } else if (p->noise_mode == NFI_NOISE_PHILOX) {
+    return fail("NFI_NOISE_PHILOX is a host-entry mode: fill noise_t / noise_u with "
+                "nfi_fill_uniform and pass NFI_NOISE_EXPLICIT");
   } else if (p->noise_mode != NFI_NOISE_DETERMINISTIC) {
     return fail("unknown noise_mode");
   }
@@ -255,6 +258,41 @@ decoder_forward_simt(const float* __restrict__ feats, long long n, int nout,
     if (o < nout) outp[row * nout + o] = out[o];
 }
 
+// ---------------------------------------------------------------- device-side noise
+// Philox-4x32-10 (Salmon et al., SC'11), one counter -> four uniforms.
+__device__ __forceinline__ void philox_round(uint32_t (&c)[4], uint32_t k0, uint32_t k1) {
+  const uint64_t p0 = (uint64_t)0xD2511F53u * c[0], p1 = (uint64_t)0xCD9E8D57u * c[2];
+  const uint32_t hi0 = (uint32_t)(p0 >> 32), lo0 = (uint32_t)p0;
+  const uint32_t hi1 = (uint32_t)(p1 >> 32), lo1 = (uint32_t)p1;
+  c[0] = hi1 ^ c[1] ^ k0;
+  c[1] = lo1;
+  c[2] = hi0 ^ c[3] ^ k1;
+  c[3] = lo0;
+}
+__global__ void __launch_bounds__(256)
+fill_uniform_kernel(float* __restrict__ dst, long long n, unsigned long long seed,
+                    unsigned stream_id, long long offset) {
+  const long long i4 = (long long)blockIdx.x * blockDim.x + threadIdx.x;  // group of 4 outputs
+  if (4 * i4 >= n) return;
+  const unsigned long long ctr = (unsigned long long)(offset / 4 + i4);
+  uint32_t c[4] = {(uint32_t)ctr, (uint32_t)(ctr >> 32), stream_id, 0u};
+  uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    philox_round(c, k0, k1);
+    k0 += 0x9E3779B9u;
+    k1 += 0xBB67AE85u;
+  }
+  float v[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) v[j] = (float)(c[j] >> 8) * (1.0f / 16777216.0f);
+  if (4 * i4 + 3 < n) {
+    *reinterpret_cast<float4*>(dst + 4 * i4) = make_float4(v[0], v[1], v[2], v[3]);
+  } else {
+    for (int j = 0; j < 4 && 4 * i4 + j < n; ++j) dst[4 * i4 + j] = v[j];
+  }
+}
+
 // ---------------------------------------------------------------- re-layout
 // [B,32,R,R] x3 (channel-first)  ->  [B,3,R,R,32] (channel-last), and back.
 // 32 channels x 32 pixels per block through a padded shared tile: both the
@@ -346,6 +384,18 @@ int nfi_planes_from_channel_last(const float* src, int32_t batch, int32_t plane_
   const int RR = plane_res * plane_res;
   dim3 grid((RR + 31) / 32, 3, batch);
   planes_from_cl_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(src, RR, dst);
+  NFI_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int nfi_fill_uniform(float* dst, int64_t n, uint64_t seed, uint32_t stream_id, int64_t offset,
+                     void* stream) {
+  if (!dst || n < 0 || offset < 0 || (offset & 3) || ((uintptr_t)dst & 15))
+    return fail("nfi_fill_uniform: dst must be 16-byte aligned, offset a multiple of 4");
+  if (n == 0) return 0;
+  const long long groups = (n + 3) / 4;
+  fill_uniform_kernel<<<(unsigned)((groups + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+      dst, n, seed, stream_id, offset);
   NFI_CUDA(cudaGetLastError());
   return 0;
 }
@@ -517,8 +567,10 @@ int nfi_render_forward_host(const nfi_render_params* hp, int32_t device) {
   const size_t plane_img = 3 * R * R * 32;
   float* planes_cf = dalloc(B * plane_img * sizeof(float));
   float* planes_cl = dalloc(B * plane_img * sizeof(float));
-  const bool has_nt = hp->noise_mode == NFI_NOISE_EXPLICIT && hp->noise_t;
-  const bool has_nu = has_nt && hp->fine_sampling && hp->noise_u;
+  const bool philox = hp->noise_mode == NFI_NOISE_PHILOX;
+  const bool has_nt = philox || (hp->noise_mode == NFI_NOISE_EXPLICIT && hp->noise_t);
+  const bool has_nu = has_nt && hp->fine_sampling && (philox || hp->noise_u);
+  if (philox) d.noise_mode = NFI_NOISE_EXPLICIT;
   float* noise_t = has_nt ? dalloc(n_rays * S * sizeof(float)) : nullptr;
   float* noise_u = has_nu ? dalloc(n_rays * S * sizeof(float)) : nullptr;
   d.w1 = up(hp->w1, 64 * 32);
@@ -559,10 +611,10 @@ int nfi_render_forward_host(const nfi_render_params* hp, int32_t device) {
       const size_t b0 = c * CB, nb = (b0 + CB <= B) ? CB : B - b0;
       cudaMemcpyAsync(planes_cf + b0 * plane_img, hp->planes + b0 * plane_img,
                       nb * plane_img * sizeof(float), cudaMemcpyHostToDevice, cp);
-      if (has_nt)
+      if (has_nt && !philox)
         cudaMemcpyAsync(noise_t + b0 * rays_img * S, hp->noise_t + b0 * rays_img * S,
                         nb * rays_img * S * sizeof(float), cudaMemcpyHostToDevice, cp);
-      if (has_nu)
+      if (has_nu && !philox)
         cudaMemcpyAsync(noise_u + b0 * rays_img * S, hp->noise_u + b0 * rays_img * S,
                         nb * rays_img * S * sizeof(float), cudaMemcpyHostToDevice, cp);
       cudaEventCreateWithFlags(&ready[c], cudaEventDisableTiming);
@@ -583,6 +635,12 @@ int nfi_render_forward_host(const nfi_render_params* hp, int32_t device) {
       q.depth = depth + b0 * rays_img;
       q.mask = mask + b0 * rays_img;
       q.extra = extra ? extra + b0 * rays_img * ne : nullptr;
+      if (philox) {  // the two draws of the path, generated where the reference draws them
+        const int64_t off = (int64_t)(b0 * rays_img * S), cnt = (int64_t)(nb * rays_img * S);
+        rc = nfi_fill_uniform(noise_t + off, cnt, hp->noise_seed, 0u, off, st);
+        if (!rc && has_nu) rc = nfi_fill_uniform(noise_u + off, cnt, hp->noise_seed, 1u, off, st);
+        if (rc) break;
+      }
       const float* cf = planes_cf + b0 * plane_img;
       rc = nfi_planes_to_channel_last(cf, cf + 32 * R * R, cf + 64 * R * R, (int64_t)(96 * R * R),
                                       (int32_t)nb, (int32_t)R, planes_cl + b0 * plane_img, st);

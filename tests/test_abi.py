@@ -25,7 +25,7 @@ def test_library_exports_every_declared_symbol():
     lib = _lib.load()
     for name in header_functions():
         assert hasattr(lib, name), name
-    assert lib.nfi_abi_version() == 1
+    assert lib.nfi_abi_version() == 2
     assert b'sm_100a' in lib.nfi_build_info()
 
 

@@ -253,3 +253,46 @@ def test_full_size_against_gpu_oracle(cuda_lib):
     assert Hh.rel_l2(rgb, ref['rgb']) < TOL
     assert Hh.rel_l2(mask, ref['mask']) < TOL
     assert mask.min().item() >= -1e-6 and mask.max().item() <= 1 + 1e-5
+
+
+def test_fill_uniform_and_host_entry_philox(cuda_lib):
+    """nfi_fill_uniform: range, determinism, independence of how the buffer is split; and the
+    host entry point with NFI_NOISE_PHILOX equals the device path fed with the same noise."""
+    import ctypes
+    from nerf_from_image_b200 import _lib
+    lib = cuda_lib
+    st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+    n = 4 * 12345 + 2
+    a = torch.empty(n, device='cuda')
+    b = torch.empty(n, device='cuda')
+    _lib.check(lib.nfi_fill_uniform(ctypes.c_void_p(a.data_ptr()), n, 77, 0, 0, st))
+    _lib.check(lib.nfi_fill_uniform(ctypes.c_void_p(b.data_ptr()), 4000, 77, 0, 0, st))
+    _lib.check(lib.nfi_fill_uniform(ctypes.c_void_p(b.data_ptr() + 16000), n - 4000, 77, 0, 4000, st))
+    assert torch.equal(a, b)
+    assert 0.0 <= a.min().item() and a.max().item() < 1.0
+    assert abs(a.mean().item() - 0.5) < 0.01 and abs(a.var().item() - 1 / 12) < 0.005
+    c = torch.empty(n, device='cuda')
+    _lib.check(lib.nfi_fill_uniform(ctypes.c_void_p(c.data_ptr()), n, 77, 1, 0, st))
+    assert not torch.equal(a, c)
+
+    B, H, W, S = 2, 16, 16, 16
+    scene, cams = Hh.make_case('p3d_plain', batch=B)
+    nt = torch.empty(B, H, W, S, device='cuda')
+    nu = torch.empty(B * H * W, S, device='cuda')
+    _lib.check(lib.nfi_fill_uniform(ctypes.c_void_p(nt.data_ptr()), nt.numel(), 5, 0, 0, st))
+    _lib.check(lib.nfi_fill_uniform(ctypes.c_void_p(nu.data_ptr()), nu.numel(), 5, 1, 0, st))
+    rgb, depth, mask, _ = Hh.run_cuda(scene, cams, H, W, S, nt, nu)
+    host = {k: scene[k].contiguous() for k in ('planes', 'w1', 'b1', 'w2', 'b2', 'palette', 'beta', 'alpha')}
+    host['c2w'], host['focal'] = cams['c2w'].contiguous(), cams['focal'].contiguous()
+    host['rgb'], host['depth'], host['mask'] = torch.empty(B, H, W, 3), torch.empty(B, H, W), torch.empty(B, H, W)
+    p = _lib.RenderParams()
+    p.batch, p.height, p.width, p.num_samples = B, H, W, S
+    p.plane_res, p.n_attention = scene['planes'].shape[-1], scene['palette'].shape[1]
+    p.scene_range, p.white_background = scene['scene_range'], int(scene['white_background'])
+    p.use_sdf, p.fine_sampling, p.noise_mode, p.noise_seed = 1, 1, _lib.NOISE_PHILOX, 5
+    p.mlp_mode = Hh.MLP_MODE
+    for k, v in host.items():
+        setattr(p, k, ctypes.c_void_p(v.data_ptr()))
+    _lib.check(lib.nfi_render_forward_host(ctypes.byref(p), 0))
+    assert torch.equal(host['rgb'], rgb.cpu())
+    assert torch.equal(host['mask'], mask.cpu())

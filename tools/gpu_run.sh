@@ -5,12 +5,13 @@ for a in "$@"; do
     tests) timeout 600 python -m pytest tests -m gpu -q -x -k "pipe or golden" 2>&1 | tail -5 > gpurun_out/pytest_pipe.log; cat gpurun_out/pytest_pipe.log;;
     alltests) timeout 900 python -m pytest tests -m gpu -q -x 2>&1 | tail -5 > gpurun_out/pytest_all.log; cat gpurun_out/pytest_all.log;;
     phase) timeout 300 python tools/phase_times_pipe.py 8 > gpurun_out/phase_times.txt 2>&1; head -6 gpurun_out/phase_times.txt;;
+    newtests) timeout 600 python -m pytest tests -m gpu -q -x -k "fill_uniform or abi" 2>&1 | tail -12 > gpurun_out/pytest_new.log; cat gpurun_out/pytest_new.log;;
     bwdtests) timeout 600 python -m pytest tests -m gpu -q -x -k "backward" 2>&1 | tail -12 > gpurun_out/pytest_bwd.log; cat gpurun_out/pytest_bwd.log;;
     bwd) timeout 200 python tools/time_backward.py 8 2>&1 | tail -3 > gpurun_out/time_backward.txt; cat gpurun_out/time_backward.txt;;
-    ncu_list) timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 60 --csv --log-file gpurun_out/launches.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-e2e > gpurun_out/ncu_list.log 2>&1; tail -12 gpurun_out/launches.csv | cut -c1-220;;
-    ncu_full) timeout 500 ncu --set full --clock-control none --import-source on -k regex:render_forward_pipe -s 2 -c 1 -f -o gpurun_out/pipe_full python bench.py --batch 8 --steps 1 --warmup 3 --no-cpu-baseline --no-e2e > gpurun_out/ncu_full.log 2>&1; tail -2 gpurun_out/ncu_full.log | cut -c1-200;;
+    ncu_list) timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 60 --csv --log-file gpurun_out/launches.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-e2e --no-backward > gpurun_out/ncu_list.log 2>&1; tail -12 gpurun_out/launches.csv | cut -c1-220;;
+    ncu_full) timeout 500 ncu --set full --clock-control none --import-source on -k regex:render_forward_pipe -s 2 -c 1 -f -o gpurun_out/pipe_full python bench.py --batch 8 --steps 1 --warmup 3 --no-cpu-baseline --no-e2e --no-backward > gpurun_out/ncu_full.log 2>&1; tail -2 gpurun_out/ncu_full.log | cut -c1-200;;
     full) timeout 280 python bench.py > gpurun_out/bench_full.json 2> gpurun_out/bench_full.err; cat gpurun_out/bench_full.json; tail -2 gpurun_out/bench_full.err;;
-    *) timeout 120 python bench.py --steps 10 --no-cpu-baseline --no-e2e --mlp-mode $a > gpurun_out/bench_m$a.json 2> gpurun_out/bench_m$a.err
+    *) timeout 120 python bench.py --steps 10 --no-cpu-baseline --no-e2e --no-backward --mlp-mode $a > gpurun_out/bench_m$a.json 2> gpurun_out/bench_m$a.err
        echo "mode $a: $(python -c "import json,sys; d=json.load(open('gpurun_out/bench_m$a.json')); print(d['value']/1e6, 'Mrays/s kernel_ms', d['roofline']['kernel_ms'])" 2>&1 | tail -1)";;
   esac
 done
