@@ -62,7 +62,10 @@ struct PipeCfg {
   static constexpr int kSmBytes = kSmTmemPtr + 16;
   // setmaxnreg moves registers inside the CTA's launch allocation (threads x launch regs):
   //   P = 3: 768 x 80 = 61440 = 128 x (88 + 80 + 24) + 384 x 96 (12 texel loads in flight per
-  //   producer warp: 48 data registers + 64-bit addresses + taps)
+  //   producer warp: 48 data registers + 64-bit addresses + taps).  A 256-bit variant
+  //   (ld.global.nc.v8.f32, 4 lanes per texel, 8 points per iteration: 23 instead of 37
+  //   instructions per point) assembles for sm_100a but traps as an illegal instruction
+  //   on the B200, so 128-bit loads it is.
 #ifndef NFI_ACT_REGS
 #define NFI_ACT_REGS 88
 #define NFI_SHADE_REGS 80

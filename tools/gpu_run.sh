@@ -4,7 +4,7 @@ for a in "$@"; do
   case $a in
     tests) timeout 600 python -m pytest tests -m gpu -q -x -k "pipe or golden" 2>&1 | tail -5 > gpurun_out/pytest_pipe.log; cat gpurun_out/pytest_pipe.log;;
     alltests) timeout 900 python -m pytest tests -m gpu -q -x 2>&1 | tail -5 > gpurun_out/pytest_all.log; cat gpurun_out/pytest_all.log;;
-    phase) timeout 300 python tools/phase_times_pipe.py 8 > gpurun_out/phase_times.txt 2>&1; head -6 gpurun_out/phase_times.txt;;
+    phase) timeout 300 python tools/phase_times_pipe.py 8 > gpurun_out/phase_times.txt 2>&1; head -20 gpurun_out/phase_times.txt;;
     newtests) timeout 600 python -m pytest tests -m gpu -q -x -k "fill_uniform or abi" 2>&1 | tail -12 > gpurun_out/pytest_new.log; cat gpurun_out/pytest_new.log;;
     bwdtests) timeout 600 python -m pytest tests -m gpu -q -x -k "backward" 2>&1 | tail -12 > gpurun_out/pytest_bwd.log; cat gpurun_out/pytest_bwd.log;;
     bwd) timeout 200 python tools/time_backward.py 8 2>&1 | tail -3 > gpurun_out/time_backward.txt; cat gpurun_out/time_backward.txt;;
