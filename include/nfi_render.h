@@ -182,7 +182,7 @@ NFI_API int nfi_decoder_forward(const float *features, int64_t n_points, const f
 
 /* autograd of the above: recomputes the samples.
  * With params->workspace >= 64 KiB, frozen decoder weights (grad_w1/b1/w2/b2 NULL), no
- * semantics output and S <= 64, S % 4 == 0 the four GEMMs of a sample step run on
+ * semantics output and S <= 128, S % 4 == 0 the four GEMMs of a sample step run on
  * tcgen05 (render_backward_pipe); otherwise the fp32 SIMT kernel is used. */
 NFI_API int nfi_render_backward(const nfi_render_params *params, const nfi_render_grads *grads,
                         void *stream);

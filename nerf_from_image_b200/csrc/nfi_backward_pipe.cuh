@@ -49,7 +49,7 @@ struct BwdCfg {
   static constexpr int kStageWarp = 32 * 36 * 4 + 32 * 4 * 4;           // [32][36] dF + [32][4] coord grads
   static constexpr int kSmPal = kSmStage + P * 4 * kStageWarp;
   static constexpr int kSmFrac = kSmPal + 48 * 4;
-  static constexpr int kSmBars = kSmFrac + 64 * 4;
+  static constexpr int kSmBars = kSmFrac + 128 * 4;
   // full[3], a_free[3], per slot: d1_full, h_ready, d2_full, dout_ready, d3_full, dpre_ready,
   // d4_full, slot_free; weights x2
   static constexpr int kNumBars = 2 * kBwdStages + 8 * kBwdSlots + 2;
@@ -219,7 +219,7 @@ render_backward_pipe(const nfi_render_params p, const nfi_render_grads g,
   const float* b2s = reinterpret_cast<const float*>(base + kWiB2);
   float* pal = reinterpret_cast<float*>(base + Cfg::kSmPal);
   float* frac = reinterpret_cast<float*>(base + Cfg::kSmFrac);
-  if (tid < 64) frac[tid] = (float)tid / (float)S;
+  if (tid < 128) frac[tid] = (float)tid / (float)S;
 
   if (tid == 0) {
     if (tc::smem_u32(base) & 1023u) __trap();

@@ -53,8 +53,8 @@ struct PipeCfg {
   static constexpr int kStages = P + 1;  // one spare: a set never waits for its own MMA
   static constexpr int kSmA = 25600;
   static constexpr int kSmPal = kSmA + kStages * kPipeStageBytes;
-  static constexpr int kSmFrac = kSmPal + 48 * 4;  // s / S for s < 64 (one IEEE division each)
-  static constexpr int kSmBars = kSmFrac + 64 * 4;
+  static constexpr int kSmFrac = kSmPal + 48 * 4;  // s / S for s < 128 (one IEEE division each)
+  static constexpr int kSmBars = kSmFrac + 128 * 4;
   // full[P], a_free[P], d1_full[3], h_ready[3], d2_full[3], slot_free[3], cw_ready, zf_ready,
   // weights
   static constexpr int kNumBars = 2 * kStages + 4 * kPipeSlots + 3;
@@ -197,45 +197,62 @@ __device__ __forceinline__ void field_head_fast(const float (&out)[NOUT_PAD], co
 
 // ------------------------------------------------------------------ resampling
 // Warp-per-ray importance resampling (run.py:266-281, lib/nerf_utils.py:183-222).
-// Per-ray arrays of (up to) 64 entries live two per lane: element e = lane in
-// .a, e = lane + 32 in .b.
-struct Pair {
-  float a, b;
+// Per-ray arrays of up to 32 N entries live N per lane: element e = 32 i + lane in v[i]
+// (N = 2 for S <= 64, N = 4 for S <= 128).
+template <int N>
+struct LaneVec {
+  float v[N];
 };
 // y_e = x_{e+1}; the element past the end is `pad`
-__device__ __forceinline__ Pair shift_down1(Pair x, float pad, int lane) {
-  const float a = __shfl_down_sync(kFull, x.a, 1);
-  const float b = __shfl_down_sync(kFull, x.b, 1);
-  const float b0 = __shfl_sync(kFull, x.b, 0);
-  Pair y;
-  y.a = (lane == 31) ? b0 : a;
-  y.b = (lane == 31) ? pad : b;
+template <int N>
+__device__ __forceinline__ LaneVec<N> shift_down1(const LaneVec<N>& x, float pad, int lane) {
+  LaneVec<N> y;
+#pragma unroll
+  for (int i = 0; i < N; ++i) {
+    const float a = __shfl_down_sync(kFull, x.v[i], 1);
+    const float nxt0 = (i + 1 < N) ? __shfl_sync(kFull, x.v[(i + 1 < N) ? i + 1 : i], 0) : pad;
+    y.v[i] = (lane == 31) ? nxt0 : a;
+  }
   return y;
 }
-__device__ __forceinline__ float pick64(Pair x, int idx) {
-  const float a = __shfl_sync(kFull, x.a, idx & 31);
-  const float b = __shfl_sync(kFull, x.b, idx & 31);
-  return (idx & 32) ? b : a;
-}
-// ascending bitonic sort of 64 values (2 per lane)
-__device__ __forceinline__ void bitonic_sort64(Pair& x, int lane) {
+template <int N>
+__device__ __forceinline__ float pick(const LaneVec<N>& x, int idx) {
+  float r = __shfl_sync(kFull, x.v[0], idx & 31);
 #pragma unroll
-  for (int k = 2; k <= 64; k <<= 1) {
+  for (int i = 1; i < N; ++i) {
+    const float t = __shfl_sync(kFull, x.v[i], idx & 31);
+    r = ((idx >> 5) == i) ? t : r;
+  }
+  return r;
+}
+// ascending bitonic sort of 32 N values
+template <int N>
+__device__ __forceinline__ void bitonic_sort(LaneVec<N>& x, int lane) {
+#pragma unroll
+  for (int k = 2; k <= 32 * N; k <<= 1) {
 #pragma unroll
     for (int j = k >> 1; j > 0; j >>= 1) {
-      if (j == 32) {  // partner is the other register of the same lane (k = 64: ascending)
-        const float lo = fminf(x.a, x.b), hi = fmaxf(x.a, x.b);
-        x.a = lo;
-        x.b = hi;
+      if (j >= 32) {  // partner is another register of the same lane
+        const int dj = j >> 5;
+#pragma unroll
+        for (int i = 0; i < N; ++i) {
+          if ((i & dj) == 0) {
+            const int ip = i | dj;
+            const bool asc = (k >= 32 * N) ? true : (((32 * i) & k) == 0);
+            const float lo = fminf(x.v[i], x.v[ip]), hi = fmaxf(x.v[i], x.v[ip]);
+            x.v[i] = asc ? lo : hi;
+            x.v[ip] = asc ? hi : lo;
+          }
+        }
       } else {
-        const float oa = __shfl_xor_sync(kFull, x.a, j);
-        const float ob = __shfl_xor_sync(kFull, x.b, j);
         const bool lower = (lane & j) == 0;
-        // element indices: lane (bit 5 clear) and lane + 32 (bit 5 set)
-        const bool asc_a = (k == 64) ? true : ((lane & k) == 0);
-        const bool asc_b = (k == 64) ? true : (k == 32 ? false : ((lane & k) == 0));
-        x.a = (lower == asc_a) ? fminf(x.a, oa) : fmaxf(x.a, oa);
-        x.b = (lower == asc_b) ? fminf(x.b, ob) : fmaxf(x.b, ob);
+#pragma unroll
+        for (int i = 0; i < N; ++i) {
+          const float o = __shfl_xor_sync(kFull, x.v[i], j);
+          // element index 32 i + lane: bit of k taken from the lane (k < 32) or from i
+          const bool asc = (k >= 32 * N) ? true : (k < 32 ? ((lane & k) == 0) : (((32 * i) & k) == 0));
+          x.v[i] = (lower == asc) ? fminf(x.v[i], o) : fmaxf(x.v[i], o);
+        }
       }
     }
   }
@@ -244,72 +261,136 @@ __device__ __forceinline__ void bitonic_sort64(Pair& x, int lane) {
 // One ray.  w: coarse weights (elements >= S are don't-care), t: coarse depths,
 // u: uniforms (padded with 2.0 beyond S; sorted inside unless `sorted`).  Returns
 // the S fine depths in ascending order.
-__device__ __forceinline__ Pair resample_ray(Pair w, Pair t, Pair u, bool sorted, int S, int lane) {
+template <int N>
+__device__ __forceinline__ LaneVec<N> resample_ray(const LaneVec<N>& w, const LaneVec<N>& t,
+                                                   LaneVec<N> u, bool sorted, int S, int lane) {
   const float inf = __int_as_float(0x7f800000);
   // smoothed pdf p_m, m = 0 .. S-3  (run.py:266-272, + 1e-5 of sample_pdf)
-  const Pair w1 = shift_down1(w, 0.f, lane);
-  const Pair w2 = shift_down1(w1, 0.f, lane);
-  Pair pm;
-  pm.a = ((fmaxf(w.a, w1.a) + fmaxf(w1.a, w2.a)) * 0.5f + 0.01f) + 1e-5f;
-  pm.b = ((fmaxf(w.b, w1.b) + fmaxf(w1.b, w2.b)) * 0.5f + 0.01f) + 1e-5f;
-  if (lane >= S - 2) pm.a = 0.f;
-  if (lane + 32 >= S - 2) pm.b = 0.f;
-  float sum = pm.a + pm.b;
+  const LaneVec<N> w1 = shift_down1<N>(w, 0.f, lane);
+  const LaneVec<N> w2 = shift_down1<N>(w1, 0.f, lane);
+  LaneVec<N> q;
+  float sum = 0.f;
+#pragma unroll
+  for (int i = 0; i < N; ++i) {
+    float pm = ((fmaxf(w.v[i], w1.v[i]) + fmaxf(w1.v[i], w2.v[i])) * 0.5f + 0.01f) + 1e-5f;
+    if (32 * i + lane >= S - 2) pm = 0.f;
+    q.v[i] = pm;
+    sum += pm;
+  }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(kFull, sum, o);
-  // inclusive scan of q_m = p_m / sum over the 64 slots
-  Pair q;
-  q.a = pm.a / sum;
-  q.b = pm.b / sum;
+  // inclusive scan of q_m = p_m / sum over the 32 N slots
+#pragma unroll
+  for (int i = 0; i < N; ++i) q.v[i] = q.v[i] / sum;
 #pragma unroll
   for (int o = 1; o < 32; o <<= 1) {
-    const float ya = __shfl_up_sync(kFull, q.a, o);
-    const float yb = __shfl_up_sync(kFull, q.b, o);
-    if (lane >= o) {
-      q.a += ya;
-      q.b += yb;
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+      const float y = __shfl_up_sync(kFull, q.v[i], o);
+      if (lane >= o) q.v[i] += y;
     }
   }
-  q.b += __shfl_sync(kFull, q.a, 31);
+#pragma unroll
+  for (int i = 1; i < N; ++i) q.v[i] += __shfl_sync(kFull, q.v[i - 1], 31);
   // cdf c_j, j = 0 .. S-2: c_0 = 0, c_j = scan_{j-1}; +inf beyond
-  Pair c;
-  {
-    const float ua = __shfl_up_sync(kFull, q.a, 1);
-    const float ub = __shfl_up_sync(kFull, q.b, 1);
-    const float a31 = __shfl_sync(kFull, q.a, 31);
-    c.a = (lane == 0) ? 0.f : ua;
-    c.b = (lane == 0) ? a31 : ub;
-    if (lane > S - 2) c.a = inf;
-    if (lane + 32 > S - 2) c.b = inf;
+  LaneVec<N> c;
+#pragma unroll
+  for (int i = 0; i < N; ++i) {
+    const float up = __shfl_up_sync(kFull, q.v[i], 1);
+    const float prev31 = (i > 0) ? __shfl_sync(kFull, q.v[(i > 0) ? i - 1 : 0], 31) : 0.f;
+    c.v[i] = (lane == 0) ? prev31 : up;
+    if (32 * i + lane > S - 2) c.v[i] = inf;
   }
   // bins b_j = (t_j + t_{j+1}) / 2, j = 0 .. S-2
-  const Pair t1 = shift_down1(t, 0.f, lane);
-  Pair bn;
-  bn.a = 0.5f * (t1.a + t.a);
-  bn.b = 0.5f * (t1.b + t.b);
-  if (!sorted) bitonic_sort64(u, lane);
-  Pair z;
+  const LaneVec<N> t1 = shift_down1<N>(t, 0.f, lane);
+  LaneVec<N> bn;
 #pragma unroll
-  for (int h = 0; h < 2; ++h) {
-    const float uu = h ? u.b : u.a;
+  for (int i = 0; i < N; ++i) bn.v[i] = 0.5f * (t1.v[i] + t.v[i]);
+  if (!sorted) bitonic_sort<N>(u, lane);
+  LaneVec<N> z;
+#pragma unroll
+  for (int h = 0; h < N; ++h) {
+    const float uu = u.v[h];
     int pos = 0;  // number of cdf entries <= u (searchsorted right=True)
 #pragma unroll
-    for (int s = 32; s > 0; s >>= 1) {
-      const float val = pick64(c, pos + s - 1);
+    for (int s = 16 * N; s > 0; s >>= 1) {
+      const float val = pick<N>(c, pos + s - 1);
       if (val <= uu) pos += s;
     }
     const int below = max(pos - 1, 0), above = min(pos, S - 2);
-    const float c0 = pick64(c, below), c1 = pick64(c, above);
-    const float b0 = pick64(bn, below), b1 = pick64(bn, above);
+    const float c0 = pick<N>(c, below), c1 = pick<N>(c, above);
+    const float b0 = pick<N>(bn, below), b1 = pick<N>(bn, above);
     float den = c1 - c0;
     if (den < 1e-5f) den = 1.f;
-    const float zz = b0 + (uu - c0) / den * (b1 - b0);
-    if (h) z.b = zz; else z.a = zz;
+    z.v[h] = b0 + (uu - c0) / den * (b1 - b0);
   }
   return z;
 }
 
-template <int NOUT_PAD, int EXTRA, bool FINE, int P, bool DBG>
+// Importance resampling of the 16 rays [first, first + 16) of a warp's 32 rows, one
+// warp-pass per ray.  (tnear, tfar, ray, valid) are this lane's own row's.  N = 2 slots per
+// lane serve S <= 64, N = 4 (a separate kernel instantiation, so that its register needs
+// do not touch the allocation of the common case's per-step loops) S <= 128.
+struct ResampleArgs {
+  const float* sc_w;
+  float* sc_zf;
+  float* z_fine;
+  const float* noise_t;
+  const float* noise_u;
+  const float* frac;
+  int S, wig;
+  bool explicit_noise;
+};
+template <int N>
+__device__ __forceinline__ void resample_rows_impl(const ResampleArgs& a, int first, float tnear,
+                                                   float tfar, size_t ray, bool valid, int lane) {
+  const int S = a.S;
+  // inputs of ray j+1 are loaded while ray j is resampled
+  struct In {
+    LaneVec<N> w, n, u;
+    size_t rayj;
+  };
+  auto load = [&](int j, In& in) {
+    in.rayj = ((size_t)__shfl_sync(kFull, (unsigned)(ray >> 32), j) << 32) |
+              (size_t)__shfl_sync(kFull, (unsigned)ray, j);
+    const int col = 32 * a.wig + j;
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+      const int e = 32 * i + lane;
+      in.w.v[i] = (e < S) ? ldcg(a.sc_w + e * kThreads + col) : 0.f;
+      in.n.v[i] = 0.f;
+      if (a.explicit_noise) {
+        in.n.v[i] = (e < S) ? a.noise_t[in.rayj * S + e] : 0.f;
+        in.u.v[i] = (e < S) ? a.noise_u[in.rayj * S + e] : 2.f;
+      } else {
+        in.u.v[i] = (e < S) ? linspace01(e, S) : 2.f;
+      }
+    }
+  };
+  In cur, nxt;
+  load(first, cur);
+#pragma unroll 1
+  for (int j = first; j < first + 16; ++j) {
+    load(j + 1 < first + 16 ? j + 1 : j, nxt);
+    const float nearj = __shfl_sync(kFull, tnear, j), farj = __shfl_sync(kFull, tfar, j);
+    const bool validj = __shfl_sync(kFull, (int)valid, j) != 0;
+    const int col = 32 * a.wig + j;
+    const float spanj = farj - nearj;
+    LaneVec<N> t;
+#pragma unroll
+    for (int i = 0; i < N; ++i)
+      t.v[i] = lerp_torch(nearj, farj, a.frac[32 * i + lane]) + cur.n.v[i] * (spanj / (float)S);
+    const LaneVec<N> z = resample_ray<N>(cur.w, t, cur.u, !a.explicit_noise, S, lane);
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+      const int e = 32 * i + lane;
+      if (e < S) a.sc_zf[e * kThreads + col] = z.v[i];
+      if (a.z_fine != nullptr && validj && e < S) a.z_fine[cur.rayj * S + e] = z.v[i];
+    }
+    cur = nxt;
+  }
+}
+template <int NOUT_PAD, int EXTRA, bool FINE, int P, bool DBG, int NSLOT = 2>
 __global__ void __launch_bounds__(PipeCfg<P>::kThreadsTotal, 1)
 render_forward_pipe(const nfi_render_params p, const unsigned char* __restrict__ wimg,
                     float* __restrict__ scratch) {
@@ -344,7 +425,7 @@ render_forward_pipe(const nfi_render_params p, const unsigned char* __restrict__
   const float* b2s = reinterpret_cast<const float*>(base + kWiB2);
   float* pal = reinterpret_cast<float*>(base + Cfg::kSmPal);
   float* frac = reinterpret_cast<float*>(base + Cfg::kSmFrac);
-  if (tid < 64) frac[tid] = (float)tid / (float)S;
+  if (tid < 128) frac[tid] = (float)tid / (float)S;
 
   if (tid == 0) {
     if (tc::smem_u32(base) & 1023u) __trap();
@@ -414,50 +495,17 @@ render_forward_pipe(const nfi_render_params p, const unsigned char* __restrict__
   // Importance resampling of the 16 rays [first, first + 16) of this warp's 32 rows:
   // one warp-pass per ray.  (tnear, tfar, ray index, valid) are this lane's own row's.
   auto resample_rows = [&](int first, float tnear, float tfar, size_t ray, bool valid) {
-    // inputs of ray j+1 are loaded while ray j is resampled
-    struct In {
-      Pair w, n, u;
-      size_t rayj;
-    };
-    const int e0 = lane, e1 = lane + 32;
-    auto load = [&](int j, In& in) {
-      in.rayj = ((size_t)__shfl_sync(kFull, (unsigned)(ray >> 32), j) << 32) |
-                (size_t)__shfl_sync(kFull, (unsigned)ray, j);
-      const int col = 32 * wig + j;
-      in.w.a = (e0 < S) ? ldcg(sc_w + e0 * kThreads + col) : 0.f;
-      in.w.b = (e1 < S) ? ldcg(sc_w + e1 * kThreads + col) : 0.f;
-      in.n.a = in.n.b = 0.f;
-      if (explicit_noise) {
-        in.n.a = (e0 < S) ? p.noise_t[in.rayj * S + e0] : 0.f;
-        in.n.b = (e1 < S) ? p.noise_t[in.rayj * S + e1] : 0.f;
-        in.u.a = (e0 < S) ? p.noise_u[in.rayj * S + e0] : 2.f;
-        in.u.b = (e1 < S) ? p.noise_u[in.rayj * S + e1] : 2.f;
-      } else {
-        in.u.a = (e0 < S) ? linspace01(e0, S) : 2.f;
-        in.u.b = (e1 < S) ? linspace01(e1, S) : 2.f;
-      }
-    };
-    In cur, nxt;
-    load(first, cur);
-#pragma unroll 1
-    for (int j = first; j < first + 16; ++j) {
-      load(j + 1 < first + 16 ? j + 1 : j, nxt);
-      const float nearj = __shfl_sync(kFull, tnear, j), farj = __shfl_sync(kFull, tfar, j);
-      const bool validj = __shfl_sync(kFull, (int)valid, j) != 0;
-      const int col = 32 * wig + j;
-      const float spanj = farj - nearj;
-      Pair t;
-      t.a = lerp_torch(nearj, farj, frac[e0]) + cur.n.a * (spanj / (float)S);
-      t.b = lerp_torch(nearj, farj, frac[e1]) + cur.n.b * (spanj / (float)S);
-      const Pair z = resample_ray(cur.w, t, cur.u, !explicit_noise, S, lane);
-      if (e0 < S) sc_zf[e0 * kThreads + col] = z.a;
-      if (e1 < S) sc_zf[e1 * kThreads + col] = z.b;
-      if (p.z_fine != nullptr && validj) {
-        if (e0 < S) p.z_fine[cur.rayj * S + e0] = z.a;
-        if (e1 < S) p.z_fine[cur.rayj * S + e1] = z.b;
-      }
-      cur = nxt;
-    }
+    ResampleArgs ra;
+    ra.sc_w = sc_w;
+    ra.sc_zf = sc_zf;
+    ra.z_fine = p.z_fine;
+    ra.noise_t = p.noise_t;
+    ra.noise_u = p.noise_u;
+    ra.frac = frac;
+    ra.S = S;
+    ra.wig = wig;
+    ra.explicit_noise = explicit_noise;
+    resample_rows_impl<NSLOT>(ra, first, tnear, tfar, ray, valid, lane);
   };
 
   // The roles never share code after setmaxnreg: ptxas budgets registers per

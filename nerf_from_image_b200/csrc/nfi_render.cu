@@ -96,8 +96,8 @@ bool tc_supported(const nfi_render_params* p) {
   if (p->extra_mode == NFI_EXTRA_SEMANTICS) return false;
   const int mode = p->mlp_mode & 0xff;
   const int smax = (mode == NFI_MLP_TC_WARPSPEC) ? 128 : 64;  // per-ray columns in tile memory
-  if ((mode == NFI_MLP_TC_PIPE || mode == NFI_MLP_AUTO) && (p->num_samples > 64 || p->num_samples % 4))
-    return false;  // pipelined kernel: 2 samples per lane in the resampler, float4 jitter loads
+  if (mode == NFI_MLP_TC_PIPE || mode == NFI_MLP_AUTO)  // pipelined kernel: <= 4 samples per lane
+    return p->num_samples <= 128 && p->num_samples % 4 == 0;  // in the resampler, float4 jitter
   if (p->fine_sampling && p->num_samples > smax) return false;
   return true;
 }
@@ -159,8 +159,17 @@ int launch_fwd_tc_fine(const nfi_render_params& p, const unsigned char* wimg, fl
         return 0;
       }
     }
-    if (p.fine_sampling) NFI_PIPE(true, false);
-    else NFI_PIPE(false, false);
+    if (p.fine_sampling && p.num_samples > 64) {  // 4 resampling slots per lane (S <= 128)
+      auto k = nfi::render_forward_pipe<NP, EX, true, 3, false, 4>;
+      NFI_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    nfi::PipeCfg<3>::kSmBytes));
+      k<<<(unsigned)grid, nfi::PipeCfg<3>::kThreadsTotal, nfi::PipeCfg<3>::kSmBytes, st>>>(
+          p, wimg, scratch);
+    } else if (p.fine_sampling) {
+      NFI_PIPE(true, false);
+    } else {
+      NFI_PIPE(false, false);
+    }
 #undef NFI_PIPE
     NFI_CUDA(cudaGetLastError());
     return 0;
@@ -408,7 +417,7 @@ int nfi_render_forward(const nfi_render_params* params, void* stream) {
   const int mode = p.mlp_mode & 0xff;
   if ((mode == NFI_MLP_TC_3XTF32 || mode == NFI_MLP_TC_WARPSPEC || mode == NFI_MLP_TC_PIPE) &&
       !tc_supported(params))
-    return fail("tensor-core modes need S <= 64 (warp-specialised: 128) with fine sampling and "
+    return fail("tensor-core modes need S <= 128 and S % 4 == 0 (lockstep kernel: S <= 64) and "
                 "no semantics output; use NFI_MLP_AUTO");
   const bool want_tc = mode == NFI_MLP_TC_3XTF32 || mode == NFI_MLP_TC_WARPSPEC ||
                        mode == NFI_MLP_TC_PIPE ||
@@ -483,7 +492,7 @@ int nfi_render_backward(const nfi_render_params* params, const nfi_render_grads*
   const int mode = p.mlp_mode & 0xff;
   const bool wgrad = g.grad_w1 || g.grad_b1 || g.grad_w2 || g.grad_b2;
   const bool tc_ok = !wgrad && mode != NFI_MLP_FP32_SIMT && p.extra_mode != NFI_EXTRA_SEMANTICS &&
-                     p.num_samples <= 64 && p.num_samples % 4 == 0 && p.workspace != nullptr &&
+                     p.num_samples <= 128 && p.num_samples % 4 == 0 && p.workspace != nullptr &&
                      p.workspace_bytes >= kBackwardWorkspaceBytes &&
                      (!p.fine_sampling || p.z_fine != nullptr) && g.out_rgb && g.out_mask &&
                      (!g.g_extra || g.out_extra) &&

@@ -60,6 +60,30 @@ def test_forward_variants(cuda_lib, fine, A, use_sdf):
     assert Hh.rel_l2(depth.cpu(), ref['depth']) < TOL
 
 
+@pytest.mark.parametrize('S', [32, 64, 128])
+def test_forward_and_backward_sample_counts(cuda_lib, S, mlp_mode):
+    """BASELINE config 5 sweeps 32 -> 128 samples per ray: the pipelined kernels take
+    S <= 128 (2 or 4 resampling slots per lane), the older tensor-core kernels S <= 64."""
+    if mlp_mode in (2, 3) and S > 64:
+        pytest.skip('lockstep / first warp-specialised kernel: S <= 64')
+    B, H, W = 1, 16, 24
+    scene, cams = Hh.make_case('p3d_bbox', batch=B)
+    nt, nu = _noise(37, B, H, W, S)
+    outs = []
+    for dev in ('cpu', 'cuda'):
+        sc, cm = Hh.to_device(scene, dev), Hh.to_device(cams, dev)
+        sc['planes'] = sc['planes'].clone().requires_grad_()
+        if dev == 'cpu':
+            r = Hh.run_oracle(sc, cm, H, W, S, nt, nu)
+            rgb, mask, depth = r['rgb'], r['mask'], r['depth']
+        else:
+            rgb, depth, mask, _ = Hh.run_cuda(sc, cm, H, W, S, nt, nu)
+        outs.append((rgb.detach().cpu(), mask.detach().cpu(), depth.detach().cpu(),
+                     _grads((rgb, mask), [sc['planes']])[0].cpu()))
+    for a, b, tol in zip(outs[1], outs[0], (TOL, TOL, TOL, 2e-3)):
+        assert Hh.rel_l2(a, b) < tol
+
+
 @pytest.mark.parametrize('mode', ['coords', 'semantics'])
 def test_extra_outputs(cuda_lib, mode, mlp_mode):
     if mode == 'semantics' and mlp_mode != 1:
