@@ -207,6 +207,59 @@ __device__ __forceinline__ void gather_features(const float* __restrict__ planes
   __syncwarp();
 }
 
+// Bilinear interpolation plus its derivatives along the plane's two axes in TEXEL units
+// (d/dix = (ne-nw) gy0 + (se-sw) gy1, d/diy = (sw-nw) gx0 + (se-ne) gx1; zero where
+// the coordinate was clamped, as F.grid_sample's backward does).
+__device__ __forceinline__ void bilerp4_grad(const float4* plane, const Taps& t, float4& e,
+                                             float4& gx, float4& gy) {
+  const float4 a = ldg4(plane + (size_t)t.o00 * (kC / 4));
+  const float4 b = ldg4(plane + (size_t)t.o01 * (kC / 4));
+  const float4 c = ldg4(plane + (size_t)t.o10 * (kC / 4));
+  const float4 d = ldg4(plane + (size_t)t.o11 * (kC / 4));
+  const float mx = t.inx ? 1.f : 0.f, my = t.iny ? 1.f : 0.f;
+#define NFI_G(cmp)                                                                      \
+  e.cmp = fmaf(d.cmp, t.w11, fmaf(c.cmp, t.w10, fmaf(b.cmp, t.w01, a.cmp * t.w00)));    \
+  gx.cmp = ((b.cmp - a.cmp) * t.gy0 + (d.cmp - c.cmp) * t.gy1) * mx;                    \
+  gy.cmp = ((c.cmp - a.cmp) * t.gx0 + (d.cmp - b.cmp) * t.gx1) * my;
+  NFI_G(x) NFI_G(y) NFI_G(z) NFI_G(w)
+#undef NFI_G
+}
+
+// gather_features plus the derivatives of the features with respect to the three
+// normalised coordinates (rows of Grow: [3][32][kFRow]), up to the common factor
+// (R-1)/2 / 3 the caller applies.  Plane xy sees (x0, x1), xz (x0, x2), yz (x1, x2).
+__device__ __forceinline__ void gather_features_grad(const float* __restrict__ planes_b, int R,
+                                                     float x0, float x1, float x2, float* Frow,
+                                                     float* Grow, int lane) {
+  const int q = lane >> 3, k = lane & 7;
+  const size_t plane_stride = (size_t)R * R * kC;
+#pragma unroll 1
+  for (int g = 0; g < 8; ++g) {
+    const int src = 4 * g + q;
+    const float c0 = __shfl_sync(kFull, x0, src);
+    const float c1 = __shfl_sync(kFull, x1, src);
+    const float c2 = __shfl_sync(kFull, x2, src);
+    const float4* base = reinterpret_cast<const float4*>(planes_b) + k;
+    float4 e0, e1, e2, ax, ay, bx, by, cx, cy;
+    bilerp4_grad(base, make_taps(c0, c1, R), e0, ax, ay);
+    bilerp4_grad(base + plane_stride / 4, make_taps(c0, c2, R), e1, bx, by);
+    bilerp4_grad(base + 2 * (plane_stride / 4), make_taps(c1, c2, R), e2, cx, cy);
+    float4 f;
+    f.x = ((e0.x + e1.x) + e2.x) / 3.f;
+    f.y = ((e0.y + e1.y) + e2.y) / 3.f;
+    f.z = ((e0.z + e1.z) + e2.z) / 3.f;
+    f.w = ((e0.w + e1.w) + e2.w) / 3.f;
+    *reinterpret_cast<float4*>(Frow + src * kFRow + 4 * k) = f;
+    *reinterpret_cast<float4*>(Grow + src * kFRow + 4 * k) =
+        make_float4(ax.x + bx.x, ax.y + bx.y, ax.z + bx.z, ax.w + bx.w);
+    *reinterpret_cast<float4*>(Grow + (32 + src) * kFRow + 4 * k) =
+        make_float4(ay.x + cx.x, ay.y + cx.y, ay.z + cx.z, ay.w + cx.w);
+    *reinterpret_cast<float4*>(Grow + (64 + src) * kFRow + 4 * k) =
+        make_float4(by.x + cy.x, by.y + cy.y, by.z + cy.z, by.w + cy.w);
+  }
+  __syncwarp();
+}
+
 // softplus as torch.nn.Softplus(beta=1, threshold=20): MUFU ex2 + lg2.
 __device__ __forceinline__ float softplus_fast(float x) {
   const float e = __expf(-fabsf(x));

@@ -67,12 +67,15 @@ struct FwdSmem {
   float* b2;   // [NOUT_PAD]
   float* pal;  // [16*3]
   float* F;    // [4][32][kFRow]
+  float* G;    // [4][3][32][kFRow]  (normals only)
   float* colA; // [S][128]
   float* colB; // [S][128]
 };
 
-__host__ __device__ inline size_t fwd_smem_floats(int nout_pad, int S, bool fine) {
+__host__ __device__ inline size_t fwd_smem_floats(int nout_pad, int S, bool fine,
+                                                  bool normals = false) {
   size_t n = kC * kHid + kHid + kHid * nout_pad + nout_pad + 48 + kWarps * 32 * kFRow;
+  if (normals) n += kWarps * 3 * 32 * kFRow;  // d features / d coords, per warp
   if (fine) n += 2 * (size_t)S * kThreads;
   return n;
 }
@@ -103,12 +106,17 @@ __device__ __forceinline__ void load_weights_smem(const nfi_render_params& p, in
                     : 0.f;
 }
 
-// EXTRA: 0 none, 1 coords (3), 2 semantics (A)
-template <int NOUT_PAD, int EXTRA, bool FINE>
+// EXTRA: 0 none, 1 coords (3), 2 semantics (A).  NORM: also the composited surface normals
+// (models/generator.py:599-623: normalised analytic gradient of the SDF with respect to the
+// sample position; lib/nerf_utils.py:146-148: weighted with the detached weights), carried
+// as three more "extras" after the EXTRA ones.
+template <int NOUT_PAD, int EXTRA, bool FINE, bool NORM = false>
 __global__ void __launch_bounds__(kThreads)
 render_forward_simt(const nfi_render_params p) {
-  constexpr int NE = (EXTRA == 0) ? 0 : (EXTRA == 1 ? 3 : NOUT_PAD - 1);
-  constexpr int NES = (EXTRA == 2) ? NOUT_PAD - 1 : 0;  // extras parked in scratch
+  constexpr int NE0 = (EXTRA == 0) ? 0 : (EXTRA == 1 ? 3 : NOUT_PAD - 1);
+  constexpr int NE = NE0 + (NORM ? 3 : 0);
+  constexpr int NES0 = (EXTRA == 2) ? NOUT_PAD - 1 : 0;
+  constexpr int NES = NES0 + (NORM ? 3 : 0);  // extras parked in scratch
   extern __shared__ __align__(16) float smem_f[];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int S = p.num_samples;
@@ -122,6 +130,7 @@ render_forward_simt(const nfi_render_params p) {
     sm.b2 = q; q += NOUT_PAD;
     sm.pal = q; q += 48;
     sm.F = q; q += kWarps * 32 * kFRow;
+    sm.G = q; q += NORM ? kWarps * 3 * 32 * kFRow : 0;
     sm.colA = q; q += FINE ? (size_t)S * kThreads : 0;
     sm.colB = q;
   }
@@ -178,10 +187,46 @@ render_forward_simt(const nfi_render_params p) {
     const float x0 = wx / p.scene_range, x1 = wy / p.scene_range, x2 = wz / p.scene_range;
     const float keep =
         (fabsf(x0) > 1.f || fabsf(x1) > 1.f || fabsf(x2) > 1.f) ? 0.f : 1.f;
-    gather_features(planes_b, p.plane_res, x0, x1, x2, Fw, lane);
     float out[NOUT_PAD];
     float h[kHid];
-    mlp_forward<NOUT_PAD, false>(frow, sm.W1t, sm.b1, sm.W2t, sm.b2, out, h);
+    if (NORM) {
+      float* Gw = sm.G + warp * 3 * 32 * kFRow;
+      gather_features_grad(planes_b, p.plane_res, x0, x1, x2, Fw, Gw, lane);
+      mlp_forward<NOUT_PAD, true>(frow, sm.W1t, sm.b1, sm.W2t, sm.b2, out, h);  // h = pre-activations
+      // d sdf / d x = W2[0,:] diag(sigmoid(pre)) W1 dF/dx
+#pragma unroll
+      for (int j = 0; j < kHid; ++j)
+        h[j] = sm.W2t[j * NOUT_PAD] * (h[j] > 20.f ? 1.f : 1.f / (1.f + expf(-h[j])));
+      float n0 = 0.f, n1 = 0.f, n2 = 0.f;
+#pragma unroll 1
+      for (int c = 0; c < kC; ++c) {
+        const float4* wr = reinterpret_cast<const float4*>(sm.W1t + c * kHid);
+        float u = 0.f;
+#pragma unroll
+        for (int j4 = 0; j4 < kHid / 4; ++j4) {
+          const float4 w = wr[j4];
+          u = fmaf(w.x, h[4 * j4 + 0], u);
+          u = fmaf(w.y, h[4 * j4 + 1], u);
+          u = fmaf(w.z, h[4 * j4 + 2], u);
+          u = fmaf(w.w, h[4 * j4 + 3], u);
+        }
+        n0 = fmaf(u, Gw[lane * kFRow + c], n0);
+        n1 = fmaf(u, Gw[(32 + lane) * kFRow + c], n1);
+        n2 = fmaf(u, Gw[(64 + lane) * kFRow + c], n2);
+      }
+      // common factors of the chain: (R-1)/2 per texel unit, 1/3 plane mean, 1/scene_range
+      const float sc = 0.5f * (float)(p.plane_res - 1) / (3.f * p.scene_range);
+      n0 *= sc;
+      n1 *= sc;
+      n2 *= sc;
+      const float inv = 1.f / fmaxf(sqrtf((n0 * n0 + n1 * n1) + n2 * n2), 1e-12f);  // F.normalize
+      ex[NE0 + 0] = n0 * inv;
+      ex[NE0 + 1] = n1 * inv;
+      ex[NE0 + 2] = n2 * inv;
+    } else {
+      gather_features(planes_b, p.plane_res, x0, x1, x2, Fw, lane);
+      mlp_forward<NOUT_PAD, false>(frow, sm.W1t, sm.b1, sm.W2t, sm.b2, out, h);
+    }
     __syncwarp();
     float probs[NOUT_PAD];
     field_head<NOUT_PAD>(out, fc, sm.pal, keep, sigma, cr, cg, cb, probs);
@@ -191,7 +236,7 @@ render_forward_simt(const nfi_render_params p) {
       ex[2] = wz;
     } else if (EXTRA == 2) {
 #pragma unroll
-      for (int a = 0; a < NE; ++a) ex[a] = probs[a];
+      for (int a = 0; a < NE0; ++a) ex[a] = probs[a];
     }
   };
 
@@ -208,7 +253,8 @@ render_forward_simt(const nfi_render_params p) {
       sc_srgb[s * kThreads + tid] = make_float4(sigma, cr, cg, cb);
       sc_t[s * kThreads + tid] = t;
 #pragma unroll
-      for (int a = 0; a < NES; ++a) sc_e[((size_t)s * NES + a) * kThreads + tid] = ex[a];
+      for (int a = 0; a < NES; ++a)
+        sc_e[((size_t)s * NES + a) * kThreads + tid] = ex[a < NES0 ? a : NE0 + (a - NES0)];
       // render_volume_density_weights_only (lib/nerf_utils.py:164-180)
       if (s > 0) {
         const float delta = (t - prev_t) * r.dn;
@@ -299,7 +345,8 @@ render_forward_simt(const nfi_render_params p) {
           ce[2] = r.oz + r.dz * ct;
         }
 #pragma unroll
-        for (int a = 0; a < NES; ++a) ce[a] = sc_e[((size_t)c * NES + a) * kThreads + tid];
+        for (int a = 0; a < NES; ++a)
+          ce[a < NES0 ? a : NE0 + (a - NES0)] = sc_e[((size_t)c * NES + a) * kThreads + tid];
         comp.push(ct, q.x, q.y, q.z, q.w, ce, r.dn);
         ++c;
         ct = (c < S) ? sc_t[c * kThreads + tid] : 0.f;
@@ -315,7 +362,8 @@ render_forward_simt(const nfi_render_params p) {
         ce[2] = r.oz + r.dz * ct;
       }
 #pragma unroll
-      for (int a = 0; a < NES; ++a) ce[a] = sc_e[((size_t)c * NES + a) * kThreads + tid];
+      for (int a = 0; a < NES; ++a)
+        ce[a < NES0 ? a : NE0 + (a - NES0)] = sc_e[((size_t)c * NES + a) * kThreads + tid];
       comp.push(ct, q.x, q.y, q.z, q.w, ce, r.dn);
       ++c;
       ct = (c < S) ? sc_t[c * kThreads + tid] : 0.f;
@@ -332,9 +380,11 @@ render_forward_simt(const nfi_render_params p) {
     p.mask[ray] = comp.am;
     if (EXTRA != 0 && p.extra != nullptr) {
       const int ne_out = (EXTRA == 1) ? 3 : p.n_attention;
-      for (int a = 0; a < NE; ++a)
+      for (int a = 0; a < NE0; ++a)
         if (a < ne_out) p.extra[ray * ne_out + a] = comp.ae[a];
     }
+    if (NORM && p.normals != nullptr)  // lib/nerf_utils.py:157-158: white background applies too
+      for (int a = 0; a < 3; ++a) p.normals[ray * 3 + a] = comp.ae[NE0 + a] + bg;
   }
 }
 

@@ -68,8 +68,10 @@ int check_params(const nfi_render_params* p) {
     return fail("compute_semantics needs attention_values > 0");  // run.py:232
   if (p->extra_mode < 0 || p->extra_mode > 2) return fail("unknown extra_mode");
   if (p->extra_mode != NFI_EXTRA_NONE && !p->extra) return fail("extra output buffer missing");
-  if (p->compute_normals && !(p->mlp_mode & 0x1000))
-    return fail("compute_normals is not implemented in this build");
+  if (p->compute_normals && !(p->mlp_mode & 0x1000)) {  // (0x1000: p->normals is a debug buffer)
+    if (!p->use_sdf) return fail("compute_normals needs use_sdf");  // run.py:229
+    if (!p->normals) return fail("normals output buffer missing");
+  }
   if (!p->rgb || !p->depth || !p->mask) return fail("output buffers missing");
   return 0;
 }
@@ -94,6 +96,7 @@ size_t num_tc_ctas(const nfi_render_params* p) {
 // Can the tensor-core kernel take this configuration?
 bool tc_supported(const nfi_render_params* p) {
   if (p->extra_mode == NFI_EXTRA_SEMANTICS) return false;
+  if (p->compute_normals && !(p->mlp_mode & 0x1000)) return false;  // evaluation-only: SIMT kernel
   const int mode = p->mlp_mode & 0xff;
   const int smax = (mode == NFI_MLP_TC_WARPSPEC) ? 128 : 64;  // per-ray columns in tile memory
   if (mode == NFI_MLP_TC_PIPE || mode == NFI_MLP_AUTO)  // pipelined kernel: <= 4 samples per lane
@@ -102,8 +105,13 @@ bool tc_supported(const nfi_render_params* p) {
   return true;
 }
 
+bool wants_normals(const nfi_render_params* p) {
+  return p->compute_normals && !(p->mlp_mode & 0x1000);
+}
+
 int ne_store_of(const nfi_render_params* p) {
-  return p->extra_mode == NFI_EXTRA_SEMANTICS ? nout_pad_of(p) - 1 : 0;
+  return (p->extra_mode == NFI_EXTRA_SEMANTICS ? nout_pad_of(p) - 1 : 0) +
+         (wants_normals(p) ? 3 : 0);
 }
 
 template <typename K>
@@ -119,6 +127,10 @@ int launch(K kernel, const nfi_render_params& p, size_t smem_bytes, cudaStream_t
 
 template <int NP, int EX>
 int launch_fwd_fine(const nfi_render_params& p, size_t smem, cudaStream_t st) {
+  if (wants_normals(&p)) {
+    if (p.fine_sampling) return launch(nfi::render_forward_simt<NP, EX, true, true>, p, smem, st);
+    return launch(nfi::render_forward_simt<NP, EX, false, true>, p, smem, st);
+  }
   if (p.fine_sampling) return launch(nfi::render_forward_simt<NP, EX, true>, p, smem, st);
   return launch(nfi::render_forward_simt<NP, EX, false>, p, smem, st);
 }
@@ -427,7 +439,9 @@ int nfi_render_forward(const nfi_render_params* params, void* stream) {
       return fail("workspace too small (see nfi_render_workspace_bytes)");
   }
   if (want_tc) return launch_fwd_tc(p, np, st);
-  const size_t smem = nfi::fwd_smem_floats(np, p.num_samples, p.fine_sampling != 0) * sizeof(float);
+  const size_t smem =
+      nfi::fwd_smem_floats(np, p.num_samples, p.fine_sampling != 0, wants_normals(params)) *
+      sizeof(float);
   nfi_render_params ps = p;  // SIMT scratch starts after the weight-image header
   if (ps.workspace) ps.workspace = (unsigned char*)ps.workspace + kWeightImageBytes;
   switch (np) {
@@ -598,7 +612,8 @@ int nfi_render_forward_host(const nfi_render_params* hp, int32_t device) {
   float* depth = dalloc(n_rays * sizeof(float));
   float* mask = dalloc(n_rays * sizeof(float));
   float* extra = ne ? dalloc(n_rays * ne * sizeof(float)) : nullptr;
-  d.normals = nullptr;
+  d.normals = (hp->compute_normals && hp->normals) ? dalloc(n_rays * 3 * sizeof(float)) : nullptr;
+  float* normals = d.normals;
   d.z_fine = nullptr;
   d.batch = (int32_t)CB;
   d.workspace_bytes = nfi_render_workspace_bytes(&d);
@@ -644,6 +659,7 @@ int nfi_render_forward_host(const nfi_render_params* hp, int32_t device) {
       q.depth = depth + b0 * rays_img;
       q.mask = mask + b0 * rays_img;
       q.extra = extra ? extra + b0 * rays_img * ne : nullptr;
+      q.normals = normals ? normals + b0 * rays_img * 3 : nullptr;
       if (philox) {  // the two draws of the path, generated where the reference draws them
         const int64_t off = (int64_t)(b0 * rays_img * S), cnt = (int64_t)(nb * rays_img * S);
         rc = nfi_fill_uniform(noise_t + off, cnt, hp->noise_seed, 0u, off, st);
@@ -664,6 +680,9 @@ int nfi_render_forward_host(const nfi_render_params* hp, int32_t device) {
         if (ne && hp->extra)
           cudaMemcpyAsync(hp->extra + b0 * rays_img * ne, q.extra,
                           nb * rays_img * ne * sizeof(float), cudaMemcpyDeviceToHost, st);
+        if (normals)
+          cudaMemcpyAsync(hp->normals + b0 * rays_img * 3, q.normals,
+                          nb * rays_img * 3 * sizeof(float), cudaMemcpyDeviceToHost, st);
       }
     }
   }

@@ -138,7 +138,7 @@ class FusedTriplaneRender(torch.autograd.Function):
     @staticmethod
     def forward(ctx, planes, w1, b1, w2, b2, palette, beta, alpha, c2w, focal,
                 center, bbox, cfg, height, width, S, noise_t, noise_u,
-                extra_mode, cam_grad):
+                extra_mode, cam_grad, compute_normals=False):
         _check_shapes(cfg, planes, w1, b1, w2, b2, palette, c2w, focal, center,
                       bbox, height, width, S, noise_t, noise_u)
         lib = _lib.load()
@@ -167,6 +167,12 @@ class FusedTriplaneRender(torch.autograd.Function):
                 extra = torch.empty(B, height, width, 3, device=dev)
             elif extra_mode == _lib.EXTRA_SEMANTICS:
                 extra = torch.empty(B, height, width, A, device=dev)
+            normals = None
+            if compute_normals:
+                # models/generator.py:599-601: SDF models only; forward quantity, no gradient
+                # (create_graph=False, weights detached: lib/nerf_utils.py:146-148)
+                assert cfg.use_sdf
+                normals = torch.empty(B, height, width, 3, device=dev)
             z_fine = None
             if needs_grad and cfg.fine_sampling:
                 z_fine = torch.empty(B * height * width, S, device=dev)
@@ -176,6 +182,8 @@ class FusedTriplaneRender(torch.autograd.Function):
                              S, t['noise_t'], t['noise_u'], extra_mode)
             p.rgb, p.depth, p.mask, p.extra = _ptr(rgb), _ptr(depth), _ptr(mask), _ptr(extra)
             p.z_fine = _ptr(z_fine)
+            if normals is not None:
+                p.compute_normals, p.normals = 1, _ptr(normals)
             if DEBUG_BUF is not None:
                 p.normals = _ptr(DEBUG_BUF)
             ws_bytes = lib.nfi_render_workspace_bytes(ctypes.byref(p))
@@ -200,10 +208,13 @@ class FusedTriplaneRender(torch.autograd.Function):
         if extra is None:
             extra = torch.empty(0, device=dev)
             ctx.mark_non_differentiable(extra)
-        return rgb, depth, mask, extra
+        if normals is None:
+            normals = torch.empty(0, device=dev)
+        ctx.mark_non_differentiable(normals)
+        return rgb, depth, mask, extra, normals
 
     @staticmethod
-    def backward(ctx, g_rgb, g_depth, g_mask, g_extra):
+    def backward(ctx, g_rgb, g_depth, g_mask, g_extra, g_normals=None):
         cfg, (height, width, S), t = ctx.cfg, ctx.dims, ctx.t
         lib = _lib.load()
         planes_cl = ctx.planes_cl
@@ -279,14 +290,20 @@ class FusedTriplaneRender(torch.autograd.Function):
                 if t['bbox'] is not None and n_bbox:
                     gbbox = res.pop(0)
         return (gplanes, gw1, gb1, gw2, gb2, gpal, gbeta, galpha, gc2w, gfocal,
-                gcenter, gbbox, None, None, None, None, None, None, None, None)
+                gcenter, gbbox, None, None, None, None, None, None, None, None, None)
 
 
 def fused_render(planes, w1, b1, w2, b2, palette, beta, alpha, c2w, focal,
                  center, bbox, cfg, height, width, num_samples, noise_t=None,
-                 noise_u=None, extra_mode=_lib.EXTRA_NONE, cam_grad=True):
-    """Functional form; returns (rgb, depth, mask, extra|None)."""
-    rgb, depth, mask, extra = FusedTriplaneRender.apply(
+                 noise_u=None, extra_mode=_lib.EXTRA_NONE, cam_grad=True,
+                 compute_normals=False):
+    """Functional form; returns (rgb, depth, mask, extra|None), with
+    ``compute_normals`` (rgb, depth, mask, extra|None, normals)."""
+    rgb, depth, mask, extra, normals = FusedTriplaneRender.apply(
         planes, w1, b1, w2, b2, palette, beta, alpha, c2w, focal, center, bbox,
-        cfg, height, width, num_samples, noise_t, noise_u, extra_mode, cam_grad)
-    return rgb, depth, mask, (extra if extra_mode != _lib.EXTRA_NONE else None)
+        cfg, height, width, num_samples, noise_t, noise_u, extra_mode, cam_grad,
+        compute_normals)
+    extra = extra if extra_mode != _lib.EXTRA_NONE else None
+    if compute_normals:
+        return rgb, depth, mask, extra, normals
+    return rgb, depth, mask, extra

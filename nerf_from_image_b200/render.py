@@ -138,8 +138,6 @@ def render(target_model,
             'fused path (SURVEY.md section 8f N4)')
     if compute_normals:
         assert args.use_sdf  # run.py:229
-        raise NotImplementedError('compute_normals is not fused yet '
-                                  '(SURVEY.md section 8f N3)')
     if compute_semantics:
         assert args.attention_values > 0  # run.py:232
     S = int(depth_samples_per_ray)
@@ -172,11 +170,14 @@ def render(target_model,
     elif compute_semantics:
         extra_mode = _lib.EXTRA_SEMANTICS
 
-    rgb, depth, mask, extra = fused_render(
+    out = fused_render(
         planes, w1, b1, w2, b2, palette, beta, alpha, tform_cam2world,
         focal_length, center, bbox, cfg, height, width, S, noise_t, noise_u,
-        extra_mode, cam_grad=not force_no_cam_grad)
-    return rgb, depth, mask, None, extra, model_outputs
+        extra_mode, cam_grad=not force_no_cam_grad,
+        compute_normals=bool(compute_normals))
+    rgb, depth, mask, extra = out[:4]
+    normals = out[4] if compute_normals else None
+    return rgb, depth, mask, normals, extra, model_outputs
 
 
 class ParallelModel(nn.Module):

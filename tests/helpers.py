@@ -43,7 +43,7 @@ MLP_MODE = 0  # tests/test_parity_gpu.py switches this (0 auto, 1 SIMT, 2 tensor
 
 
 def run_cuda(scene, cams, H, W, S, noise_t, noise_u, use_sdf=True, fine_sampling=True,
-             extra_mode=0, cam_grad=True, device='cuda', mlp_mode=None):
+             extra_mode=0, cam_grad=True, device='cuda', mlp_mode=None, compute_normals=False):
     from nerf_from_image_b200.fused import RenderConfig, fused_render
     sc = to_device(scene, device)
     cm = to_device(cams, device)
@@ -55,7 +55,8 @@ def run_cuda(scene, cams, H, W, S, noise_t, noise_u, use_sdf=True, fine_sampling
     nu = noise_u.to(device) if noise_u is not None else None
     return fused_render(sc['planes'], sc['w1'], sc['b1'], sc['w2'], sc['b2'], sc['palette'],
                         sc['beta'], sc['alpha'], cm['c2w'], cm['focal'], cm['center'],
-                        cm['bbox'], cfg, H, W, S, nt, nu, extra_mode, cam_grad)
+                        cm['bbox'], cfg, H, W, S, nt, nu, extra_mode, cam_grad,
+                        compute_normals=compute_normals)
 
 
 def rel_l2(a, b):

@@ -99,6 +99,28 @@ def test_extra_outputs(cuda_lib, mode, mlp_mode):
     assert Hh.rel_l2(extra.cpu(), ref['semantics']) < TOL
 
 
+@pytest.mark.parametrize('case,fine,semantics', [('p3d_plain', True, True), ('p3d_bbox', False, False),
+                                                 ('chairs_white_center', True, False)])
+def test_normals_match_oracle(cuda_lib, case, fine, semantics, mlp_mode):
+    """compute_normals (evaluation / visualisation calls of run.py:1263,1453,2043,2132):
+    normalised analytic SDF gradient, composited with the weights; together with
+    compute_semantics as the reference's evaluation loops request them."""
+    B, H, W, S = 2, 16, 16, 16
+    scene, cams = Hh.make_case(case, batch=B)
+    nt, nu = _noise(41, B, H, W, S, fine=fine)
+    ref = Hh.run_oracle(scene, cams, H, W, S, nt, nu, fine_sampling=fine, compute_normals=True,
+                        compute_semantics=semantics)
+    # explicit tensor-core modes refuse normals / semantics; NFI_MLP_AUTO (0) falls back by itself
+    rgb, depth, mask, extra, normals = Hh.run_cuda(scene, cams, H, W, S, nt, nu, fine_sampling=fine,
+                                                   extra_mode=2 if semantics else 0,
+                                                   compute_normals=True,
+                                                   mlp_mode=1 if mlp_mode == 1 else 0)
+    assert Hh.rel_l2(rgb.cpu(), ref['rgb'].detach()) < TOL
+    assert Hh.rel_l2(normals.cpu(), ref['normals'].detach()) < 1e-3
+    if semantics:
+        assert Hh.rel_l2(extra.cpu(), ref['semantics'].detach()) < TOL
+
+
 def test_fine_depths_match(cuda_lib):
     """The importance-resampled depths themselves (sorted) on rays that hit."""
     B, H, W, S = 1, 16, 16, 16
