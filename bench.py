@@ -180,8 +180,13 @@ def run_reference(args):
         'n_gpus': args.gpus, 'steps': args.steps, 'warmup': args.warmup,
         'ms_per_step': 1e3 * total / len(times), 'higher_is_better': True, 'scaling': 'weak',
         'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-        'config': {'workload': 'p3d_car render 128x128, 64+64 samples/ray, 256^2 tri-planes '
-                               '(config 2 geometry), CPU sample of %d image(s) per step' % n_img},
+        # same workload as the b200 arm; each step times a bounded sample of it (see cpu_baseline)
+        'config': {'workload': 'config 2: p3d_car render 128x128, 64 coarse + 64 fine '
+                               'samples/ray, batch %d per GPU, 256^2x32ch fp32 tri-planes given '
+                               '(channel-first) -> rgb/depth/mask' % CFG['batch'],
+                   'global_batch': args.gpus * CFG['batch'],
+                   'parallelism': 'host CPU cores (reference CPU path), rank 0 only',
+                   'randomize': True},
         'cpu_baseline': {'value': value, 'unit': UNIT, 'cores': threads, 'host_cores': os.cpu_count(), 'kind': 'port',
                          'sample': '%d image(s) of the 32-image batch per step, torch CPU fp32, '
                                    'no_grad' % n_img},
