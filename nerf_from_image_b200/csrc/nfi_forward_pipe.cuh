@@ -47,6 +47,11 @@ constexpr int kPipeSlots = 3;
 constexpr int kPipeSlotCols = 160;  // [0,64) D1 then H_lo, [64,128) H_hi, [128,144) D2
 constexpr int kPipeStageBytes = 32768;
 
+// scratch per CTA: the tc_scratch layout plus NES parked extras per coarse sample
+__host__ __device__ inline size_t pipe_scratch_floats(int S, int nes) {
+  return tc_scratch_floats_per_group(S) + (size_t)S * kThreads * nes;
+}
+
 template <int P>
 struct PipeCfg {
   static constexpr int kThreadsTotal = 384 + 128 * P;
@@ -148,7 +153,8 @@ __device__ __forceinline__ void softplus_split16(float (&v)[16], float (&hi)[16]
 template <int NOUT_PAD>
 __device__ __forceinline__ void field_head_fast(const float (&out)[NOUT_PAD], const FieldConst& fc,
                                                 const float* __restrict__ pal, float keep,
-                                                float& sigma, float& cr, float& cg, float& cb) {
+                                                float& sigma, float& cr, float& cg, float& cb,
+                                                float* probs = nullptr) {
   constexpr int NA = NOUT_PAD - 1;
   const float d = out[0];
   if (fc.use_sdf) {
@@ -179,6 +185,7 @@ __device__ __forceinline__ void field_head_fast(const float (&out)[NOUT_PAD], co
 #pragma unroll
     for (int a = 0; a < NA; ++a) {
       const float e = tc::ex2_approx(out[1 + a] - m);
+      if (probs != nullptr) probs[a] = e;
       s += e;
       r = fmaf(e, pv[3 * a + 0], r);
       g = fmaf(e, pv[3 * a + 1], g);
@@ -188,6 +195,10 @@ __device__ __forceinline__ void field_head_fast(const float (&out)[NOUT_PAD], co
     cr = r * inv;
     cg = g * inv;
     cb = b * inv;
+    if (probs != nullptr) {
+#pragma unroll
+      for (int a = 0; a < NA; ++a) probs[a] *= inv;
+    }
   } else {
     cr = sigmoid_fast(out[1]) * 2.004f - 1.002f;
     cg = sigmoid_fast(out[2]) * 2.004f - 1.002f;
@@ -395,7 +406,11 @@ __global__ void __launch_bounds__(PipeCfg<P>::kThreadsTotal, 1)
 render_forward_pipe(const nfi_render_params p, const unsigned char* __restrict__ wimg,
                     float* __restrict__ scratch) {
   using Cfg = PipeCfg<P>;
-  constexpr int NE = (EXTRA == 1) ? 3 : 0;
+  // extras composited with the weights: 3 world coordinates (EXTRA 1, recomputed from the
+  // depth) or the NA attention probabilities (EXTRA 2, parked in scratch for the coarse samples)
+  constexpr int NA_ = NOUT_PAD - 1;
+  constexpr int NE = (EXTRA == 1) ? 3 : (EXTRA == 2 ? NA_ : 0);
+  constexpr int NES = (EXTRA == 2) ? NA_ : 0;
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   unsigned char* base = smem_raw;
   const int tid = threadIdx.x, lane = tid & 31;
@@ -486,11 +501,12 @@ render_forward_pipe(const nfi_render_params p, const unsigned char* __restrict__
     tacc[i] += now__ - tprev;            \
     tprev = now__;                       \
   }
-  float* slab = scratch + (size_t)blockIdx.x * tc_scratch_floats_per_group(S);
+  float* slab = scratch + (size_t)blockIdx.x * pipe_scratch_floats(S, NES);
   float4* sc_srgb = reinterpret_cast<float4*>(slab);   // [S][128] coarse (sigma, r, g, b)
   float* sc_t = slab + (size_t)4 * S * kThreads;       // [S][128] coarse depths
   float* sc_w = sc_t + (size_t)S * kThreads;           // [S][128] coarse weights
   float* sc_zf = sc_w + (size_t)S * kThreads;          // [S][128] fine depths, ascending
+  float* sc_e = sc_zf + (size_t)S * kThreads;          // [S][NES][128] coarse attention probabilities
 
   // Importance resampling of the 16 rays [first, first + 16) of this warp's 32 rows:
   // one warp-pass per ray.  (tnear, tfar, ray index, valid) are this lane's own row's.
@@ -771,7 +787,8 @@ render_forward_pipe(const nfi_render_params p, const unsigned char* __restrict__
           sigma = out[0];
           cr = cg = cb = out[1];
         } else {
-          field_head_fast<NOUT_PAD>(out, fc, pal, keep, sigma, cr, cg, cb);
+          field_head_fast<NOUT_PAD>(out, fc, pal, keep, sigma, cr, cg, cb,
+                                    EXTRA == 2 ? ex : nullptr);
         }
         if (EXTRA == 1) {
           ex[0] = wx;
@@ -805,6 +822,8 @@ render_forward_pipe(const nfi_render_params p, const unsigned char* __restrict__
           if (FINE) {
             sc_srgb[s * kThreads + gt] = make_float4(sigma, cr, cg, cb);
             sc_t[s * kThreads + gt] = t;
+#pragma unroll
+            for (int a = 0; a < NES; ++a) sc_e[((size_t)s * NES + a) * kThreads + gt] = ex[a];
             if (s > 0) {
               const float delta = (t - prev_t) * r.dn;
               const float a = 1.f - __expf(-prev_s * delta);
@@ -847,6 +866,8 @@ render_forward_pipe(const nfi_render_params p, const unsigned char* __restrict__
             ce[1] = r.oy + r.dy * ct0;
             ce[2] = r.oz + r.dz * ct0;
           }
+#pragma unroll
+          for (int a = 0; a < NES; ++a) ce[a] = ldcg(sc_e + ((size_t)c * NES + a) * kThreads + gt);
           comp.push(ct0, cq0.x, cq0.y, cq0.z, cq0.w, ce, r.dn);
           ++c;
           ct0 = ct1;
@@ -883,6 +904,9 @@ render_forward_pipe(const nfi_render_params p, const unsigned char* __restrict__
         p.mask[ray] = comp.am;
         if (EXTRA == 1 && p.extra != nullptr)
           for (int a = 0; a < 3; ++a) p.extra[ray * 3 + a] = comp.ae[a];
+        if (EXTRA == 2 && p.extra != nullptr)
+          for (int a = 0; a < NE; ++a)
+            if (a < p.n_attention) p.extra[ray * p.n_attention + a] = comp.ae[a];
       }
     }
     if (DBG && dbg_time)

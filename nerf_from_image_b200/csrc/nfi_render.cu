@@ -95,9 +95,12 @@ size_t num_tc_ctas(const nfi_render_params* p) {
 
 // Can the tensor-core kernel take this configuration?
 bool tc_supported(const nfi_render_params* p) {
-  if (p->extra_mode == NFI_EXTRA_SEMANTICS) return false;
   if (p->compute_normals && !(p->mlp_mode & 0x1000)) return false;  // evaluation-only: SIMT kernel
   const int mode = p->mlp_mode & 0xff;
+  const bool pipe_mode = (mode == NFI_MLP_TC_PIPE || mode == NFI_MLP_AUTO);
+  // semantics: the pipelined kernel parks the coarse samples' probabilities; NOUT_PAD = 4 only
+  // exists for palettes of <= 3 entries, kept on the SIMT kernel
+  if (p->extra_mode == NFI_EXTRA_SEMANTICS && !(pipe_mode && p->n_attention > 3)) return false;
   const int smax = (mode == NFI_MLP_TC_WARPSPEC) ? 128 : 64;  // per-ray columns in tile memory
   if (mode == NFI_MLP_TC_PIPE || mode == NFI_MLP_AUTO)  // pipelined kernel: <= 4 samples per lane
     return p->num_samples <= 128 && p->num_samples % 4 == 0;  // in the resampler, float4 jitter
@@ -186,6 +189,9 @@ int launch_fwd_tc_fine(const nfi_render_params& p, const unsigned char* wimg, fl
     NFI_CUDA(cudaGetLastError());
     return 0;
   }
+  if constexpr (EX == 2) {
+    return fail("semantics output on tensor cores: pipelined kernel only");
+  } else {
   const bool lockstep = mode != NFI_MLP_TC_WARPSPEC;
   if (lockstep) {  // render_forward_tc: 4 tile groups per 512-thread CTA, one CTA per 2x2 tiles
     const size_t tx = (p.width + nfi::kTileW - 1) / nfi::kTileW;
@@ -223,6 +229,7 @@ int launch_fwd_tc_fine(const nfi_render_params& p, const unsigned char* wimg, fl
   }
   NFI_CUDA(cudaGetLastError());
   return 0;
+  }
 }
 
 int launch_fwd_tc(const nfi_render_params& p, int np, cudaStream_t st) {
@@ -237,14 +244,17 @@ int launch_fwd_tc(const nfi_render_params& p, int np, cudaStream_t st) {
                                             (pipe && p.n_attention > 0) ? nfi::kLog2e : 1.f);
   NFI_CUDA(cudaGetLastError());
   const bool coords = p.extra_mode == NFI_EXTRA_COORDS;
+  const bool sem = p.extra_mode == NFI_EXTRA_SEMANTICS;  // pipelined kernel only (tc_supported)
   switch (np) {
     case 4:
       return coords ? launch_fwd_tc_fine<4, 1>(p, wimg, scratch, st)
                     : launch_fwd_tc_fine<4, 0>(p, wimg, scratch, st);
     case 12:
+      if (sem) return launch_fwd_tc_fine<12, 2>(p, wimg, scratch, st);
       return coords ? launch_fwd_tc_fine<12, 1>(p, wimg, scratch, st)
                     : launch_fwd_tc_fine<12, 0>(p, wimg, scratch, st);
     default:
+      if (sem) return launch_fwd_tc_fine<16, 2>(p, wimg, scratch, st);
       return coords ? launch_fwd_tc_fine<16, 1>(p, wimg, scratch, st)
                     : launch_fwd_tc_fine<16, 0>(p, wimg, scratch, st);
   }
@@ -377,7 +387,10 @@ size_t nfi_render_workspace_bytes(const nfi_render_params* p) {
   if (p->fine_sampling) {
     fwd = num_ctas(p) * nfi::fwd_scratch_floats_per_cta(p->num_samples, ne_store_of(p)) *
           sizeof(float);
-    const size_t per_group = nfi::tc_scratch_floats_per_group(p->num_samples) * sizeof(float);
+    const size_t per_group =
+        nfi::pipe_scratch_floats(p->num_samples,
+                                 p->extra_mode == NFI_EXTRA_SEMANTICS ? nout_pad_of(p) - 1 : 0) *
+        sizeof(float);
     const size_t ws = num_tc_ctas(p) * nfi::kWsGroups * per_group;
     const size_t tx = (p->width + nfi::kTileW - 1) / nfi::kTileW;
     const size_t ty = (p->height + nfi::kTileH - 1) / nfi::kTileH;

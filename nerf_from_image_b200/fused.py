@@ -298,7 +298,17 @@ def fused_render(planes, w1, b1, w2, b2, palette, beta, alpha, c2w, focal,
                  noise_u=None, extra_mode=_lib.EXTRA_NONE, cam_grad=True,
                  compute_normals=False):
     """Functional form; returns (rgb, depth, mask, extra|None), with
-    ``compute_normals`` (rgb, depth, mask, extra|None, normals)."""
+    ``compute_normals`` (rgb, depth, mask, extra|None, normals).
+
+    The kernels compute in fp32 like the reference's render (run.py:59-60).  Under
+    autocast (BASELINE config 4 trains the synthesis network in bf16) the field tensors
+    may arrive in half precision: they are widened here, differentiably, so the
+    gradients flow back in the caller's dtype."""
+    def f32(t):
+        return t.float() if (t is not None and t.dtype in (torch.float16, torch.bfloat16)) else t
+    planes, w1, b1, w2, b2, palette, beta, alpha = map(f32, (planes, w1, b1, w2, b2, palette,
+                                                              beta, alpha))
+    c2w, focal, center, bbox = map(f32, (c2w, focal, center, bbox))
     rgb, depth, mask, extra, normals = FusedTriplaneRender.apply(
         planes, w1, b1, w2, b2, palette, beta, alpha, c2w, focal, center, bbox,
         cfg, height, width, num_samples, noise_t, noise_u, extra_mode, cam_grad,

@@ -86,8 +86,8 @@ def test_forward_and_backward_sample_counts(cuda_lib, S, mlp_mode):
 
 @pytest.mark.parametrize('mode', ['coords', 'semantics'])
 def test_extra_outputs(cuda_lib, mode, mlp_mode):
-    if mode == 'semantics' and mlp_mode != 1:
-        pytest.skip('semantics output runs on the SIMT kernel (NFI_MLP_AUTO falls back)')
+    if mode == 'semantics' and mlp_mode in (2, 3):
+        pytest.skip('semantics output: SIMT and pipelined kernels only')
     B, H, W, S = 2, 16, 16, 16
     scene, cams = Hh.make_case('p3d_plain', batch=B)
     nt, nu = _noise(7, B, H, W, S)
@@ -342,3 +342,20 @@ def test_fill_uniform_and_host_entry_philox(cuda_lib):
     _lib.check(lib.nfi_render_forward_host(ctypes.byref(p), 0))
     assert torch.equal(host['rgb'], rgb.cpu())
     assert torch.equal(host['mask'], mask.cpu())
+
+
+def test_half_precision_inputs_are_widened(cuda_lib):
+    """bf16 planes (autocast around the synthesis network) render like their fp32 widening,
+    and the gradient comes back in bf16."""
+    B, H, W, S = 1, 16, 16, 16
+    scene, cams = Hh.make_case('p3d_plain', batch=B)
+    nt, nu = _noise(43, B, H, W, S)
+    sc = Hh.to_device(scene, 'cuda')
+    pl16 = sc['planes'].to(torch.bfloat16).requires_grad_()
+    sc16 = dict(sc, planes=pl16)
+    sc32 = dict(sc, planes=pl16.detach().float())
+    a = Hh.run_cuda(sc16, cams, H, W, S, nt, nu)
+    b = Hh.run_cuda(sc32, cams, H, W, S, nt, nu)
+    assert torch.equal(a[0], b[0]) and torch.equal(a[2], b[2])
+    a[0].square().sum().backward()
+    assert pl16.grad is not None and pl16.grad.dtype == torch.bfloat16 and pl16.grad.abs().sum() > 0
