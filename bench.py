@@ -427,6 +427,48 @@ def main():
                   'depth_rel_l2': rel_l2(dep_g.cpu(), ref['depth']),
                   'against': 'CPU oracle, identical injected noise, %d images' % n_img}
 
+    # ------------------------------------------------------------ PyTorch eager on this GPU
+    # The same torch ops as the reference's render (the oracle port), fp32 with TF32 off like
+    # run.py:59-60, on a sample that fits (the unfused path materialises ~2 GB per image).
+    eager = None
+    if world == 1 and not args.no_cpu_baseline:
+        try:
+            from oracle import render_oracle as O
+            torch.backends.cuda.matmul.allow_tf32 = False
+            torch.backends.cudnn.allow_tf32 = False
+            n_img = 2
+            sc_e = synthetic.make_scene(77, n_img, plane_res=CFG['plane_res'],
+                                        attention_values=CFG['attention_values'],
+                                        scene_range=ds['scene_range'],
+                                        white_background=ds['white_background'], device=dev)
+            cm_e = synthetic.make_cameras(77, n_img, radius=ds['radius'], device=dev)
+            nt_e, nu_e = synthetic.make_noise(77, n_img, H, W, S, device=dev)
+
+            def eager_step():
+                with torch.no_grad():
+                    return O.render_oracle(sc_e['planes'], sc_e['w1'], sc_e['b1'], sc_e['w2'],
+                                           sc_e['b2'], sc_e['palette'], sc_e['beta'],
+                                           sc_e['alpha'], cm_e['c2w'], cm_e['focal'], None, None,
+                                           H, W, S, nt_e, nu_e, scene_range=sc_e['scene_range'],
+                                           white_background=sc_e['white_background'])
+            for _ in range(2):
+                eager_step()
+            torch.cuda.synchronize()
+            g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            g0.record()
+            for _ in range(3):
+                eager_step()
+            g1.record()
+            torch.cuda.synchronize()
+            ms_e = g0.elapsed_time(g1) / 3
+            eager = {'value': n_img * H * W / (ms_e * 1e-3), 'unit': UNIT, 'ms_per_step': ms_e,
+                     'sample': '%d images per step (same geometry), torch eager fp32 on this GPU, '
+                               'no_grad, oracle port of the reference ops' % n_img}
+            del sc_e, cm_e, nt_e, nu_e
+            torch.cuda.empty_cache()
+        except Exception as exc:  # out of memory on a smaller part: report, do not fail the bench
+            eager = {'unavailable': repr(exc)[:200]}
+
     line = {
         'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps,
         'warmup': args.warmup, 'ms_per_step': ms_step, 'higher_is_better': True,
@@ -441,7 +483,8 @@ def main():
         'clocks': clocks, 'e2e': e2e,
         # per step: planes_to_cl_kernel, prep_weight_image, render_forward_pipe
         'gpu_launches': 3 * args.steps,
-        'roofline': roofline, 'fwd_bwd': fwd_bwd, 'cpu_baseline': cpu_baseline, 'parity': parity,
+        'roofline': roofline, 'fwd_bwd': fwd_bwd, 'cpu_baseline': cpu_baseline,
+        'torch_eager_gpu': eager, 'parity': parity,
     }
     print(json.dumps(line))
     if world > 1:
