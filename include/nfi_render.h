@@ -70,7 +70,8 @@ enum nfi_mlp_mode {
   NFI_MLP_AUTO = 0,
   NFI_MLP_FP32_SIMT = 1, /* fp32 FFMA on CUDA cores                      */
   NFI_MLP_TC_3XTF32 = 2, /* tcgen05.mma kind::tf32, hi/lo split (3 MMAs), lockstep tile groups */
-  NFI_MLP_TC_WARPSPEC = 3, /* same arithmetic, producer/consumer warp-specialised, persistent */
+  NFI_MLP_TC_WARPSPEC = 3, /* alias of NFI_MLP_TC_PIPE (the first warp-specialised kernel, whose two
+                              roles shared one ring stage per chain, was retired) */
   NFI_MLP_TC_PIPE = 4 /* same arithmetic, fully pipelined: A stages released at MMA completion,
                          hidden activations stay in TMEM, consumers software-pipelined (default) */
 };

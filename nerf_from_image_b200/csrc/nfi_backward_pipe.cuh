@@ -63,7 +63,7 @@ struct BwdCfg {
 };
 
 // W2^T (padded to K = 32) and W1^T / 3, split into TF32 hi/lo, K-major SWIZZLE_128B.
-__global__ void prep_weight_image_bwd(const float* __restrict__ w1, const float* __restrict__ w2,
+static __global__ void prep_weight_image_bwd(const float* __restrict__ w1, const float* __restrict__ w2,
                                       int nout, unsigned char* __restrict__ img) {
   for (int i = threadIdx.x; i < kHid * 32; i += blockDim.x) {
     const int j = i / 32, o = i % 32;  // B3[j][o] = W2[o][j]

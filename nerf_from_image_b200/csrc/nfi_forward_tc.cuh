@@ -63,7 +63,7 @@ __host__ __device__ inline size_t tc_scratch_floats_per_group(int S) {
 // Builds the weight image: W1 split into TF32 hi/lo and laid out as the UMMA
 // B operand ([64 rows = hidden unit][32 k] fp32, K-major, SWIZZLE_128B), W2
 // transposed/padded, biases.
-__global__ void prep_weight_image(const float* __restrict__ w1, const float* __restrict__ b1,
+static __global__ void prep_weight_image(const float* __restrict__ w1, const float* __restrict__ b1,
                                   const float* __restrict__ w2, const float* __restrict__ b2,
                                   int nout, unsigned char* __restrict__ img, float scale1,
                                   float pad_b2, float scale2) {

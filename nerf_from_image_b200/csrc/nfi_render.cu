@@ -11,8 +11,7 @@
 #include "nfi_forward.cuh"
 #include "nfi_forward_tc.cuh"
 #include "nfi_forward_ws.cuh"
-#include "nfi_forward_pipe.cuh"
-#include "nfi_backward_pipe.cuh"
+#include "nfi_pipe_launch.h"
 #include "nfi_render.h"
 
 #define NFI_STR_(x) #x
@@ -97,12 +96,12 @@ size_t num_tc_ctas(const nfi_render_params* p) {
 bool tc_supported(const nfi_render_params* p) {
   if (p->compute_normals && !(p->mlp_mode & 0x1000)) return false;  // evaluation-only: SIMT kernel
   const int mode = p->mlp_mode & 0xff;
-  const bool pipe_mode = (mode == NFI_MLP_TC_PIPE || mode == NFI_MLP_AUTO);
+  const bool pipe_mode = (mode == NFI_MLP_TC_PIPE || mode == NFI_MLP_AUTO || mode == NFI_MLP_TC_WARPSPEC);
   // semantics: the pipelined kernel parks the coarse samples' probabilities; NOUT_PAD = 4 only
   // exists for palettes of <= 3 entries, kept on the SIMT kernel
   if (p->extra_mode == NFI_EXTRA_SEMANTICS && !(pipe_mode && p->n_attention > 3)) return false;
-  const int smax = (mode == NFI_MLP_TC_WARPSPEC) ? 128 : 64;  // per-ray columns in tile memory
-  if (mode == NFI_MLP_TC_PIPE || mode == NFI_MLP_AUTO)  // pipelined kernel: <= 4 samples per lane
+  const int smax = 64;  // lockstep kernel: per-ray columns in tile memory
+  if (pipe_mode)  // pipelined kernel: <= 4 samples per lane
     return p->num_samples <= 128 && p->num_samples % 4 == 0;  // in the resampler, float4 jitter
   if (p->fine_sampling && p->num_samples > smax) return false;
   return true;
@@ -151,49 +150,21 @@ template <int NP, int EX>
 int launch_fwd_tc_fine(const nfi_render_params& p, const unsigned char* wimg, float* scratch,
                        cudaStream_t st) {
   const int mode = p.mlp_mode & 0xff;
-  if (mode == NFI_MLP_TC_PIPE || mode == NFI_MLP_AUTO) {
-    // persistent pipelined kernel: one CTA per SM, tiles strided over the grid
+  if (mode == NFI_MLP_TC_PIPE || mode == NFI_MLP_AUTO || mode == NFI_MLP_TC_WARPSPEC) {
+    // persistent pipelined kernel (nfi_pipe.cu): one CTA per SM, tiles strided over the grid
     int dev = 0, sms = 0;
     NFI_CUDA(cudaGetDevice(&dev));
     NFI_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
     size_t grid = num_ctas(&p);
     if (grid > (size_t)sms) grid = sms;
     if (grid > kMaxPersistentCtas) grid = kMaxPersistentCtas;
-#define NFI_PIPE(FINE, DBG)                                                                  \
-  do {                                                                                       \
-    auto k = nfi::render_forward_pipe<NP, EX, FINE, 3, DBG>;                                 \
-    NFI_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize,            \
-                                  nfi::PipeCfg<3>::kSmBytes));                               \
-    k<<<(unsigned)grid, nfi::PipeCfg<3>::kThreadsTotal, nfi::PipeCfg<3>::kSmBytes, st>>>(    \
-        p, wimg, scratch);                                                                   \
-  } while (0)
-    if constexpr (NP == 12 && EX == 0) {
-      if ((p.mlp_mode & 0x1000) && p.fine_sampling) {  // phase-timer build (tools/phase_times_pipe.py)
-        NFI_PIPE(true, true);
-        NFI_CUDA(cudaGetLastError());
-        return 0;
-      }
-    }
-    if (p.fine_sampling && p.num_samples > 64) {  // 4 resampling slots per lane (S <= 128)
-      auto k = nfi::render_forward_pipe<NP, EX, true, 3, false, 4>;
-      NFI_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                    nfi::PipeCfg<3>::kSmBytes));
-      k<<<(unsigned)grid, nfi::PipeCfg<3>::kThreadsTotal, nfi::PipeCfg<3>::kSmBytes, st>>>(
-          p, wimg, scratch);
-    } else if (p.fine_sampling) {
-      NFI_PIPE(true, false);
-    } else {
-      NFI_PIPE(false, false);
-    }
-#undef NFI_PIPE
-    NFI_CUDA(cudaGetLastError());
-    return 0;
+    return nfi::launch_pipe_forward(p, NP, wimg, scratch, (unsigned)grid, st, g_err,
+                                    sizeof(g_err));
   }
   if constexpr (EX == 2) {
     return fail("semantics output on tensor cores: pipelined kernel only");
   } else {
-  const bool lockstep = mode != NFI_MLP_TC_WARPSPEC;
-  if (lockstep) {  // render_forward_tc: 4 tile groups per 512-thread CTA, one CTA per 2x2 tiles
+  {  // render_forward_tc: 4 tile groups per 512-thread CTA, one CTA per 2x2 tiles
     const size_t tx = (p.width + nfi::kTileW - 1) / nfi::kTileW;
     const size_t ty = (p.height + nfi::kTileH - 1) / nfi::kTileH;
     const unsigned grid = (unsigned)(((tx + 1) / 2) * ((ty + 1) / 2) * (size_t)p.batch);
@@ -211,24 +182,6 @@ int launch_fwd_tc_fine(const nfi_render_params& p, const unsigned char* wimg, fl
     NFI_CUDA(cudaGetLastError());
     return 0;
   }
-  int dev = 0, sms = 0;
-  NFI_CUDA(cudaGetDevice(&dev));
-  NFI_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-  size_t grid = num_tc_ctas(&p);
-  if (grid > (size_t)sms) grid = sms;
-  if (p.fine_sampling) {
-    auto k = nfi::render_forward_ws<NP, EX, true>;
-    NFI_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  nfi::kWsSmBytes));
-    k<<<(unsigned)grid, nfi::kWsThreads, nfi::kWsSmBytes, st>>>(p, wimg, scratch);
-  } else {
-    auto k = nfi::render_forward_ws<NP, EX, false>;
-    NFI_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  nfi::kWsSmBytes));
-    k<<<(unsigned)grid, nfi::kWsThreads, nfi::kWsSmBytes, st>>>(p, wimg, scratch);
-  }
-  NFI_CUDA(cudaGetLastError());
-  return 0;
   }
 }
 
@@ -237,11 +190,12 @@ int launch_fwd_tc(const nfi_render_params& p, int np, cudaStream_t st) {
   float* scratch = (float*)(wimg + kWeightImageBytes);
   const int nout = 1 + (p.n_attention > 0 ? p.n_attention : 3);
   const int wmode = p.mlp_mode & 0xff;
-  const bool pipe = (wmode == NFI_MLP_TC_PIPE || wmode == NFI_MLP_AUTO);
-  nfi::prep_weight_image<<<1, 256, 0, st>>>(p.w1, p.b1, p.w2, p.b2, nout, wimg,
-                                            pipe ? nfi::kLog2e : 1.f,
-                                            (pipe && p.n_attention > 0) ? nfi::kPadLogit : 0.f,
-                                            (pipe && p.n_attention > 0) ? nfi::kLog2e : 1.f);
+  const bool pipe = (wmode == NFI_MLP_TC_PIPE || wmode == NFI_MLP_AUTO || wmode == NFI_MLP_TC_WARPSPEC);
+  if (pipe) {
+    if (nfi::launch_pipe_weight_image(p, wimg, st)) return fail("weight image launch failed");
+  } else {
+    nfi::prep_weight_image<<<1, 256, 0, st>>>(p.w1, p.b1, p.w2, p.b2, nout, wimg, 1.f, 0.f, 1.f);
+  }
   NFI_CUDA(cudaGetLastError());
   const bool coords = p.extra_mode == NFI_EXTRA_COORDS;
   const bool sem = p.extra_mode == NFI_EXTRA_SEMANTICS;  // pipelined kernel only (tc_supported)
@@ -387,10 +341,8 @@ size_t nfi_render_workspace_bytes(const nfi_render_params* p) {
   if (p->fine_sampling) {
     fwd = num_ctas(p) * nfi::fwd_scratch_floats_per_cta(p->num_samples, ne_store_of(p)) *
           sizeof(float);
-    const size_t per_group =
-        nfi::pipe_scratch_floats(p->num_samples,
-                                 p->extra_mode == NFI_EXTRA_SEMANTICS ? nout_pad_of(p) - 1 : 0) *
-        sizeof(float);
+    const size_t per_group = nfi::pipe_scratch_bytes_per_cta(
+        p->num_samples, p->extra_mode == NFI_EXTRA_SEMANTICS ? nout_pad_of(p) - 1 : 0);
     const size_t ws = num_tc_ctas(p) * nfi::kWsGroups * per_group;
     const size_t tx = (p->width + nfi::kTileW - 1) / nfi::kTileW;
     const size_t ty = (p->height + nfi::kTileH - 1) / nfi::kTileH;
@@ -525,39 +477,13 @@ int nfi_render_backward(const nfi_render_params* params, const nfi_render_grads*
                      (!g.g_extra || g.out_extra) &&
                      ((g.grad_origins == nullptr) == (g.grad_dirs == nullptr));
   if (tc_ok) {
-    unsigned char* wimg = (unsigned char*)p.workspace;
-    const int nout = 1 + (p.n_attention > 0 ? p.n_attention : 3);
-    nfi::prep_weight_image<<<1, 256, 0, st>>>(p.w1, p.b1, p.w2, p.b2, nout, wimg, nfi::kLog2e,
-                                              p.n_attention > 0 ? nfi::kPadLogit : 0.f,
-                                              p.n_attention > 0 ? nfi::kLog2e : 1.f);
-    nfi::prep_weight_image_bwd<<<1, 256, 0, st>>>(p.w1, p.w2, nout, wimg + 32768);
-    NFI_CUDA(cudaGetLastError());
     int dev = 0, sms = 0;
     NFI_CUDA(cudaGetDevice(&dev));
     NFI_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
     size_t grid = num_ctas(&p);
     if (grid > (size_t)sms) grid = sms;
-    const bool cam = g.grad_origins != nullptr;
-    const bool coords = p.extra_mode == NFI_EXTRA_COORDS && g.g_extra != nullptr;
-    using Cfg = nfi::BwdCfg<2>;
-#define NFI_BWD(NP, EX, CAM)                                                               \
-  do {                                                                                     \
-    auto k = nfi::render_backward_pipe<NP, EX, CAM, 2>;                                    \
-    NFI_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize,          \
-                                  Cfg::kSmBytes));                                         \
-    k<<<(unsigned)grid, Cfg::kThreadsTotal, Cfg::kSmBytes, st>>>(p, g, wimg);              \
-  } while (0)
-#define NFI_BWD_NP(NP)                                                                     \
-  do {                                                                                     \
-    if (coords) { if (cam) NFI_BWD(NP, 1, true); else NFI_BWD(NP, 1, false); }             \
-    else { if (cam) NFI_BWD(NP, 0, true); else NFI_BWD(NP, 0, false); }                    \
-  } while (0)
-    const int np = nout_pad_of(params);
-    if (np == 4) NFI_BWD_NP(4); else if (np == 12) NFI_BWD_NP(12); else NFI_BWD_NP(16);
-#undef NFI_BWD_NP
-#undef NFI_BWD
-    NFI_CUDA(cudaGetLastError());
-    return 0;
+    return nfi::launch_pipe_backward(p, g, nout_pad_of(params), (unsigned char*)p.workspace,
+                                     (unsigned)grid, st, g_err, sizeof(g_err));
   }
   return nfi::launch_backward(*params, *grads, st, g_err, sizeof(g_err));
 }

@@ -14,7 +14,7 @@ pytestmark = pytest.mark.gpu
 TOL = 2e-4
 
 
-@pytest.fixture(autouse=True, params=[1, 2, 3, 4], ids=['simt', 'tc', 'tcws', 'pipe'])
+@pytest.fixture(autouse=True, params=[1, 2, 4], ids=['simt', 'tc', 'pipe'])
 def mlp_mode(request):
     """Every test below runs with the fp32 SIMT MLP and with the tcgen05
     3xTF32 MLP (S = 16 keeps the fine pass inside the tensor-core kernel's
@@ -64,7 +64,7 @@ def test_forward_variants(cuda_lib, fine, A, use_sdf):
 def test_forward_and_backward_sample_counts(cuda_lib, S, mlp_mode):
     """BASELINE config 5 sweeps 32 -> 128 samples per ray: the pipelined kernels take
     S <= 128 (2 or 4 resampling slots per lane), the older tensor-core kernels S <= 64."""
-    if mlp_mode in (2, 3) and S > 64:
+    if mlp_mode == 2 and S > 64:
         pytest.skip('lockstep / first warp-specialised kernel: S <= 64')
     B, H, W = 1, 16, 24
     scene, cams = Hh.make_case('p3d_bbox', batch=B)
@@ -86,7 +86,7 @@ def test_forward_and_backward_sample_counts(cuda_lib, S, mlp_mode):
 
 @pytest.mark.parametrize('mode', ['coords', 'semantics'])
 def test_extra_outputs(cuda_lib, mode, mlp_mode):
-    if mode == 'semantics' and mlp_mode in (2, 3):
+    if mode == 'semantics' and mlp_mode == 2:
         pytest.skip('semantics output: SIMT and pipelined kernels only')
     B, H, W, S = 2, 16, 16, 16
     scene, cams = Hh.make_case('p3d_plain', batch=B)
