@@ -39,9 +39,68 @@
 #include <type_traits>
 
 #include "nfi_forward_tc.cuh"
-#include "nfi_forward_ws.cuh"
 
 namespace nfi {
+
+// ------------------------------------------------------------------ small helpers
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tc::smem_u32(bar)) : "memory");
+}
+
+__device__ __forceinline__ float ld_relaxed(const float* p) {
+  float v;
+  asm volatile("ld.relaxed.cta.global.f32 %0, [%1];" : "=f"(v) : "l"(p) : "memory");
+  return v;
+}
+
+// Shell sort (gaps 23, 10, 4, 1) of a thread-private shared-memory column.
+__device__ __forceinline__ void column_sort(float* col, int n, int stride) {
+  const int gaps[4] = {23, 10, 4, 1};
+#pragma unroll 1
+  for (int gi = 0; gi < 4; ++gi) {
+    const int gap = gaps[gi];
+    for (int i = gap; i < n; ++i) {
+      const float v = col[i * stride];
+      int j = i - gap;
+      while (j >= 0 && col[j * stride] > v) {
+        col[(j + gap) * stride] = col[j * stride];
+        j -= gap;
+      }
+      col[(j + gap) * stride] = v;
+    }
+  }
+}
+
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n.reg .pred p;\nelect.sync _|p, 0xffffffff;\nselp.u32 %0, 1, 0, p;\n}\n"
+      : "=r"(pred));
+  return pred != 0;
+}
+
+struct TileCoord {
+  int b, tile_x, tile_y;
+};
+
+__device__ __forceinline__ TileCoord tile_coord(int tile, int tiles_x, int tiles_y) {
+  TileCoord c;
+  const int per_img = tiles_x * tiles_y;
+  c.b = tile / per_img;
+  const int r = tile % per_img;
+  // 2x2 blocks of tiles are consecutive: the two groups of a CTA (and the next
+  // CTA) work on neighbouring tiles of the same image -> shared texels in L1/L2
+  const int bx = (tiles_x + 1) / 2;
+  const int blk = r / 4, in = r % 4;
+  int tx = 2 * (blk % bx) + (in & 1), ty = 2 * (blk / bx) + (in >> 1);
+  if ((tiles_x & 1) || (tiles_y & 1)) {  // odd tile grids: plain row-major order
+    tx = r % tiles_x;
+    ty = r / tiles_x;
+  }
+  c.tile_x = tx;
+  c.tile_y = ty;
+  return c;
+}
 
 constexpr int kPipeSlots = 3;
 constexpr int kPipeSlotCols = 160;  // [0,64) D1 then H_lo, [64,128) H_hi, [128,144) D2

@@ -10,7 +10,6 @@
 #include "nfi_backward.cuh"
 #include "nfi_forward.cuh"
 #include "nfi_forward_tc.cuh"
-#include "nfi_forward_ws.cuh"
 #include "nfi_pipe_launch.h"
 #include "nfi_render.h"
 
@@ -86,9 +85,9 @@ constexpr size_t kBackwardWorkspaceBytes = 65536;  // forward + backward weight 
 
 constexpr size_t kMaxPersistentCtas = 160;  // >= SM count of any sm_100 part (B200: 148)
 
-// persistent warp-specialised kernel: one CTA per SM, two tiles in flight per CTA
-size_t num_tc_ctas(const nfi_render_params* p) {
-  const size_t want = (num_ctas(p) + nfi::kWsGroups - 1) / nfi::kWsGroups;
+// persistent pipelined kernels (nfi_pipe.cu): one CTA per SM, one scratch slab per CTA
+size_t num_tc_ctas(const nfi_render_params* p) {  // persistent grid: at most one CTA per SM
+  const size_t want = num_ctas(p);
   return want < kMaxPersistentCtas ? want : kMaxPersistentCtas;
 }
 
@@ -339,16 +338,23 @@ size_t nfi_render_workspace_bytes(const nfi_render_params* p) {
   if (p == nullptr) return 0;
   size_t fwd = 0;
   if (p->fine_sampling) {
-    fwd = num_ctas(p) * nfi::fwd_scratch_floats_per_cta(p->num_samples, ne_store_of(p)) *
-          sizeof(float);
-    const size_t per_group = nfi::pipe_scratch_bytes_per_cta(
-        p->num_samples, p->extra_mode == NFI_EXTRA_SEMANTICS ? nout_pad_of(p) - 1 : 0);
-    const size_t ws = num_tc_ctas(p) * nfi::kWsGroups * per_group;
-    const size_t tx = (p->width + nfi::kTileW - 1) / nfi::kTileW;
-    const size_t ty = (p->height + nfi::kTileH - 1) / nfi::kTileH;
-    const size_t ls = ((tx + 1) / 2) * ((ty + 1) / 2) * (size_t)p->batch * nfi::kGroups * per_group;
-    if (ws > fwd) fwd = ws;
-    if (ls > fwd) fwd = ls;
+    // scratch for the coarse samples, sized for the kernel that will run
+    const int mode = p->mlp_mode & 0xff;
+    const bool pipe_mode =
+        (mode == NFI_MLP_TC_PIPE || mode == NFI_MLP_AUTO || mode == NFI_MLP_TC_WARPSPEC);
+    if (pipe_mode && tc_supported(p)) {  // persistent: one slab per CTA (<= one per SM)
+      fwd = num_tc_ctas(p) * nfi::pipe_scratch_bytes_per_cta(
+                                 p->num_samples,
+                                 p->extra_mode == NFI_EXTRA_SEMANTICS ? nout_pad_of(p) - 1 : 0);
+    } else if (mode == NFI_MLP_TC_3XTF32) {  // lockstep: one slab per tile group of every CTA
+      const size_t tx = (p->width + nfi::kTileW - 1) / nfi::kTileW;
+      const size_t ty = (p->height + nfi::kTileH - 1) / nfi::kTileH;
+      fwd = ((tx + 1) / 2) * ((ty + 1) / 2) * (size_t)p->batch * nfi::kGroups *
+            nfi::pipe_scratch_bytes_per_cta(p->num_samples, 0);
+    } else {  // fp32 SIMT kernel: one slab per CTA (= tile)
+      fwd = num_ctas(p) * nfi::fwd_scratch_floats_per_cta(p->num_samples, ne_store_of(p)) *
+            sizeof(float);
+    }
   }
   return kWeightImageBytes + fwd + 256;
 }
