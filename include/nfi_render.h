@@ -35,7 +35,7 @@
 extern "C" {
 #endif
 
-#define NFI_ABI_VERSION 2
+#define NFI_ABI_VERSION 3
 
 #if defined(__GNUC__)
 #define NFI_API __attribute__((visibility("default")))
@@ -200,6 +200,51 @@ NFI_API int nfi_fill_uniform(float *dst, int64_t n, uint64_t seed, uint32_t stre
  * copies rgb/depth/mask/extra/normals out and synchronises.  This is the
  * end-to-end entry the bench's `e2e` figure is measured through. */
 NFI_API int nfi_render_forward_host(const nfi_render_params *params, int32_t device);
+
+/* ---- secondary seam: the generator's `sampler` closure ----
+ * models/generator.py:587-681 evaluated at arbitrary points: x = points / scene_range,
+ * tri-plane fetch, decoder, then whichever of the outputs below are non-NULL.  Forward only
+ * (the regulariser heads that differentiate through the closure stay on the reference path).
+ * fp32 SIMT arithmetic -- this seam serves point clouds (marching cubes, the 31^3 regulariser
+ * grids, SDF pre-training targets), not the per-ray hot loop. */
+typedef struct nfi_sample_params {
+  int32_t batch;       /* B */
+  int32_t plane_res;   /* R */
+  int32_t n_attention; /* A (0: three colour logits -> wide sigmoid) */
+  int32_t use_sdf;
+  int32_t bbox_debug;  /* 1: sigma += 100 on the cube's edges (generator.py:640-657) */
+  float scene_range;
+  int64_t n_points;    /* N points per image */
+  const float *planes; /* [B,3,R,R,32] channel-last */
+  const float *w1; /* effective decoder weights, as nfi_render_params */
+  const float *b1;
+  const float *w2;
+  const float *b2;
+  const float *palette; /* [B,A,3] or NULL */
+  const float *beta; /* device scalars (use_sdf) */
+  const float *alpha;
+  const float *points;  /* [B,N,3] world units (x_in) */
+  float *sdf_distance;  /* [B,N]   decoder output 0 ('sdf_distance')   or NULL */
+  float *sigma;         /* [B,N]   ('sigma')                            or NULL */
+  float *rgb;           /* [B,N,3] ('rgb')                              or NULL */
+  float *semantics;     /* [B,N,A] softmax probabilities ('semantics')  or NULL */
+  float *normals;       /* [B,N,3] normalised grad of the SDF ('normals') or NULL */
+} nfi_sample_params;
+NFI_API int nfi_sample_field(const nfi_sample_params *params, void *stream);
+
+/* ---- neighbour of the path in the inversion loop ----
+ * lib/pose_utils.py:48-70 pose_to_matrix: (z0|NULL, t2 [B,2], s [B], q [B,4] unit quaternion)
+ * -> tform_cam2world [B,4,4] (+ focal [B] = (1 + e^z0) / 2 when z0 is given; z0 == NULL is the
+ * orthographic model: translation (t2, 10), whole matrix divided by s).  One thread per image. */
+NFI_API int nfi_pose_to_matrix(const float *z0, const float *t2, const float *s, const float *q,
+                               int32_t camera_flipped, int32_t batch, float *c2w, float *focal,
+                               void *stream);
+/* its vector-Jacobian product: g_c2w [B,4,4], g_focal [B]|NULL in; g_z0 (NULL iff z0 NULL),
+ * g_t2, g_s, g_q out (overwritten). */
+NFI_API int nfi_pose_to_matrix_backward(const float *z0, const float *t2, const float *s,
+                                        const float *q, int32_t camera_flipped, int32_t batch,
+                                        const float *g_c2w, const float *g_focal, float *g_z0,
+                                        float *g_t2, float *g_s, float *g_q, void *stream);
 
 #ifdef __cplusplus
 }

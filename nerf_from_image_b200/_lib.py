@@ -14,6 +14,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, 'csrc', 'libnfi_render.so')
 
 c_float_p = ctypes.POINTER(ctypes.c_float)
+ABI_VERSION = 3  # NFI_ABI_VERSION of include/nfi_render.h
 
 EXTRA_NONE, EXTRA_COORDS, EXTRA_SEMANTICS = 0, 1, 2
 NOISE_DETERMINISTIC, NOISE_EXPLICIT, NOISE_PHILOX = 0, 1, 2
@@ -55,6 +56,18 @@ class RenderGrads(ctypes.Structure):
         'grad_dirs')]
 
 
+class SampleParams(ctypes.Structure):
+    """struct nfi_sample_params."""
+    _fields_ = [
+        ('batch', ctypes.c_int32), ('plane_res', ctypes.c_int32),
+        ('n_attention', ctypes.c_int32), ('use_sdf', ctypes.c_int32),
+        ('bbox_debug', ctypes.c_int32), ('scene_range', ctypes.c_float),
+        ('n_points', ctypes.c_int64),
+    ] + [(n, ctypes.c_void_p) for n in (
+        'planes', 'w1', 'b1', 'w2', 'b2', 'palette', 'beta', 'alpha', 'points',
+        'sdf_distance', 'sigma', 'rgb', 'semantics', 'normals')]
+
+
 # every symbol include/nfi_render.h declares (tests/test_abi.py checks the
 # header against this table and the table against the built library)
 EXPORTS = {
@@ -82,6 +95,14 @@ EXPORTS = {
                                                ctypes.c_int32]),
     'nfi_fill_uniform': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int64, ctypes.c_uint64,
                                         ctypes.c_uint32, ctypes.c_int64, ctypes.c_void_p]),
+    'nfi_sample_field': (ctypes.c_int, [ctypes.POINTER(SampleParams), ctypes.c_void_p]),
+    'nfi_pose_to_matrix': (ctypes.c_int, [
+        ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int32,
+        ctypes.c_int32, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]),
+    'nfi_pose_to_matrix_backward': (ctypes.c_int, [
+        ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int32,
+        ctypes.c_int32, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
+        ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]),
 }
 
 _lib = None
@@ -120,7 +141,7 @@ def load():
                 fn = getattr(lib, name)
                 fn.restype = restype
                 fn.argtypes = argtypes
-            if lib.nfi_abi_version() != 2:
+            if lib.nfi_abi_version() != ABI_VERSION:
                 raise NfiError('libnfi_render.so ABI version mismatch')
             _lib = lib
     return _lib

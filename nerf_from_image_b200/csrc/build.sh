@@ -1,9 +1,10 @@
 #!/bin/bash
 # Builds libnfi_render.so in-tree for sm_100a (cross-compiles without a GPU).
-# Two translation units compiled in parallel: the pipelined tcgen05 kernels (nfi_pipe.cu)
-# and everything else (nfi_render.cu: C ABI, re-layout, SIMT and lockstep kernels).  The
-# second one takes --split-compile 0 (its kernels are optimised in parallel); the first does
-# not: the pipelined forward kernel schedules ~3 % slower with it (measured).
+# Three translation units compiled in parallel: the pipelined tcgen05 kernels (nfi_pipe.cu),
+# the sampler seam and pose kernels (nfi_field.cu), and everything else (nfi_render.cu: C ABI,
+# re-layout, SIMT and lockstep kernels).  Only nfi_render.cu takes --split-compile 0 (its many
+# kernels are optimised in parallel); the pipelined forward kernel schedules ~3 % slower with
+# it (measured).
 set -e
 cd "$(dirname "$0")"
 NVCC=${NVCC:-/usr/local/cuda/bin/nvcc}
@@ -11,7 +12,10 @@ FLAGS="-O3 -std=c++17 --fmad=false -lineinfo -gencode arch=compute_100a,code=sm_
   -Xcompiler -fPIC -Xcompiler -fvisibility=hidden -I../../include ${NFI_PTXAS_V:+-Xptxas -v}"
 $NVCC $FLAGS -c -o nfi_pipe.o nfi_pipe.cu "$@" &
 pipe_pid=$!
+$NVCC $FLAGS -c -o nfi_field.o nfi_field.cu "$@" &
+field_pid=$!
 $NVCC $FLAGS --split-compile 0 -c -o nfi_render.o nfi_render.cu "$@"
 wait $pipe_pid
+wait $field_pid
 $NVCC -shared -cudart static -gencode arch=compute_100a,code=sm_100a \
-  -Xcompiler -fPIC -o libnfi_render.so nfi_render.o nfi_pipe.o
+  -Xcompiler -fPIC -o libnfi_render.so nfi_render.o nfi_pipe.o nfi_field.o

@@ -332,6 +332,37 @@ __device__ __forceinline__ void mlp_forward(const float* __restrict__ frow,
   }
 }
 
+// d sdf / d(texel-unit coordinates) = W2[0,:] diag(sigmoid(pre)) W1 dF/dx  (analytic form of
+// the autograd.grad call of models/generator.py:614-623).  `h` holds the 64 pre-activations on
+// entry (mlp_forward<.., KEEP = true>) and is overwritten; Gw is this warp's
+// gather_features_grad block.  The caller applies (R-1)/2 / 3 / scene_range.
+template <int NOUT_PAD>
+__device__ __forceinline__ void sdf_gradient(float (&h)[kHid], const float* __restrict__ W1t,
+                                             const float* __restrict__ W2t,
+                                             const float* __restrict__ Gw, int lane, float& n0,
+                                             float& n1, float& n2) {
+#pragma unroll
+  for (int j = 0; j < kHid; ++j)
+    h[j] = W2t[j * NOUT_PAD] * (h[j] > 20.f ? 1.f : 1.f / (1.f + expf(-h[j])));
+  n0 = n1 = n2 = 0.f;
+#pragma unroll 1
+  for (int c = 0; c < kC; ++c) {
+    const float4* wr = reinterpret_cast<const float4*>(W1t + c * kHid);
+    float u = 0.f;
+#pragma unroll
+    for (int j4 = 0; j4 < kHid / 4; ++j4) {
+      const float4 w = wr[j4];
+      u = fmaf(w.x, h[4 * j4 + 0], u);
+      u = fmaf(w.y, h[4 * j4 + 1], u);
+      u = fmaf(w.z, h[4 * j4 + 2], u);
+      u = fmaf(w.w, h[4 * j4 + 3], u);
+    }
+    n0 = fmaf(u, Gw[lane * kFRow + c], n0);
+    n1 = fmaf(u, Gw[(32 + lane) * kFRow + c], n1);
+    n2 = fmaf(u, Gw[(64 + lane) * kFRow + c], n2);
+  }
+}
+
 // Density and colour from the decoder outputs (models/generator.py:625-679).
 struct FieldConst {
   float inv_beta;   // 1 / beta

@@ -193,27 +193,8 @@ render_forward_simt(const nfi_render_params p) {
       float* Gw = sm.G + warp * 3 * 32 * kFRow;
       gather_features_grad(planes_b, p.plane_res, x0, x1, x2, Fw, Gw, lane);
       mlp_forward<NOUT_PAD, true>(frow, sm.W1t, sm.b1, sm.W2t, sm.b2, out, h);  // h = pre-activations
-      // d sdf / d x = W2[0,:] diag(sigmoid(pre)) W1 dF/dx
-#pragma unroll
-      for (int j = 0; j < kHid; ++j)
-        h[j] = sm.W2t[j * NOUT_PAD] * (h[j] > 20.f ? 1.f : 1.f / (1.f + expf(-h[j])));
-      float n0 = 0.f, n1 = 0.f, n2 = 0.f;
-#pragma unroll 1
-      for (int c = 0; c < kC; ++c) {
-        const float4* wr = reinterpret_cast<const float4*>(sm.W1t + c * kHid);
-        float u = 0.f;
-#pragma unroll
-        for (int j4 = 0; j4 < kHid / 4; ++j4) {
-          const float4 w = wr[j4];
-          u = fmaf(w.x, h[4 * j4 + 0], u);
-          u = fmaf(w.y, h[4 * j4 + 1], u);
-          u = fmaf(w.z, h[4 * j4 + 2], u);
-          u = fmaf(w.w, h[4 * j4 + 3], u);
-        }
-        n0 = fmaf(u, Gw[lane * kFRow + c], n0);
-        n1 = fmaf(u, Gw[(32 + lane) * kFRow + c], n1);
-        n2 = fmaf(u, Gw[(64 + lane) * kFRow + c], n2);
-      }
+      float n0, n1, n2;
+      sdf_gradient<NOUT_PAD>(h, sm.W1t, sm.W2t, Gw, lane, n0, n1, n2);
       // common factors of the chain: (R-1)/2 per texel unit, 1/3 plane mean, 1/scene_range
       const float sc = 0.5f * (float)(p.plane_res - 1) / (3.f * p.scene_range);
       n0 *= sc;

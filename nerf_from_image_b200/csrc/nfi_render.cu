@@ -10,6 +10,7 @@
 #include "nfi_backward.cuh"
 #include "nfi_forward.cuh"
 #include "nfi_forward_tc.cuh"
+#include "nfi_field_launch.h"
 #include "nfi_pipe_launch.h"
 #include "nfi_render.h"
 
@@ -492,6 +493,67 @@ int nfi_render_backward(const nfi_render_params* params, const nfi_render_grads*
                                      (unsigned)grid, st, g_err, sizeof(g_err));
   }
   return nfi::launch_backward(*params, *grads, st, g_err, sizeof(g_err));
+}
+
+int nfi_sample_field(const nfi_sample_params* sp, void* stream) {
+  if (sp == nullptr) return fail("params is NULL");
+  if (sp->batch <= 0 || sp->batch > 65535 || sp->n_points <= 0) return fail("empty point set");
+  if (sp->n_points > ((int64_t)1 << 37)) return fail("too many points per image");
+  if (sp->plane_res < 2) return fail("plane_res must be >= 2");
+  if (sp->n_attention < 0 || sp->n_attention > NFI_MAX_ATTENTION)
+    return fail("attention_values must be in [0, 15]");
+  if (!(sp->scene_range > 0.f)) return fail("scene_range must be positive");
+  if (!sp->planes || !sp->w1 || !sp->b1 || !sp->w2 || !sp->b2 || !sp->points)
+    return fail("planes / decoder weights / points must be given");
+  if (sp->n_attention > 0 && !sp->palette)
+    return fail("palette missing (attention_values > 0)");
+  if (sp->use_sdf && (!sp->beta || !sp->alpha)) return fail("use_sdf needs beta and alpha");
+  if (sp->semantics && sp->n_attention <= 0)
+    return fail("'semantics' needs attention_values > 0");  // generator.py:673
+  if (sp->normals && !sp->use_sdf) return fail("'normals' needs use_sdf");  // generator.py:600
+  if (sp->bbox_debug && !sp->sigma) return fail("bbox_debug modifies sigma: request it");
+  if (!sp->sdf_distance && !sp->sigma && !sp->rgb && !sp->semantics && !sp->normals)
+    return fail("no sampler output requested");
+  nfi_render_params p;
+  memset(&p, 0, sizeof(p));
+  p.batch = sp->batch;
+  p.plane_res = sp->plane_res;
+  p.n_attention = sp->n_attention;
+  p.use_sdf = sp->use_sdf;
+  p.scene_range = sp->scene_range;
+  p.planes = sp->planes;
+  p.w1 = sp->w1;
+  p.b1 = sp->b1;
+  p.w2 = sp->w2;
+  p.b2 = sp->b2;
+  p.palette = sp->palette;
+  p.beta = sp->beta;
+  p.alpha = sp->alpha;
+  return nfi::launch_sample_field(p, *sp, nout_pad_of(&p), (cudaStream_t)stream, g_err,
+                                  sizeof(g_err));
+}
+
+int nfi_pose_to_matrix(const float* z0, const float* t2, const float* s, const float* q,
+                       int32_t camera_flipped, int32_t batch, float* c2w, float* focal,
+                       void* stream) {
+  if (batch <= 0) return fail("empty batch");
+  if (!t2 || !s || !q || !c2w) return fail("t2 / s / q / c2w must be given");
+  if (z0 && !focal) return fail("perspective pose (z0 given) needs the focal output");
+  return nfi::launch_pose_to_matrix(z0, t2, s, q, camera_flipped, batch, c2w, focal,
+                                    (cudaStream_t)stream, g_err, sizeof(g_err));
+}
+
+int nfi_pose_to_matrix_backward(const float* z0, const float* t2, const float* s, const float* q,
+                                int32_t camera_flipped, int32_t batch, const float* g_c2w,
+                                const float* g_focal, float* g_z0, float* g_t2, float* g_s,
+                                float* g_q, void* stream) {
+  if (batch <= 0) return fail("empty batch");
+  if (!t2 || !s || !q || !g_c2w || !g_t2 || !g_s || !g_q)
+    return fail("t2 / s / q / g_c2w and the three gradient outputs must be given");
+  if (z0 && !g_z0) return fail("perspective pose (z0 given) needs g_z0");
+  return nfi::launch_pose_to_matrix_backward(z0, t2, s, q, camera_flipped, batch, g_c2w, g_focal,
+                                             g_z0, g_t2, g_s, g_q, (cudaStream_t)stream, g_err,
+                                             sizeof(g_err));
 }
 
 int nfi_render_forward_host(const nfi_render_params* hp, int32_t device) {

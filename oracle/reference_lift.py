@@ -134,3 +134,25 @@ def reference_render(scene, cams, height, width, num_samples, seed=None,
         if fine_sampling:
             noise_u = torch.rand(B * height * width, num_samples)
     return out, noise_t, noise_u
+
+
+def reference_sampler(scene, x_in, request, use_sdf=True, bbox_debug=False, generator=None):
+    """Calls the reference Generator's own ``sampler`` closure
+    (models/generator.py:587-681) at ``x_in`` [B, ..., S, 3]; returns its dict."""
+    A = scene['palette'].shape[1] if scene['palette'] is not None else 0
+    g = generator if generator is not None else build_reference_generator(scene, use_sdf)
+    planes = scene['planes']
+    B, _, C, R, _ = planes.shape
+    g.synthesis_network.planes = planes.reshape(B, 3 * C, R, R)
+    ws = torch.zeros(B, 15 if A > 0 else 14, 512)
+    extra_in = {'attention_values': scene['palette']} if A > 0 else {}
+    outputs = ['sampler'] + (['bbox'] if bbox_debug else [])
+    closure = g(None, ws, request_model_outputs=outputs, model_inputs=extra_in)['sampler']
+    return closure(x_in, request_sampler_outputs=list(request))
+
+
+def reference_pose_utils():
+    """The reference's lib.pose_utils module (lib/pose_utils.py)."""
+    _import_reference()
+    from lib import pose_utils  # noqa
+    return pose_utils

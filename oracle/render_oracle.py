@@ -196,6 +196,57 @@ def field(points, planes, w1, b1, w2, b2, palette, beta, alpha, scene_range,
     return sigma, rgb, probs, normals
 
 
+def sampler(x_in, planes, w1, b1, w2, b2, palette, beta, alpha, scene_range,
+            request=('sigma', 'rgb'), use_sdf=True, bbox_debug=False):
+    """The generator's ``sampler`` closure (models/generator.py:587-681) as a dict
+    of flat outputs: 'sdf_distance' [B,N,1], 'sigma' [B,N], 'rgb' [B,N,3],
+    'semantics' [B,N,A], 'normals' (x_in's shape), 'coords' (= x_in).
+    ``x_in`` is [B, ..., 3] in world units."""
+    out = {}
+    bs = x_in.shape[0]
+    pts = x_in.reshape(bs, -1, 3)
+    if 'normals' in request:
+        pts = pts.detach().requires_grad_()
+    x = pts / scene_range
+    with torch.no_grad():
+        outside = (x.abs() > 1).any(dim=-1).float()
+    dec = triplane_decoder(planes, x, w1, b1, w2, b2)
+    dist, feat = dec[..., :1], dec[..., 1:]
+    if 'normals' in request:
+        grad, = torch.autograd.grad(dist[..., -1].sum(), pts, create_graph=False)
+        out['normals'] = F.normalize(grad, dim=-1).reshape(x_in.shape)
+        dist, feat = dist.detach(), feat.detach()
+    if 'sdf_distance' in request:
+        out['sdf_distance'] = dist
+    if 'sigma' in request:
+        if use_sdf:
+            nd = -dist[..., -1]
+            cdf = 0.5 + 0.5 * torch.sign(nd) * (1 - torch.exp(-nd.abs() / beta))
+            sigma = (1 / alpha) * (cdf * (1 - outside))
+        else:
+            sigma = F.softplus(dist[..., -1] - 1) * (1 - outside)
+        if bbox_debug and 'coords' in request:  # generator.py:640-657
+            a = pts.detach().abs()
+            inside = a < scene_range - 5e-2
+            m = torch.ones_like(sigma)
+            for i, j in ((0, 1), (0, 2), (1, 2), (1, 2)):
+                m = m * (1 - (inside[..., i] & inside[..., j]).float())
+            sigma = sigma + 100 * (m * (1 - outside))
+        out['sigma'] = sigma
+    if 'coords' in request:
+        out['coords'] = x_in
+    if 'rgb' in request or 'semantics' in request:
+        if palette is not None:
+            probs = F.softmax(feat, dim=-1)
+            if 'semantics' in request:
+                out['semantics'] = probs
+            if 'rgb' in request:
+                out['rgb'] = torch.matmul(probs, palette)
+        elif 'rgb' in request:
+            out['rgb'] = torch.sigmoid(feat) * 2.004 - 1.002
+    return out
+
+
 # --------------------------------------------------------------------------
 # quadrature
 # --------------------------------------------------------------------------

@@ -17,7 +17,7 @@ def header_functions():
 
 def test_header_and_binding_agree():
     names = header_functions()
-    assert len(names) >= 9
+    assert len(names) >= 12
     assert sorted(names) == sorted(_lib.EXPORTS)
 
 
@@ -25,7 +25,8 @@ def test_library_exports_every_declared_symbol():
     lib = _lib.load()
     for name in header_functions():
         assert hasattr(lib, name), name
-    assert lib.nfi_abi_version() == 2
+    assert lib.nfi_abi_version() == _lib.ABI_VERSION
+    assert ('#define NFI_ABI_VERSION %d' % _lib.ABI_VERSION) in open(HEADER).read()
     assert b'sm_100a' in lib.nfi_build_info()
 
 
@@ -33,7 +34,8 @@ def test_struct_layout_matches_header():
     """Field order / count of the ctypes mirrors vs the C structs."""
     src = open(HEADER).read()
     for cname, cls in (('nfi_render_params', _lib.RenderParams),
-                       ('nfi_render_grads', _lib.RenderGrads)):
+                       ('nfi_render_grads', _lib.RenderGrads),
+                       ('nfi_sample_params', _lib.SampleParams)):
         body = re.search(r'typedef struct %s \{(.*?)\} %s;' % (cname, cname), src, re.S).group(1)
         body = re.sub(r'/\*.*?\*/', '', body, flags=re.S)
         fields = [re.search(r'(\w+)\s*$', d.strip()).group(1)

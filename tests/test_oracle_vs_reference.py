@@ -6,6 +6,7 @@ tests/test_golden.py carries the same information as committed vectors.
 import pytest
 import torch
 
+from oracle import pose_oracle as PO
 from oracle import reference_lift as RL
 from oracle import render_oracle as O
 from tests import helpers as Hh
@@ -78,3 +79,84 @@ def test_missed_rays_do_not_need_the_global_fallback():
     assert (~hit).any() and hit.any()
     for k in ('rgb', 'depth', 'mask'):
         assert torch.equal(a[k], b[k]), k
+
+
+def sampler_points(scene, batch, n, seed):
+    """Points filling the cube and a margin outside it (the out-of-box mask must trigger)."""
+    g = torch.Generator().manual_seed(seed)
+    return (torch.rand(batch, 5, n // 5, 3, generator=g) * 2 - 1) * 1.15 * scene['scene_range']
+
+
+@pytest.mark.parametrize('A,use_sdf,request_', [
+    (10, True, ['sigma', 'rgb']),
+    (10, True, ['sdf_distance', 'sigma', 'rgb', 'semantics', 'coords']),
+    (0, True, ['sigma', 'rgb', 'sdf_distance']),
+    (10, False, ['sigma', 'rgb']),
+])
+def test_sampler_matches_reference(A, use_sdf, request_):
+    scene, _ = Hh.make_case('p3d_plain', seed=12, batch=2, plane_res=24, attention_values=A)
+    x = sampler_points(scene, 2, 200, 3)
+    with torch.no_grad():
+        ref = RL.reference_sampler(scene, x, request_, use_sdf=use_sdf)
+        o = O.sampler(x, scene['planes'], scene['w1'], scene['b1'], scene['w2'], scene['b2'],
+                      scene['palette'], scene['beta'], scene['alpha'], scene['scene_range'],
+                      request=request_, use_sdf=use_sdf)
+    assert sorted(ref) == sorted(o)
+    for k in ref:
+        assert ref[k].shape == o[k].shape, k
+        assert (ref[k] - o[k]).abs().max().item() < 2e-5, k
+
+
+def test_sampler_normals_and_bbox_match_reference():
+    scene, _ = Hh.make_case('p3d_plain', seed=13, batch=2, plane_res=24)
+    x = sampler_points(scene, 2, 200, 4)
+    ref = RL.reference_sampler(scene, x.clone(), ['normals', 'sigma'])
+    o = O.sampler(x, scene['planes'], scene['w1'], scene['b1'], scene['w2'], scene['b2'],
+                  scene['palette'], scene['beta'], scene['alpha'], scene['scene_range'],
+                  request=['normals', 'sigma'])
+    assert ref['normals'].shape == o['normals'].shape == x.shape
+    assert (ref['normals'] - o['normals']).abs().max().item() < 1e-4
+    assert (ref['sigma'] - o['sigma']).abs().max().item() < 2e-5
+    with torch.no_grad():
+        ref = RL.reference_sampler(scene, x, ['sigma', 'coords'], bbox_debug=True)
+        o = O.sampler(x, scene['planes'], scene['w1'], scene['b1'], scene['w2'], scene['b2'],
+                      scene['palette'], scene['beta'], scene['alpha'], scene['scene_range'],
+                      request=['sigma', 'coords'], bbox_debug=True)
+    assert (ref['sigma'] > 50).any()
+    assert (ref['sigma'] - o['sigma']).abs().max().item() < 2e-5
+
+
+def pose_inputs(seed, batch, persp):
+    g = torch.Generator().manual_seed(seed)
+    q = torch.nn.functional.normalize(torch.randn(batch, 4, generator=g), dim=-1)
+    t2 = 0.3 * torch.randn(batch, 2, generator=g)
+    s = 0.8 + 0.5 * torch.rand(batch, generator=g)
+    z0 = 0.5 * torch.randn(batch, generator=g) if persp else None
+    return z0, t2, s, q
+
+
+@pytest.mark.parametrize('persp', [True, False])
+@pytest.mark.parametrize('flipped', [True, False])
+def test_pose_to_matrix_matches_reference(persp, flipped):
+    pu = RL.reference_pose_utils()
+    z0, t2, s, q = pose_inputs(5, 6, persp)
+    leaves = [t.clone().requires_grad_() for t in (z0, t2, s, q) if t is not None]
+    leaves_o = [t.clone().requires_grad_() for t in (z0, t2, s, q) if t is not None]
+    args = lambda L: ((L[0], L[1], L[2], L[3]) if persp else (None, L[0], L[1], L[2]))
+    mat_r, f_r = pu.pose_to_matrix(*args(leaves), flipped)
+    mat_o, f_o = PO.pose_to_matrix(*args(leaves_o), flipped)
+    assert torch.equal(mat_r, mat_o)
+    assert (f_r is None) == (f_o is None)
+    g = torch.Generator().manual_seed(9)
+    wm = torch.randn(6, 4, 4, generator=g)
+    wf = torch.randn(6, generator=g)
+    loss = lambda m, f: (m * wm).sum() + ((f * wf).sum() if f is not None else 0)
+    gr = torch.autograd.grad(loss(mat_r, f_r), leaves)
+    go = torch.autograd.grad(loss(mat_o, f_o), leaves_o)
+    for a, b in zip(gr, go):
+        assert (a - b).abs().max().item() < 1e-5
+    # (lib/pose_utils.py:72 matrix_to_pose, the reference's inverse, does not run under
+    # numpy >= 2 -- np.array(copy=False) -- so the round trip is not checked through it)
+    rows = PO.quaternion_rows(q)
+    eye = torch.eye(3).expand(6, 3, 3)
+    assert (rows @ rows.transpose(-1, -2) - eye).abs().max().item() < 1e-5
