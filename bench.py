@@ -246,14 +246,19 @@ def main():
         with torch.no_grad():
             if time_kernel:
                 fused.KERNEL_EVENTS = kernel_events
+            out = full = None
+            if world > 1:
+                # the path's one exchange step, in place: the kernel writes this rank's tiles
+                # into its slice of the full-batch buffers, NCCL all-gathers them where they lie
+                full = parallel.gathered_buffers(world * B, H, W, dev)
+                out = parallel.shard_views(full, world * B, world, rank)
             rgb, depth, mask, _ = fused.fused_render(
                 scene['planes'], scene['w1'], scene['b1'], scene['w2'], scene['b2'],
                 scene['palette'], scene['beta'], scene['alpha'], cams['c2w'], cams['focal'],
-                None, None, cfg, H, W, S, nt, nu)
+                None, None, cfg, H, W, S, nt, nu, out=out)
             fused.KERNEL_EVENTS = None
             if world > 1:
-                # the path's one exchange step: packed [rgb, depth, mask] tiles to every rank
-                rgb, depth, mask = parallel.all_gather_outputs(rgb, depth, mask, world * B)
+                rgb, depth, mask = parallel.all_gather_inplace(full, world * B)
         return rgb, depth, mask
 
     for _ in range(args.warmup):

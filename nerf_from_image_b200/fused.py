@@ -138,7 +138,7 @@ class FusedTriplaneRender(torch.autograd.Function):
     @staticmethod
     def forward(ctx, planes, w1, b1, w2, b2, palette, beta, alpha, c2w, focal,
                 center, bbox, cfg, height, width, S, noise_t, noise_u,
-                extra_mode, cam_grad, compute_normals=False):
+                extra_mode, cam_grad, compute_normals=False, out=None):
         _check_shapes(cfg, planes, w1, b1, w2, b2, palette, c2w, focal, center,
                       bbox, height, width, S, noise_t, noise_u)
         lib = _lib.load()
@@ -159,9 +159,20 @@ class FusedTriplaneRender(torch.autograd.Function):
             B = planes.shape[0]
             A = cfg.attention_values
             needs_grad = any(ctx.needs_input_grad)
-            rgb = torch.empty(B, height, width, 3, device=dev)
-            depth = torch.empty(B, height, width, device=dev)
-            mask = torch.empty(B, height, width, device=dev)
+            if out is not None:
+                # caller-owned outputs (parallel.render_sharded: this rank's slices of the
+                # all-gathered buffers, so that the collective runs in place)
+                rgb, depth, mask = out
+                for o, shape in ((rgb, (B, height, width, 3)), (depth, (B, height, width)),
+                                 (mask, (B, height, width))):
+                    if (tuple(o.shape) != shape or o.dtype != torch.float32
+                            or o.device != dev or not o.is_contiguous()):
+                        raise _lib.NfiError('out= must be contiguous fp32 CUDA tensors of shapes '
+                                            '[B,H,W,3], [B,H,W], [B,H,W] on the planes\' device')
+            else:
+                rgb = torch.empty(B, height, width, 3, device=dev)
+                depth = torch.empty(B, height, width, device=dev)
+                mask = torch.empty(B, height, width, device=dev)
             extra = None
             if extra_mode == _lib.EXTRA_COORDS:
                 extra = torch.empty(B, height, width, 3, device=dev)
@@ -290,15 +301,16 @@ class FusedTriplaneRender(torch.autograd.Function):
                 if t['bbox'] is not None and n_bbox:
                     gbbox = res.pop(0)
         return (gplanes, gw1, gb1, gw2, gb2, gpal, gbeta, galpha, gc2w, gfocal,
-                gcenter, gbbox, None, None, None, None, None, None, None, None, None)
+                gcenter, gbbox, None, None, None, None, None, None, None, None, None, None)
 
 
 def fused_render(planes, w1, b1, w2, b2, palette, beta, alpha, c2w, focal,
                  center, bbox, cfg, height, width, num_samples, noise_t=None,
                  noise_u=None, extra_mode=_lib.EXTRA_NONE, cam_grad=True,
-                 compute_normals=False):
+                 compute_normals=False, out=None):
     """Functional form; returns (rgb, depth, mask, extra|None), with
-    ``compute_normals`` (rgb, depth, mask, extra|None, normals).
+    ``compute_normals`` (rgb, depth, mask, extra|None, normals).  ``out=(rgb, depth,
+    mask)`` makes the kernel write into caller-owned tensors (see parallel.py).
 
     The kernels compute in fp32 like the reference's render (run.py:59-60).  Under
     autocast (BASELINE config 4 trains the synthesis network in bf16) the field tensors
@@ -312,7 +324,7 @@ def fused_render(planes, w1, b1, w2, b2, palette, beta, alpha, c2w, focal,
     rgb, depth, mask, extra, normals = FusedTriplaneRender.apply(
         planes, w1, b1, w2, b2, palette, beta, alpha, c2w, focal, center, bbox,
         cfg, height, width, num_samples, noise_t, noise_u, extra_mode, cam_grad,
-        compute_normals)
+        compute_normals, out)
     extra = extra if extra_mode != _lib.EXTRA_NONE else None
     if compute_normals:
         return rgb, depth, mask, extra, normals

@@ -4,9 +4,20 @@ The reference scales with nn.DataParallel: scatter on the batch dimension,
 replicate the module, gather the outputs on GPU 0 (run.py:636-644).  The render
 path has no cross-image arithmetic, so the B200 version
 is: every rank renders its own contiguous slice of the batch with the fused
-kernels, then ONE NCCL all-gather of the packed [rgb(3), depth, mask] tiles
-brings the full batch to every rank (``gather=True``); inversion needs no
-gradient collective because latents and poses are per image.
+kernels and the output tiles are all-gathered so every rank holds the full
+batch (``gather=True``); inversion needs no gradient collective because latents
+and poses are per image.
+
+Two forms of the exchange:
+
+* in place (``render_sharded(..., inplace=True)``, equal shards): the full-batch
+  rgb / depth / mask buffers are allocated first, the render kernel writes this
+  rank's tiles DIRECTLY into its slice of them (``fused_render(out=...)``) and
+  NCCL all-gathers each buffer in place -- the collective is the epilogue of the
+  render stream, with no pack / pad / concatenate kernels and no second copy of
+  the outputs around it;
+* packed (ragged shards, or a ``render_fn`` without ``out``): one all-gather of
+  the padded [rgb(3), depth, mask] tiles, then trim.
 """
 
 import torch
@@ -58,13 +69,59 @@ def all_gather_outputs(rgb, depth, mask, batch, group=None):
     return unpack_outputs(full)
 
 
-def render_sharded(render_fn, batch_inputs, batch, gather=True, group=None):
+def gathered_buffers(batch, height, width, device, dtype=torch.float32):
+    """Full-batch (rgb [B,H,W,3], depth [B,H,W], mask [B,H,W]) the ranks fill in place."""
+    return (torch.empty(batch, height, width, 3, device=device, dtype=dtype),
+            torch.empty(batch, height, width, device=device, dtype=dtype),
+            torch.empty(batch, height, width, device=device, dtype=dtype))
+
+
+def shard_views(full, batch, world, rank):
+    """This rank's contiguous slices of the full-batch buffers (no copy)."""
+    a, b = shard_range(batch, world, rank)
+    return tuple(t[a:b] for t in full)
+
+
+def all_gather_inplace(full, batch, group=None):
+    """Every rank has written ``full[i][a:b]`` for its own [a, b); afterwards every rank
+    holds all of ``full``.  Needs equal shards (the in-place form of the collective
+    requires rank r's contribution at offset r * count of the receive buffer)."""
+    world = dist.get_world_size(group)
+    rank = dist.get_rank(group)
+    if batch % world:
+        raise ValueError('in-place all-gather needs batch %% world == 0 (got %d, %d)'
+                         % (batch, world))
+    a, b = shard_range(batch, world, rank)
+    for t in full:
+        dist.all_gather_into_tensor(t, t[a:b], group=group)
+    return full
+
+
+def render_sharded(render_fn, batch_inputs, batch, gather=True, group=None, inplace=False,
+                   height=None, width=None):
     """Runs ``render_fn(**shard)`` on this rank's images; ``render_fn`` returns
-    (rgb, depth, mask, ...).  With ``gather`` the full batch comes back."""
+    (rgb, depth, mask, ...).  With ``gather`` the full batch comes back.
+
+    ``inplace`` (with ``height`` / ``width``): ``render_fn`` is called with an extra
+    ``out=(rgb, depth, mask)`` -- this rank's slices of the gathered buffers -- and must
+    write its outputs there (``fused_render(..., out=out)`` does); ragged batches fall back
+    to the packed exchange."""
     world = dist.get_world_size(group) if dist.is_initialized() else 1
     rank = dist.get_rank(group) if dist.is_initialized() else 0
     shard = shard_inputs(batch_inputs, world, rank)
-    rgb, depth, mask = render_fn(**shard)[:3]
+    if inplace and gather and world > 1 and batch % world == 0:
+        device = next(t.device for t in shard.values() if t is not None)
+        full = gathered_buffers(batch, height, width, device)
+        out = shard_views(full, batch, world, rank)
+        res = render_fn(**shard, out=out)[:3]
+        for got, want in zip(res, out):
+            if got.data_ptr() != want.data_ptr():
+                raise RuntimeError('render_fn ignored out=: outputs must be written in place')
+        return all_gather_inplace(full, batch, group)
+    if inplace:
+        rgb, depth, mask = render_fn(**shard, out=None)[:3]
+    else:
+        rgb, depth, mask = render_fn(**shard)[:3]
     if world == 1 or not gather:
         return rgb, depth, mask
     return all_gather_outputs(rgb, depth, mask, batch, group)

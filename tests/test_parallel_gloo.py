@@ -34,7 +34,7 @@ def _free_port():
     return port
 
 
-def _worker(rank, world, port, batch, out_dir):
+def _worker(rank, world, port, batch, out_dir, inplace=False):
     os.environ['MASTER_ADDR'] = '127.0.0.1'
     os.environ['MASTER_PORT'] = str(port)
     dist.init_process_group('gloo', rank=rank, world_size=world)
@@ -43,25 +43,36 @@ def _worker(rank, world, port, batch, out_dir):
     scene, cams = Hh.make_case('p3d_bbox', seed=5, batch=batch, plane_res=16)
     nt, nu = synthetic.make_noise(5, batch, H, W, S)
 
-    def render_fn(planes, palette, c2w, focal, bbox, noise_t, noise_u):
+    def render_fn(planes, palette, c2w, focal, bbox, noise_t, noise_u, out=None):
         sc = dict(scene, planes=planes, palette=palette)
         cm = dict(c2w=c2w, focal=focal, center=None, bbox=bbox)
         o = Hh.run_oracle(sc, cm, H, W, S, noise_t, noise_u.reshape(-1, S))
+        if out is not None:  # what fused_render(out=...) does: results land in the slices
+            for dst, k in zip(out, ('rgb', 'depth', 'mask')):
+                dst.copy_(o[k])
+            return out
         return o['rgb'], o['depth'], o['mask']
 
     inputs = dict(planes=scene['planes'], palette=scene['palette'], c2w=cams['c2w'],
                   focal=cams['focal'], bbox=cams['bbox'], noise_t=nt,
                   noise_u=nu.view(batch, H * W, S))
-    rgb, depth, mask = parallel.render_sharded(render_fn, inputs, batch)
+    if inplace:
+        rgb, depth, mask = parallel.render_sharded(render_fn, inputs, batch, inplace=True,
+                                                   height=H, width=W)
+    else:
+        rgb, depth, mask = parallel.render_sharded(render_fn, inputs, batch)
     torch.save((rgb, depth, mask), os.path.join(out_dir, 'r%d.pt' % rank))
     dist.barrier()
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize('world,batch', [(2, 4), (3, 5)])
-def test_sharded_render_equals_single_process(tmp_path, world, batch):
+@pytest.mark.parametrize('world,batch,inplace', [(2, 4, False), (3, 5, False), (2, 4, True),
+                                                 (3, 6, True), (3, 5, True)])
+def test_sharded_render_equals_single_process(tmp_path, world, batch, inplace):
+    """packed exchange (incl. ragged 5 over 3), in-place exchange (equal shards), and the
+    in-place request falling back to the packed form on a ragged batch"""
     port = _free_port()
-    mp.spawn(_worker, args=(world, port, batch, str(tmp_path)), nprocs=world, join=True)
+    mp.spawn(_worker, args=(world, port, batch, str(tmp_path), inplace), nprocs=world, join=True)
     H, W, S = 8, 8, 8
     scene, cams = Hh.make_case('p3d_bbox', seed=5, batch=batch, plane_res=16)
     nt, nu = synthetic.make_noise(5, batch, H, W, S)

@@ -359,3 +359,34 @@ def test_half_precision_inputs_are_widened(cuda_lib):
     assert torch.equal(a[0], b[0]) and torch.equal(a[2], b[2])
     a[0].square().sum().backward()
     assert pl16.grad is not None and pl16.grad.dtype == torch.bfloat16 and pl16.grad.abs().sum() > 0
+
+
+@pytest.mark.gpu
+def test_caller_owned_outputs(cuda_lib):
+    """fused_render(out=...) writes into slices of a larger buffer (the in-place all-gather of
+    parallel.render_sharded) and returns exactly what the allocating call returns."""
+    from nerf_from_image_b200 import parallel
+    from nerf_from_image_b200.fused import RenderConfig, fused_render
+    from nerf_from_image_b200._lib import NfiError
+    scene, cams = Hh.make_case('p3d_bbox', seed=4, batch=2, plane_res=32, device='cuda')
+    H, W, S = 16, 24, 16
+    nt, nu = synthetic.make_noise(4, 2, H, W, S, device='cuda')
+    cfg = RenderConfig(scene_range=scene['scene_range'], white_background=scene['white_background'],
+                       attention_values=10)
+    args = (scene['planes'], scene['w1'], scene['b1'], scene['w2'], scene['b2'], scene['palette'],
+            scene['beta'], scene['alpha'], cams['c2w'], cams['focal'], cams['center'],
+            cams['bbox'], cfg, H, W, S, nt, nu)
+    with torch.no_grad():
+        ref = fused_render(*args)
+        full = parallel.gathered_buffers(6, H, W, 'cuda')
+        for t in full:
+            t.fill_(-7.0)
+        out = parallel.shard_views(full, 6, 3, 1)  # rank 1 of 3: images 2..3
+        got = fused_render(*args, out=out)
+    for a, b, o in zip(got[:3], ref[:3], out):
+        assert a.data_ptr() == o.data_ptr()
+        assert torch.equal(a, b)
+    for t in full:  # neighbours' slices untouched
+        assert (t[:2] == -7.0).all() and (t[4:] == -7.0).all()
+    with pytest.raises(NfiError):
+        fused_render(*args, out=(full[0][:2, :, :, :2], full[1][:2], full[2][:2]))
