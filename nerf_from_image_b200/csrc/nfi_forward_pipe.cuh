@@ -397,7 +397,7 @@ __device__ __forceinline__ LaneVec<N> resample_ray(const LaneVec<N>& w, const La
   return z;
 }
 
-// Importance resampling of the 16 rays [first, first + 16) of a warp's 32 rows, one
+// Importance resampling of the rays [first, first + count) of a warp's 32 rows, one
 // warp-pass per ray.  (tnear, tfar, ray, valid) are this lane's own row's.  N = 2 slots per
 // lane serve S <= 64, N = 4 (a separate kernel instantiation, so that its register needs
 // do not touch the allocation of the common case's per-step loops) S <= 128.
@@ -412,9 +412,11 @@ struct ResampleArgs {
   bool explicit_noise;
 };
 template <int N>
-__device__ __forceinline__ void resample_rows_impl(const ResampleArgs& a, int first, float tnear,
-                                                   float tfar, size_t ray, bool valid, int lane) {
+__device__ __forceinline__ void resample_rows_impl(const ResampleArgs& a, int first, int count,
+                                                   float tnear, float tfar, size_t ray, bool valid,
+                                                   int lane) {
   const int S = a.S;
+  if (count <= 0) return;
   // inputs of ray j+1 are loaded while ray j is resampled
   struct In {
     LaneVec<N> w, n, u;
@@ -440,8 +442,8 @@ __device__ __forceinline__ void resample_rows_impl(const ResampleArgs& a, int fi
   In cur, nxt;
   load(first, cur);
 #pragma unroll 1
-  for (int j = first; j < first + 16; ++j) {
-    load(j + 1 < first + 16 ? j + 1 : j, nxt);
+  for (int j = first; j < first + count; ++j) {
+    load(j + 1 < first + count ? j + 1 : j, nxt);
     const float nearj = __shfl_sync(kFull, tnear, j), farj = __shfl_sync(kFull, tfar, j);
     const bool validj = __shfl_sync(kFull, (int)valid, j) != 0;
     const int col = 32 * a.wig + j;
@@ -492,7 +494,7 @@ render_forward_pipe(const nfi_render_params p, const unsigned char* __restrict__
   uint64_t* d2_full = h_ready + kPipeSlots;      // [3]  layer-2 accumulator ready (commit)
   uint64_t* slot_free = d2_full + kPipeSlots;    // [3]  D2 read                   (4 warps)
   uint64_t* cw_ready = slot_free + kPipeSlots;   //      coarse weights of the tile written (4 warps)
-  uint64_t* zf_ready = cw_ready + 1;             //      fine depths of the tile written (8 warps)
+  uint64_t* zf_ready = cw_ready + 1;             //      fine depths of the tile written (every resampling warp)
   uint64_t* wbar = zf_ready + 1;                 //      weight image landed
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(base + Cfg::kSmTmemPtr);
   const float* b1s = reinterpret_cast<const float*>(base + kWiB1);
@@ -516,7 +518,7 @@ render_forward_pipe(const nfi_render_params p, const unsigned char* __restrict__
       tc::mbar_init(&slot_free[i], kWarps);
     }
     tc::mbar_init(cw_ready, kWarps);
-    tc::mbar_init(zf_ready, 2 * kWarps);
+    tc::mbar_init(zf_ready, (2 + P) * kWarps);
     tc::mbar_init(wbar, 1);
     tc::fence_mbar_init();
   }
@@ -567,9 +569,21 @@ render_forward_pipe(const nfi_render_params p, const unsigned char* __restrict__
   float* sc_zf = sc_w + (size_t)S * kThreads;          // [S][128] fine depths, ascending
   float* sc_e = sc_zf + (size_t)S * kThreads;          // [S][NES][128] coarse attention probabilities
 
-  // Importance resampling of the 16 rays [first, first + 16) of this warp's 32 rows:
+  // Importance resampling of the rays [first, first + count) of this warp's 32 rows:
   // one warp-pass per ray.  (tnear, tfar, ray index, valid) are this lane's own row's.
-  auto resample_rows = [&](int first, float tnear, float tfar, size_t ray, bool valid) {
+  // The 32 rows of a quadrant are split over the 2 + P warps that serve it (shading,
+  // activation and one warp of every producer set -- the producers would otherwise idle
+  // between the coarse and the fine pass): a warp-pass is a chain of dependent shuffles at
+  // ~0.1 IPC, so five warps per sub-partition get through the tile's 128 rays sooner than
+  // two (measured per tile: 78 k -> 46 k cycles until the fine depths are complete; kernel
+  // 8.78 -> 8.65 ms at config 2; profiles/r1_phase_times_v8_pipe.txt).
+  constexpr int kRsParts = 2 + P;
+  auto rs_first = [](int part) {  // part: 0 shading, 1 activation, 2.. producer sets
+    constexpr int base_rows = 32 / kRsParts, rem = 32 % kRsParts;
+    return part * base_rows + min(max(part - 2, 0), rem);
+  };
+  auto resample_rows = [&](int part, float tnear, float tfar, size_t ray, bool valid) {
+    const int first = rs_first(part), count = rs_first(part + 1) - first;
     ResampleArgs ra;
     ra.sc_w = sc_w;
     ra.sc_zf = sc_zf;
@@ -580,7 +594,7 @@ render_forward_pipe(const nfi_render_params p, const unsigned char* __restrict__
     ra.S = S;
     ra.wig = wig;
     ra.explicit_noise = explicit_noise;
-    resample_rows_impl<NSLOT>(ra, first, tnear, tfar, ray, valid, lane);
+    resample_rows_impl<NSLOT>(ra, first, count, tnear, tfar, ray, valid, lane);
   };
 
   // The roles never share code after setmaxnreg: ptxas budgets registers per
@@ -599,6 +613,7 @@ render_forward_pipe(const nfi_render_params p, const unsigned char* __restrict__
       const int b = tcd.b;
       int px, py;
       tile_pixel(tcd.tile_x, tcd.tile_y, wig, lane, px, py);
+      const bool valid = (px < p.width) && (py < p.height);
       px = min(px, p.width - 1);
       py = min(py, p.height - 1);
       const size_t ray = ((size_t)b * p.height + py) * p.width + px;
@@ -609,7 +624,15 @@ render_forward_pipe(const nfi_render_params p, const unsigned char* __restrict__
       const unsigned char* planes_b =
           reinterpret_cast<const unsigned char*>(p.planes) + (size_t)b * 3 * plane_bytes;
       for (int pass = 0; pass < (FINE ? 2 : 1); ++pass) {
-        if (pass == 1) tc::mbar_wait(zf_ready, tile_it & 1);
+        if (pass == 1) {
+          // this set's share of the quadrant's rows
+          tc::mbar_wait(cw_ready, tile_it & 1);
+          resample_rows(2 + set, r.tnear, r.tfar, ray, valid);
+          __threadfence_block();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(zf_ready);
+          tc::mbar_wait(zf_ready, tile_it & 1);
+        }
         // first step of this pass that belongs to this set; its sample value is
         // fetched one step ahead (the load is never waited on)
         int s = (int)(((uint32_t)set + (uint32_t)P - (n % P)) % P);
@@ -771,7 +794,7 @@ render_forward_pipe(const nfi_render_params p, const unsigned char* __restrict__
         setup_ray(p, tcd.b, py, px, r);
         tc::mbar_wait(cw_ready, tile_it & 1);
         NFI_T(3)
-        resample_rows(16, r.tnear, r.tfar, ray, valid);
+        resample_rows(1, r.tnear, r.tfar, ray, valid);
         __threadfence_block();
         __syncwarp();
         if (lane == 0) mbar_arrive(zf_ready);
