@@ -365,7 +365,11 @@ def main():
             (rgb.square().mean() + mask.mean()).backward()
             planes_g.grad = pal_g.grad = c2w_g.grad = None
 
-        for _ in range(2):
+        # start from a clean caching-allocator state (the legs above leave blocks of other
+        # sizes behind), then warm up: the timed steps must not contain cudaMalloc / cudaFree
+        torch.cuda.synchronize()
+        torch.cuda.empty_cache()
+        for _ in range(3):
             step_bwd()
         torch.cuda.synchronize()
         if world > 1:

@@ -11,7 +11,9 @@ import subprocess
 import threading
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, 'csrc', 'libnfi_render.so')
+# NFI_LIB_PATH points the binding at another build of the same library (A/B timing of two
+# builds in one process launch each; tools/time_backward.py) -- never at a different backend.
+LIB_PATH = os.environ.get('NFI_LIB_PATH') or os.path.join(_HERE, 'csrc', 'libnfi_render.so')
 
 c_float_p = ctypes.POINTER(ctypes.c_float)
 ABI_VERSION = 3  # NFI_ABI_VERSION of include/nfi_render.h
@@ -137,12 +139,16 @@ def load():
                     '__graft_entry__.build(); there is no fallback path.'
                     % LIB_PATH)
             lib = ctypes.CDLL(LIB_PATH)
+            lib.nfi_abi_version.restype = ctypes.c_int
+            if lib.nfi_abi_version() != ABI_VERSION and not os.environ.get('NFI_LIB_PATH'):
+                raise NfiError('libnfi_render.so ABI version mismatch')
             for name, (restype, argtypes) in EXPORTS.items():
+                fn = getattr(lib, name, None)
+                if fn is None and os.environ.get('NFI_LIB_PATH'):
+                    continue  # an older build under test lacks the newer entry points
                 fn = getattr(lib, name)
                 fn.restype = restype
                 fn.argtypes = argtypes
-            if lib.nfi_abi_version() != ABI_VERSION:
-                raise NfiError('libnfi_render.so ABI version mismatch')
             _lib = lib
     return _lib
 
