@@ -58,3 +58,10 @@ def test_no_cpu_fallback():
     scene, cams = Hh.make_case('p3d_plain', batch=1, plane_res=8)
     with pytest.raises(_lib.NfiError):
         Hh.run_cuda(scene, cams, 8, 8, 8, None, None, device='cpu')
+
+
+def test_graft_entry_build_checks_pass(monkeypatch):
+    """__graft_entry__.build() minus the compile: its load / version / import checks."""
+    import __graft_entry__ as entry
+    monkeypatch.setattr(_lib, 'build', lambda verbose=False: _lib.LIB_PATH)
+    entry.build()
