@@ -65,3 +65,29 @@ def test_graft_entry_build_checks_pass(monkeypatch):
     import __graft_entry__ as entry
     monkeypatch.setattr(_lib, 'build', lambda verbose=False: _lib.LIB_PATH)
     entry.build()
+
+
+def test_header_is_plain_c_and_links(tmp_path):
+    """gcc -std=c99 -pedantic compiles a consumer of the header, links it against the built
+    library and runs it (error paths only: no GPU needed); struct sizes / offsets printed by
+    the C side equal the ctypes mirrors'."""
+    import subprocess
+    src = os.path.join(ROOT, 'tests', 'c', 'abi_check.c')
+    exe = str(tmp_path / 'abi_check')
+    libdir = os.path.dirname(_lib.LIB_PATH)
+    subprocess.run(['gcc', '-std=c99', '-Wall', '-Wextra', '-Werror', '-pedantic',
+                    '-I', os.path.join(ROOT, 'include'), src, '-o', exe,
+                    '-L', libdir, '-lnfi_render', '-Wl,-rpath,' + libdir], check=True)
+    res = subprocess.run([exe], capture_output=True, text=True)
+    assert res.returncode == 0, (res.returncode, res.stdout, res.stderr)
+    out = res.stdout
+    assert 'abi %d' % _lib.ABI_VERSION in out and 'sm_100a' in out
+    sizes = re.search(r'sizeof params (\d+) grads (\d+) sample (\d+)', out).groups()
+    assert [int(x) for x in sizes] == [ctypes.sizeof(_lib.RenderParams),
+                                       ctypes.sizeof(_lib.RenderGrads),
+                                       ctypes.sizeof(_lib.SampleParams)]
+    offs = re.search(r'offsets planes (\d+) workspace (\d+) noise_seed (\d+) points (\d+)', out).groups()
+    assert [int(x) for x in offs] == [_lib.RenderParams.planes.offset,
+                                      _lib.RenderParams.workspace.offset,
+                                      _lib.RenderParams.noise_seed.offset,
+                                      _lib.SampleParams.points.offset]
