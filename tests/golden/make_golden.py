@@ -17,7 +17,6 @@ import torch
 
 ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
-from nerf_from_image_b200 import synthetic  # noqa: E402
 from oracle import reference_lift as RL  # noqa: E402
 from tests import helpers as Hh  # noqa: E402
 

@@ -53,7 +53,6 @@ def test_errors_are_reported_without_a_gpu():
 
 def test_no_cpu_fallback():
     import pytest
-    import torch
     from tests import helpers as Hh
     scene, cams = Hh.make_case('p3d_plain', batch=1, plane_res=8)
     with pytest.raises(_lib.NfiError):
