@@ -109,7 +109,7 @@ def best_cpu_threads():
     """The reference's CPU path is plain PyTorch; its intra-op scaling saturates
     well before all cores of a big host, so probe a few thread counts on a small
     sample of the same workload and keep the fastest (reported as `cores`)."""
-    from nerf_from_image_b200 import synthetic
+    from fixtures import synthetic
     from oracle import render_oracle as O
     ds = synthetic.DATASET_CONFIGS[CFG['dataset']]
     scene = synthetic.make_scene(7, 1, plane_res=64, scene_range=ds['scene_range'])
@@ -135,7 +135,7 @@ def best_cpu_threads():
 
 def cpu_oracle_rate(n_images, threads=None, grad=False):
     """Times the oracle port on the host cores; returns (rays/s, seconds, outputs, inputs)."""
-    from nerf_from_image_b200 import synthetic
+    from fixtures import synthetic
     from oracle import render_oracle as O
     threads = threads or os.cpu_count()
     torch.set_num_threads(threads)
@@ -214,7 +214,8 @@ def main():
         return run_reference(args)
 
     import torch.distributed as dist
-    from nerf_from_image_b200 import _lib, fused, parallel, synthetic
+    from nerf_from_image_b200 import _lib, fused, parallel
+    from fixtures import synthetic
 
     world = int(os.environ.get('WORLD_SIZE', '1'))
     rank = int(os.environ.get('RANK', '0'))

@@ -140,8 +140,12 @@ def load():
                     % LIB_PATH)
             lib = ctypes.CDLL(LIB_PATH)
             lib.nfi_abi_version.restype = ctypes.c_int
-            if lib.nfi_abi_version() != ABI_VERSION and not os.environ.get('NFI_LIB_PATH'):
-                raise NfiError('libnfi_render.so ABI version mismatch')
+            got = lib.nfi_abi_version()
+            if got != ABI_VERSION:
+                # also under NFI_LIB_PATH: a build with another struct layout would turn into
+                # memory corruption, not an error
+                raise NfiError('%s has ABI version %d, this binding needs %d: rebuild it '
+                               '(nerf_from_image_b200/csrc/build.sh)' % (LIB_PATH, got, ABI_VERSION))
             for name, (restype, argtypes) in EXPORTS.items():
                 fn = getattr(lib, name, None)
                 if fn is None and os.environ.get('NFI_LIB_PATH'):

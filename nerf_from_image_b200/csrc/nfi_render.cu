@@ -564,12 +564,32 @@ int nfi_render_forward_host(const nfi_render_params* hp, int32_t device) {
   if (hp == nullptr) return fail("params is NULL");
   NFI_CUDA(cudaSetDevice(device));
   cudaStream_t st = nullptr, cp = nullptr;
-  NFI_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
-  NFI_CUDA(cudaStreamCreateWithFlags(&cp, cudaStreamNonBlocking));
-  cudaMemPool_t pool;
-  NFI_CUDA(cudaDeviceGetDefaultMemPool(&pool, device));
-  uint64_t keep = UINT64_MAX;
-  NFI_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
+  // Everything acquired below is released on the single exit path at the bottom (streams,
+  // events, stream-ordered allocations) and the one process-wide setting this function
+  // touches -- the release threshold of the device's default memory pool, raised so that the
+  // per-call buffers are recycled instead of returned to the driver -- is put back.
+  cudaMemPool_t pool = nullptr;
+  uint64_t old_keep = 0;
+  bool pool_changed = false;
+  {
+    cudaError_t e0 = cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking);
+    if (e0 == cudaSuccess) e0 = cudaStreamCreateWithFlags(&cp, cudaStreamNonBlocking);
+    if (e0 == cudaSuccess) e0 = cudaDeviceGetDefaultMemPool(&pool, device);
+    if (e0 == cudaSuccess)
+      e0 = cudaMemPoolGetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &old_keep);
+    if (e0 == cudaSuccess) {
+      uint64_t keep = UINT64_MAX;
+      e0 = cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+      pool_changed = (e0 == cudaSuccess);
+    }
+    if (e0 != cudaSuccess) {
+      if (pool_changed) cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &old_keep);
+      if (cp) cudaStreamDestroy(cp);
+      if (st) cudaStreamDestroy(st);
+      snprintf(g_err, sizeof(g_err), "host entry point set-up failed: %s", cudaGetErrorString(e0));
+      return 2;
+    }
+  }
 
   nfi_render_params d = *hp;
   const size_t B = hp->batch, H = hp->height, W = hp->width, S = hp->num_samples;
@@ -633,11 +653,14 @@ int nfi_render_forward_host(const nfi_render_params* hp, int32_t device) {
                             : "device allocation failed");
   } else {
     // the copy stream may only touch the buffers once their allocation (on st) is done
-    cudaEvent_t alloc_done;
-    NFI_CUDA(cudaEventCreateWithFlags(&alloc_done, cudaEventDisableTiming));
-    cudaEventRecord(alloc_done, st);
-    cudaStreamWaitEvent(cp, alloc_done, 0);
-    cudaEventDestroy(alloc_done);
+    cudaEvent_t alloc_done = nullptr;
+    if (cudaEventCreateWithFlags(&alloc_done, cudaEventDisableTiming) != cudaSuccess) {
+      rc = fail("cudaEventCreate failed");
+    } else {
+      cudaEventRecord(alloc_done, st);
+      cudaStreamWaitEvent(cp, alloc_done, 0);
+      cudaEventDestroy(alloc_done);
+    }
     for (size_t c = 0; c < n_chunks && !rc; ++c) {
       const size_t b0 = c * CB, nb = (b0 + CB <= B) ? CB : B - b0;
       cudaMemcpyAsync(planes_cf + b0 * plane_img, hp->planes + b0 * plane_img,
@@ -699,6 +722,7 @@ int nfi_render_forward_host(const nfi_render_params* hp, int32_t device) {
   for (size_t c = 0; c < n_events; ++c) cudaEventDestroy(ready[c]);
   cudaStreamDestroy(cp);
   cudaStreamDestroy(st);
+  if (pool_changed) cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &old_keep);
   if (e == cudaSuccess) e = e1;
   if (!rc && e != cudaSuccess) {
     snprintf(g_err, sizeof(g_err), "render failed: %s", cudaGetErrorString(e));

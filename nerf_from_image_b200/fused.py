@@ -124,6 +124,10 @@ def _check_shapes(cfg, planes, w1, b1, w2, b2, palette, c2w, focal, center,
                                 '(there is no CPU path)')
 
 
+_FIELD_KEYS = ('w1', 'b1', 'w2', 'b2', 'palette', 'beta', 'alpha', 'c2w', 'focal', 'center',
+               'bbox', 'noise_t', 'noise_u')
+
+
 class FusedTriplaneRender(torch.autograd.Function):
     """(planes, decoder, palette, beta, alpha, cameras) -> (rgb, depth, mask, extra).
 
@@ -209,12 +213,21 @@ class FusedTriplaneRender(torch.autograd.Function):
                 e1.record()
                 KERNEL_EVENTS.append((e0, e1))
         if needs_grad:
+            # Only non-tensor configuration lives on ctx.  Every tensor goes through
+            # save_for_backward: no output -> grad_fn -> ctx -> output cycle (the buffers are
+            # released with the graph, not by the cyclic GC), and an in-place edit of a
+            # returned output before backward() trips autograd's version check instead of
+            # silently corrupting the total L that backward rebuilds from rgb / mask / extra.
             ctx.cfg, ctx.dims, ctx.extra_mode = cfg, (height, width, S), extra_mode
             ctx.cam_grad = cam_grad
-            ctx.t = t
-            ctx.planes_cl = planes_cl
-            ctx.z_fine = z_fine
-            ctx.outs = (rgb, mask, extra)
+            # caller-owned outputs are slices of buffers an in-place all-gather completes
+            # afterwards (parallel.py); it rewrites this rank's slice with the values it
+            # already holds, so those are saved as aliases with their own version counter
+            keep = (lambda x: x) if out is None else (lambda x: x.data)
+            saved = dict(t, out_rgb=keep(rgb), out_mask=keep(mask), out_extra=extra,
+                         planes_cl=planes_cl, z_fine=z_fine)
+            ctx.saved_names = [k for k, v in saved.items() if v is not None]
+            ctx.save_for_backward(*[saved[k] for k in ctx.saved_names])
         ctx.mark_non_differentiable(depth)
         if extra is None:
             extra = torch.empty(0, device=dev)
@@ -226,14 +239,16 @@ class FusedTriplaneRender(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, g_rgb, g_depth, g_mask, g_extra, g_normals=None):
-        cfg, (height, width, S), t = ctx.cfg, ctx.dims, ctx.t
+        cfg, (height, width, S) = ctx.cfg, ctx.dims
         lib = _lib.load()
-        planes_cl = ctx.planes_cl
+        saved = dict(zip(ctx.saved_names, ctx.saved_tensors))
+        t = {k: saved.get(k) for k in _FIELD_KEYS}
+        planes_cl, z_fine = saved['planes_cl'], saved.get('z_fine')
         dev = planes_cl.device
         need = ctx.needs_input_grad
         (n_planes, n_w1, n_b1, n_w2, n_b2, n_pal, n_beta, n_alpha, n_c2w,
          n_focal, n_center, n_bbox) = need[:12]
-        rgb, mask, extra = ctx.outs
+        rgb, mask, extra = saved['out_rgb'], saved['out_mask'], saved.get('out_extra')
         A = cfg.attention_values
         with torch.cuda.device(dev):
             stream = ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
@@ -269,7 +284,7 @@ class FusedTriplaneRender(torch.autograd.Function):
                              S, t['noise_t'], t['noise_u'], ctx.extra_mode)
             p.rgb, p.depth, p.mask = _ptr(rgb), _ptr(mask), _ptr(mask)  # unused
             p.extra = _ptr(extra)
-            p.z_fine = _ptr(ctx.z_fine)
+            p.z_fine = _ptr(z_fine)
             # the tensor-core backward keeps its two weight images here (64 KiB)
             ws = torch.empty(65536, dtype=torch.uint8, device=dev)
             p.workspace, p.workspace_bytes = _ptr(ws), 65536
@@ -289,8 +304,11 @@ class FusedTriplaneRender(torch.autograd.Function):
                     leaves = [x for x, n in ((c2w_l, n_c2w), (focal_l, n_focal),
                                              (center_l, n_center), (bbox_l, n_bbox))
                               if x is not None and n]
-                    outs = [o, d] if o.requires_grad else [d]
-                    gos = [go, gd] if o.requires_grad else [gd]
+                    # an orthographic camera with only bbox requiring grad moves the origins
+                    # but not the directions (and the perspective case the reverse)
+                    pairs = [(x, gx) for x, gx in ((o, go), (d, gd)) if x.requires_grad]
+                    outs = [x for x, _ in pairs]
+                    gos = [gx for _, gx in pairs]
                     res = list(torch.autograd.grad(outs, leaves, gos, allow_unused=True))
                 if t['c2w'] is not None and n_c2w:
                     gc2w = res.pop(0)

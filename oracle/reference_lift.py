@@ -1,9 +1,12 @@
-"""Run the UNMODIFIED reference hot path in this container -- TEST INFRASTRUCTURE.
+"""Run the UNMODIFIED reference hot path -- TEST / BASELINE INFRASTRUCTURE.
 
 /root/reference is mounted read-only in the build container and does not exist
-on the GPU box, so everything here is optional: ``available()`` says whether
-the reference can be imported, and only ``tests/test_oracle_vs_reference.py``
-and ``tests/golden/make_golden.py`` call it.  No reference source is copied:
+on the GPU box; there the same files are found, unmodified, under the git-ignored
+``baseline/_ref/`` (staged by ``tools/stage_reference.py`` from ``__graft_entry__.build()``).
+Everything here is optional: ``available()`` says whether the reference can be
+imported; callers are ``tests/`` (oracle pinning, golden generation, the on-GPU
+``render()`` drop-in tests) and ``bench.py``'s reference legs (``--impl reference``,
+``cpu_baseline``) -- never the product path.  No reference source is copied:
 ``render`` (run.py:176-350) is taken from the reference file by AST at run
 time (run.py itself cannot be imported -- it parses argv, loads datasets and
 imports lpips/pytorch_fid at module level), and the radiance field is the
@@ -20,7 +23,18 @@ import warnings
 import torch
 import torch.nn.functional as F
 
-REFERENCE_ROOT = os.environ.get('NFI_REFERENCE_ROOT', '/root/reference')
+_STAGED = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))),
+                       'baseline', '_ref')
+
+
+def _find_root():
+    for cand in (os.environ.get('NFI_REFERENCE_ROOT'), '/root/reference', _STAGED):
+        if cand and os.path.isfile(os.path.join(cand, 'run.py')):
+            return cand
+    return '/root/reference'
+
+
+REFERENCE_ROOT = _find_root()
 
 
 def available():
@@ -72,7 +86,7 @@ class _PlaneStub(torch.nn.Module):
 def build_reference_generator(scene, use_sdf=True):
     """Reference Generator carrying ``scene``'s decoder weights, beta/alpha.
 
-    ``scene`` is a dict from ``nerf_from_image_b200.synthetic.make_scene``:
+    ``scene`` is a dict from ``fixtures.synthetic.make_scene``:
     effective decoder weights are divided by the EqualizedLinear gains so the
     reference module reproduces them (models/stylegan.py:168-177).
     """

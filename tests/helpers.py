@@ -1,7 +1,7 @@
 """Shared helpers for the parity tests (oracle side and CUDA side)."""
 import torch
 
-from nerf_from_image_b200 import synthetic
+from fixtures import synthetic
 from oracle import render_oracle as O
 
 CASES = {

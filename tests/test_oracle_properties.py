@@ -7,7 +7,7 @@ depths stay inside [near, far], and the deterministic mode has no hidden draw.
 """
 import torch
 
-from nerf_from_image_b200 import synthetic
+from fixtures import synthetic
 from oracle import render_oracle as O
 from tests import helpers as Hh
 

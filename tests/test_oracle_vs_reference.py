@@ -70,7 +70,7 @@ def test_missed_rays_do_not_need_the_global_fallback():
     """The CUDA path skips lib/nerf_utils.py:258-259; images must not change."""
     scene, cams = Hh.make_case('p3d_plain', seed=8, batch=2)
     cams['focal'] = torch.tensor([0.35, 0.4])  # wide field of view: corner rays miss the cube
-    from nerf_from_image_b200 import synthetic
+    from fixtures import synthetic
     nt, nu = synthetic.make_noise(1, 2, 16, 16, 8)
     a = Hh.run_oracle(scene, cams, 16, 16, 8, nt, nu, global_near_far_fallback=True)
     b = Hh.run_oracle(scene, cams, 16, 16, 8, nt, nu, global_near_far_fallback=False)

@@ -9,7 +9,8 @@ import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
-from nerf_from_image_b200 import parallel, synthetic
+from nerf_from_image_b200 import parallel
+from fixtures import synthetic
 from tests import helpers as Hh
 
 

@@ -3,7 +3,8 @@ mlp_mode bit 0x1000 selects the DBG instantiation in which lane 0 of one warp pe
 role in CTA 0 accumulates clock64 deltas).  Usage: python tools/phase_times_pipe.py [batch]"""
 import sys, torch
 sys.path.insert(0, '.')
-from nerf_from_image_b200 import fused, synthetic
+from nerf_from_image_b200 import fused
+from fixtures import synthetic
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 8
 H, W, S = 128, 128, 64
 ds = synthetic.DATASET_CONFIGS['p3d_car']

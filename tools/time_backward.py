@@ -4,7 +4,8 @@ decoder frozen; with `cam` also to tform_cam2world), the backward on its own eve
 Usage: python tools/time_backward.py [batch] [cam]"""
 import sys, torch
 sys.path.insert(0, '.')
-from nerf_from_image_b200 import fused, synthetic, _lib
+from nerf_from_image_b200 import fused, _lib
+from fixtures import synthetic
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 8
 CAM = len(sys.argv) > 2 and sys.argv[2] == 'cam'
 H, W, S = 128, 128, 64
