@@ -303,7 +303,11 @@ render_backward_pipe(const nfi_render_params p, const nfi_render_grads g,
         const uint32_t st = m % NS, u = m / NS;
         unsigned char* const stage = base + Cfg::kSmA + st * kPipeStageBytes;
         tc::mbar_wait(&a_free[st], (u & 1) ^ 1);
+#ifdef NFI_GATHER_ROT
+        gather_to_tiles_lean_rot(planes_b, R, tp, stage, stage + 16384, 32 * wig, lane);
+#else
         gather_to_tiles_lean(planes_b, R, tp, stage, stage + 16384, 32 * wig, lane);
+#endif
         tc::fence_async_smem();
         __syncwarp();
         if (lane == 0) mbar_arrive(&full[st]);

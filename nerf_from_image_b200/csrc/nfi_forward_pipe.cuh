@@ -42,6 +42,12 @@
 
 namespace nfi {
 
+// back-off between mbarrier polls of the per-step hand-offs (0 = hardware-suspended try_wait only)
+#ifndef NFI_WAIT_NS
+#define NFI_WAIT_NS 0
+#endif
+#define NFI_STEP_WAIT(bar, par) tc::mbar_wait_backoff<NFI_WAIT_NS>(bar, par)
+
 // ------------------------------------------------------------------ small helpers
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tc::smem_u32(bar)) : "memory");
@@ -648,7 +654,7 @@ render_forward_pipe(const nfi_render_params p, const unsigned char* __restrict__
           const float cur = nxt;
           nxt = fetch(s + P);
           if (DBG && dbg_time) tprev = clock64();
-          tc::mbar_wait(&a_free[st], (u & 1) ^ 1);  // tensor core has read the previous fill
+          NFI_STEP_WAIT(&a_free[st], (u & 1) ^ 1);  // tensor core has read the previous fill
           NFI_T(0)
           float t;
           if (pass == 0)
@@ -667,8 +673,13 @@ render_forward_pipe(const nfi_render_params p, const unsigned char* __restrict__
             tp.o[1] &= 0x7FFu;
             tp.o[2] &= 0x7FFu;
           }
-          if (!dbg_skip_gather)
+          if (!dbg_skip_gather) {
+#ifdef NFI_GATHER_ROT
+            gather_to_tiles_lean_rot(planes_b, R, tp, stage, stage + 16384, 32 * wig, lane);
+#else
             gather_to_tiles_lean(planes_b, R, tp, stage, stage + 16384, 32 * wig, lane);
+#endif
+          }
           NFI_T(2)
           tc::fence_async_smem();
           __syncwarp();
@@ -692,9 +703,9 @@ render_forward_pipe(const nfi_render_params p, const unsigned char* __restrict__
       uint32_t st = 0, u = 0, sl = 0, v = 0;
       for (uint32_t m = 0; m < total_steps; ++m) {
         if (DBG && dbg_time && tprev == 0) tprev = clock64();
-        tc::mbar_wait(&full[st], u & 1);
+        NFI_STEP_WAIT(&full[st], u & 1);
         NFI_T(0)
-        tc::mbar_wait(&slot_free[sl], (v & 1) ^ 1);
+        NFI_STEP_WAIT(&slot_free[sl], (v & 1) ^ 1);
         NFI_T(1)
         if (elect_one()) {
           tc::tc_fence_after();
@@ -718,7 +729,7 @@ render_forward_pipe(const nfi_render_params p, const unsigned char* __restrict__
       uint32_t sl = 0, v = 0;
       for (uint32_t m = 0; m < total_steps; ++m) {
         if (DBG && dbg_time && tprev == 0) tprev = clock64();
-        tc::mbar_wait(&h_ready[sl], v & 1);
+        NFI_STEP_WAIT(&h_ready[sl], v & 1);
         NFI_T(0)
         if (elect_one()) {
           tc::tc_fence_after();
@@ -743,7 +754,7 @@ render_forward_pipe(const nfi_render_params p, const unsigned char* __restrict__
       const uint32_t d1 = tmem_base + sl * kPipeSlotCols + lane_addr;
       if (DBG && dbg_time && tprev == 0) tprev = clock64();
       NFI_T(2)
-      tc::mbar_wait(&d1_full[sl], v & 1);
+      NFI_STEP_WAIT(&d1_full[sl], v & 1);
       tc::tc_fence_after();
       NFI_T(0)
       if (!dbg_skip_consumer) {
@@ -843,7 +854,7 @@ render_forward_pipe(const nfi_render_params p, const unsigned char* __restrict__
         const uint32_t d2 = tmem_base + sl * kPipeSlotCols + 128 + lane_addr;
         if (DBG && dbg_time && tprev == 0) tprev = clock64();
         NFI_T(2)
-        tc::mbar_wait(&d2_full[sl], v & 1);
+        NFI_STEP_WAIT(&d2_full[sl], v & 1);
         tc::tc_fence_after();
         NFI_T(0)
         float o16[16];

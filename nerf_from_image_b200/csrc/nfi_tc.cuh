@@ -53,6 +53,19 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     if (((++spins) & 63u) == 0 && clock64() - t0 > 4000000000LL) __trap();
   }
 }
+// Same, with a fixed back-off between polls (timing experiments: NFI_WAIT_NS).
+template <int NS>
+__device__ __forceinline__ void mbar_wait_backoff(uint64_t* bar, uint32_t parity) {
+  if (NS <= 0) return mbar_wait(bar, parity);
+  if (mbar_try_wait(bar, parity)) return;
+  const long long t0 = clock64();
+  uint32_t spins = 0;
+  while (true) {
+    __nanosleep(NS);
+    if (mbar_try_wait(bar, parity)) return;
+    if (((++spins) & 63u) == 0 && clock64() - t0 > 4000000000LL) __trap();
+  }
+}
 __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)),
                "r"(bytes)

@@ -136,6 +136,13 @@ def render(target_model,
         raise NotImplementedError(
             '--use_viewdir (CARLA only, generator.py:189-253) is outside the '
             'fused path (SURVEY.md section 8f N4)')
+    if 'bbox' in extra_model_outputs and compute_coords:
+        # models/generator.py:640-657: the closure adds a 100 x box-frame debug density to
+        # sigma when coords are requested together with 'bbox'; the fused kernels render
+        # without it (the sampler seam, sampler.FusedSampler(bbox_debug=True), has it)
+        raise NotImplementedError(
+            "'bbox' in extra_model_outputs with compute_coords (the debug box-frame density, "
+            'generator.py:640-657) is only available through the sampler seam')
     if compute_normals:
         assert args.use_sdf  # run.py:229
     if compute_semantics:

@@ -1,0 +1,22 @@
+# Round-2 GPU jobs (run on the box through gpurun); everything lands in gpurun_out/.
+# usage: bash tools/gpu_call.sh <job> [...]
+mkdir -p gpurun_out
+LIBDIR=$PWD/nerf_from_image_b200/csrc
+for a in "$@"; do
+  case $a in
+    tests) timeout 1500 python -m pytest tests -m gpu -q -x 2>&1 | tail -15 > gpurun_out/r2_pytest_gpu.log; cat gpurun_out/r2_pytest_gpu.log;;
+    bench) timeout 400 python bench.py > gpurun_out/r2_bench.json 2> gpurun_out/r2_bench.err; cat gpurun_out/r2_bench.json; tail -3 gpurun_out/r2_bench.err;;
+    ab) for l in $LIBDIR/libnfi_render.so $LIBDIR/libnfi_render_*.so; do NFI_LIB_PATH=$l timeout 120 python tools/ab_forward.py 32 10 2>&1 | grep -v Warn | tail -1; done > gpurun_out/r2_ab_forward.txt; cat gpurun_out/r2_ab_forward.txt;;
+    ab_bwd) for l in $LIBDIR/libnfi_render.so $LIBDIR/libnfi_render_*.so; do NFI_LIB_PATH=$l timeout 200 python tools/time_backward.py 32 cam 2>&1 | grep -v Warn; done > gpurun_out/r2_ab_backward.txt; cat gpurun_out/r2_ab_backward.txt;;
+    ncu_fwd) timeout 600 ncu --set full --clock-control none --import-source on -k regex:render_forward_pipe -s 3 -c 1 -f -o gpurun_out/r2_fwd python tools/ab_forward.py 32 2 > gpurun_out/r2_ncu_fwd.log 2>&1
+             ncu -i gpurun_out/r2_fwd.ncu-rep --page raw --csv > gpurun_out/r2_fwd_raw.csv 2>/dev/null
+             ncu -i gpurun_out/r2_fwd.ncu-rep --page source --csv > gpurun_out/r2_fwd_src.csv 2>/dev/null
+             rm -f gpurun_out/r2_fwd.ncu-rep; tail -2 gpurun_out/r2_ncu_fwd.log | cut -c1-200;;
+    ncu_bwd) timeout 600 ncu --set full --clock-control none --import-source on -k regex:render_backward_pipe -s 2 -c 1 -f -o gpurun_out/r2_bwd python tools/time_backward.py 32 cam > gpurun_out/r2_ncu_bwd.log 2>&1
+             ncu -i gpurun_out/r2_bwd.ncu-rep --page raw --csv > gpurun_out/r2_bwd_raw.csv 2>/dev/null
+             ncu -i gpurun_out/r2_bwd.ncu-rep --page source --csv > gpurun_out/r2_bwd_src.csv 2>/dev/null
+             rm -f gpurun_out/r2_bwd.ncu-rep; tail -2 gpurun_out/r2_ncu_bwd.log | cut -c1-200;;
+    ncu_list) timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 80 --csv --log-file gpurun_out/r2_launches.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-e2e > gpurun_out/r2_ncu_list.log 2>&1; tail -14 gpurun_out/r2_launches.csv | cut -c1-200;;
+    *) echo "unknown job $a";;
+  esac
+done
