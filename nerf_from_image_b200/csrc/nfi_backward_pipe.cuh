@@ -302,12 +302,8 @@ render_backward_pipe(const nfi_render_params p, const nfi_render_grads g,
         const uint32_t m = n0 + (uint32_t)i;
         const uint32_t st = m % NS, u = m / NS;
         unsigned char* const stage = base + Cfg::kSmA + st * kPipeStageBytes;
-        tc::mbar_wait(&a_free[st], (u & 1) ^ 1);
-#ifdef NFI_GATHER_ROT
-        gather_to_tiles_lean_rot(planes_b, R, tp, stage, stage + 16384, 32 * wig, lane);
-#else
+        NFI_STEP_WAIT(&a_free[st], (u & 1) ^ 1);
         gather_to_tiles_lean(planes_b, R, tp, stage, stage + 16384, 32 * wig, lane);
-#endif
         tc::fence_async_smem();
         __syncwarp();
         if (lane == 0) mbar_arrive(&full[st]);
@@ -340,7 +336,7 @@ render_backward_pipe(const nfi_render_params p, const nfi_render_grads g,
         const uint32_t m = n0 + (uint32_t)i;
         const uint32_t sl = m % kBwdSlots, v = m / kBwdSlots;
         const uint32_t d4 = tmem_base + sl * kBwdSlotCols + lane_addr;
-        tc::mbar_wait(&d4_full[sl], v & 1);
+        NFI_STEP_WAIT(&d4_full[sl], v & 1);
         tc::tc_fence_after();
         {
           uint32_t ra[16], rb[16];
@@ -456,8 +452,8 @@ render_backward_pipe(const nfi_render_params p, const nfi_render_grads g,
       const uint64_t dsc_a0 = tc::umma_desc_sw128(base_s + Cfg::kSmA);
       uint32_t st = 0, u = 0, sl = 0, v = 0;
       for (uint32_t m = 0; m < total_steps; ++m) {
-        tc::mbar_wait(&full[st], u & 1);
-        tc::mbar_wait(&slot_free[sl], (v & 1) ^ 1);
+        NFI_STEP_WAIT(&full[st], u & 1);
+        NFI_STEP_WAIT(&slot_free[sl], (v & 1) ^ 1);
         if (elect_one()) {
           tc::tc_fence_after();
           const uint64_t dsc_a = dsc_a0 + (uint64_t)st * (kPipeStageBytes >> 4);
@@ -475,7 +471,7 @@ render_backward_pipe(const nfi_render_params p, const nfi_render_grads g,
       const uint64_t dsc_w2_lo = tc::umma_desc_sw128(base_s + kWiW2Lo);
       uint32_t sl = 0, v = 0;
       for (uint32_t m = 0; m < total_steps; ++m) {
-        tc::mbar_wait(&h_ready[sl], v & 1);
+        NFI_STEP_WAIT(&h_ready[sl], v & 1);
         if (elect_one()) {
           tc::tc_fence_after();
           const uint32_t d = tmem_base + sl * kBwdSlotCols;
@@ -490,7 +486,7 @@ render_backward_pipe(const nfi_render_params p, const nfi_render_grads g,
       const uint64_t b_lo = tc::umma_desc_sw128(base_s + Cfg::kSmWb + kWbW2tLo);
       uint32_t sl = 0, v = 0;
       for (uint32_t m = 0; m < total_steps; ++m) {
-        tc::mbar_wait(&dout_ready[sl], v & 1);
+        NFI_STEP_WAIT(&dout_ready[sl], v & 1);
         if (elect_one()) {
           tc::tc_fence_after();
           const uint32_t d = tmem_base + sl * kBwdSlotCols;
@@ -505,7 +501,7 @@ render_backward_pipe(const nfi_render_params p, const nfi_render_grads g,
       const uint64_t b_lo = tc::umma_desc_sw128(base_s + Cfg::kSmWb + kWbW1tLo);
       uint32_t sl = 0, v = 0;
       for (uint32_t m = 0; m < total_steps; ++m) {
-        tc::mbar_wait(&dpre_ready[sl], v & 1);
+        NFI_STEP_WAIT(&dpre_ready[sl], v & 1);
         if (elect_one()) {
           tc::tc_fence_after();
           const uint32_t d = tmem_base + sl * kBwdSlotCols;
@@ -522,7 +518,7 @@ render_backward_pipe(const nfi_render_params p, const nfi_render_grads g,
     auto act_fwd = [&](uint32_t m) {
       const uint32_t sl = m % kBwdSlots, v = m / kBwdSlots;
       const uint32_t d1 = tmem_base + sl * kBwdSlotCols + lane_addr;
-      tc::mbar_wait(&d1_full[sl], v & 1);
+      NFI_STEP_WAIT(&d1_full[sl], v & 1);
       tc::tc_fence_after();
 #pragma unroll 1
       for (int c = 0; c < 4; ++c) {
@@ -541,7 +537,7 @@ render_backward_pipe(const nfi_render_params p, const nfi_render_grads g,
     auto act_bwd = [&](uint32_t m) {
       const uint32_t sl = m % kBwdSlots, v = m / kBwdSlots;
       const uint32_t d = tmem_base + sl * kBwdSlotCols + lane_addr;
-      tc::mbar_wait(&d3_full[sl], v & 1);
+      NFI_STEP_WAIT(&d3_full[sl], v & 1);
       tc::tc_fence_after();
 #pragma unroll 1
       for (int c = 0; c < 4; ++c) {
@@ -645,7 +641,7 @@ render_backward_pipe(const nfi_render_params p, const nfi_render_grads g,
         const float wx = r.ox + r.dx * z, wy = r.oy + r.dy * z, wz = r.oz + r.dz * z;
         const float x0 = wx * inv_range, x1 = wy * inv_range, x2 = wz * inv_range;
         const float keep = (fabsf(x0) > 1.f || fabsf(x1) > 1.f || fabsf(x2) > 1.f) ? 0.f : 1.f;
-        tc::mbar_wait(&d2_full[sl], v & 1);
+        NFI_STEP_WAIT(&d2_full[sl], v & 1);
         tc::tc_fence_after();
         float o16[16];
         tc::tmem_ld16(d + 128, o16);

@@ -674,11 +674,7 @@ render_forward_pipe(const nfi_render_params p, const unsigned char* __restrict__
             tp.o[2] &= 0x7FFu;
           }
           if (!dbg_skip_gather) {
-#ifdef NFI_GATHER_ROT
-            gather_to_tiles_lean_rot(planes_b, R, tp, stage, stage + 16384, 32 * wig, lane);
-#else
             gather_to_tiles_lean(planes_b, R, tp, stage, stage + 16384, 32 * wig, lane);
-#endif
           }
           NFI_T(2)
           tc::fence_async_smem();

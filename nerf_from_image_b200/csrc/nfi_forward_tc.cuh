@@ -317,68 +317,6 @@ __device__ __forceinline__ void gather_to_tiles_deep(const float* __restrict__ p
   }
 }
 
-// Rotated variant of gather_to_tiles_deep: the 4 taps of a plane are consumed and
-// immediately RE-ISSUED for the next point group, so ~12 texel loads stay in flight
-// for the whole 32-row gather instead of ramping 12 -> 0 eight times.  Same
-// arithmetic order (planes 0,1,2; taps nw,ne,sw,se), bit-identical features.
-struct PlaneTaps {
-  float4 v[4];
-  float fx, fy;
-};
-__device__ __forceinline__ void plane_issue(const float4* __restrict__ base, const PackedTaps& tp,
-                                            int pl, int src, uint32_t plane_stride4, int R,
-                                            PlaneTaps& t) {
-  const uint32_t o = __shfl_sync(kFull, tp.o[pl], src);
-  t.fx = __shfl_sync(kFull, tp.fx[pl], src);
-  t.fy = __shfl_sync(kFull, tp.fy[pl], src);
-  const uint32_t o00 = (o & 0x3FFFFFFFu) * (kC / 4) + pl * plane_stride4;
-  const uint32_t dx = ((o >> 30) & 1u) * (kC / 4), dy = (o >> 31) ? (uint32_t)R * (kC / 4) : 0u;
-  t.v[0] = ldg_nc_volatile(base + o00);
-  t.v[1] = ldg_nc_volatile(base + o00 + dx);
-  t.v[2] = ldg_nc_volatile(base + o00 + dy);
-  t.v[3] = ldg_nc_volatile(base + o00 + dy + dx);
-}
-__device__ __forceinline__ void plane_consume(const PlaneTaps& t, float2& lo, float2& hi) {
-  const float gx0 = 1.f - t.fx, gy0 = 1.f - t.fy;
-  const float w[4] = {gx0 * gy0, t.fx * gy0, gx0 * t.fy, t.fx * t.fy};
-#pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    lo = ffma2(make_float2(t.v[j].x, t.v[j].y), make_float2(w[j], w[j]), lo);
-    hi = ffma2(make_float2(t.v[j].z, t.v[j].w), make_float2(w[j], w[j]), hi);
-  }
-}
-__device__ __forceinline__ void gather_to_tiles_rot(const float* __restrict__ planes_b, int R,
-                                                    const PackedTaps& tp, unsigned char* a_hi,
-                                                    unsigned char* a_lo, int row0, int lane) {
-  const int q = lane >> 3, k = lane & 7;
-  const uint32_t plane_stride4 = (uint32_t)R * R * (kC / 4);
-  const float4* base = reinterpret_cast<const float4*>(planes_b) + k;
-  PlaneTaps p0, p1, p2;
-  plane_issue(base, tp, 0, q, plane_stride4, R, p0);
-  plane_issue(base, tp, 1, q, plane_stride4, R, p1);
-  plane_issue(base, tp, 2, q, plane_stride4, R, p2);
-#pragma unroll 1
-  for (int g = 0; g < 8; ++g) {
-    const int src = 4 * g + q;
-    const int nsrc = (g < 7) ? src + 4 : src;  // last round re-reads its own lines (L1 hits)
-    float2 lo = make_float2(0.f, 0.f), hi = make_float2(0.f, 0.f);
-    plane_consume(p0, lo, hi);
-    plane_issue(base, tp, 0, nsrc, plane_stride4, R, p0);
-    plane_consume(p1, lo, hi);
-    plane_issue(base, tp, 1, nsrc, plane_stride4, R, p1);
-    plane_consume(p2, lo, hi);
-    plane_issue(base, tp, 2, nsrc, plane_stride4, R, p2);
-    const float third = 0.33333334f;
-    const float4 f = make_float4(lo.x * third, lo.y * third, hi.x * third, hi.y * third);
-    const float4 fh = make_float4(tc::tf32_hi(f.x), tc::tf32_hi(f.y), tc::tf32_hi(f.z),
-                                  tc::tf32_hi(f.w));
-    const float4 fl = make_float4(f.x - fh.x, f.y - fh.y, f.z - fh.z, f.w - fh.w);
-    const uint32_t offs = tc::sw128_offset(row0 + src, k);
-    *reinterpret_cast<float4*>(a_hi + offs) = fh;
-    *reinterpret_cast<float4*>(a_lo + offs) = fl;
-  }
-}
-
 // ---------------------------------------------------------------------------
 // Lean gather (nfi_forward_pipe.cuh): same arithmetic as gather_to_tiles_deep,
 // about half the instructions.  The owner lane of a point pre-multiplies its
@@ -448,69 +386,6 @@ __device__ __forceinline__ void gather_to_tiles_lean(const unsigned char* __rest
         hi = ffma2(make_float2(x.z, x.w), make_float2(w[j], w[j]), hi);
       }
     }
-    const float third = 0.33333334f;
-    const float4 f = make_float4(lo.x * third, lo.y * third, hi.x * third, hi.y * third);
-    const float4 fh = make_float4(tc::tf32_hi(f.x), tc::tf32_hi(f.y), tc::tf32_hi(f.z),
-                                  tc::tf32_hi(f.w));
-    const float4 fl = make_float4(f.x - fh.x, f.y - fh.y, f.z - fh.z, f.w - fh.w);
-    const uint32_t offs = tc::sw128_offset(row0 + src, k);
-    *reinterpret_cast<float4*>(a_hi + offs) = fh;
-    *reinterpret_cast<float4*>(a_lo + offs) = fl;
-  }
-}
-
-// Rotated lean gather: the four taps of a plane are consumed and at once RE-ISSUED for the next
-// point group, so 8-12 texel loads stay in flight through the whole 32-row gather instead of
-// ramping 12 -> 0 eight times (same arithmetic order as gather_to_tiles_lean: bit-identical).
-struct LeanPlane {
-  float4 v[4];
-};
-__device__ __forceinline__ void lean_issue(const unsigned char* __restrict__ planes_b,
-                                           uint32_t row_units, const ByteTaps& tp, int pl, int src,
-                                           int k, LeanPlane& t) {
-  const uint32_t o = __shfl_sync(kFull, tp.o[pl], src);
-  const uint32_t a00 = (o & 0xFFFFFFF8u) | (uint32_t)k;
-  const uint32_t dx = (o & 1u) << 3;
-  const uint32_t dy = (o & 2u) ? row_units : 0u;
-  const uint32_t a10 = a00 + dy;
-  t.v[0] = ldg_nc_volatile(texel_ptr(planes_b, a00));
-  t.v[1] = ldg_nc_volatile(texel_ptr(planes_b, a00 + dx));
-  t.v[2] = ldg_nc_volatile(texel_ptr(planes_b, a10));
-  t.v[3] = ldg_nc_volatile(texel_ptr(planes_b, a10 + dx));
-}
-// (the two interpolation fractions are fetched from the owner lane here, not carried from issue)
-__device__ __forceinline__ void lean_consume(const LeanPlane& t, const ByteTaps& tp, int pl, int src,
-                                             float2& lo, float2& hi) {
-  const float fx = __shfl_sync(kFull, tp.fx[pl], src), fy = __shfl_sync(kFull, tp.fy[pl], src);
-  const float gx0 = 1.f - fx, gy0 = 1.f - fy;
-  const float w[4] = {gx0 * gy0, fx * gy0, gx0 * fy, fx * fy};
-#pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    lo = ffma2(make_float2(t.v[j].x, t.v[j].y), make_float2(w[j], w[j]), lo);
-    hi = ffma2(make_float2(t.v[j].z, t.v[j].w), make_float2(w[j], w[j]), hi);
-  }
-}
-__device__ __forceinline__ void gather_to_tiles_lean_rot(const unsigned char* __restrict__ planes_b,
-                                                         int R, const ByteTaps& tp,
-                                                         unsigned char* a_hi, unsigned char* a_lo,
-                                                         int row0, int lane) {
-  const int q = lane >> 3, k = lane & 7;
-  const uint32_t row_units = (uint32_t)R * 8u;
-  LeanPlane p0, p1, p2;
-  lean_issue(planes_b, row_units, tp, 0, q, k, p0);
-  lean_issue(planes_b, row_units, tp, 1, q, k, p1);
-  lean_issue(planes_b, row_units, tp, 2, q, k, p2);
-#pragma unroll 1
-  for (int g = 0; g < 8; ++g) {
-    const int src = 4 * g + q;
-    const bool more = g < 7;  // warp-uniform
-    float2 lo = make_float2(0.f, 0.f), hi = make_float2(0.f, 0.f);
-    lean_consume(p0, tp, 0, src, lo, hi);
-    if (more) lean_issue(planes_b, row_units, tp, 0, src + 4, k, p0);
-    lean_consume(p1, tp, 1, src, lo, hi);
-    if (more) lean_issue(planes_b, row_units, tp, 1, src + 4, k, p1);
-    lean_consume(p2, tp, 2, src, lo, hi);
-    if (more) lean_issue(planes_b, row_units, tp, 2, src + 4, k, p2);
     const float third = 0.33333334f;
     const float4 f = make_float4(lo.x * third, lo.y * third, hi.x * third, hi.y * third);
     const float4 fh = make_float4(tc::tf32_hi(f.x), tc::tf32_hi(f.y), tc::tf32_hi(f.z),

@@ -48,8 +48,9 @@ def ray_bundle(height: int, width: int, focal: Optional[torch.Tensor],
     model (lib/nerf_utils.py:66-89), otherwise perspective (:40-65).
     """
     dev = c2w.device
-    u = (torch.arange(width, device=dev) / width).view(1, 1, width)
-    v = (torch.arange(height, device=dev) / height).view(1, height, 1)
+    # (dtype follows the cameras: the fp64 runs of tests/ use the oracle as ground truth)
+    u = (torch.arange(width, device=dev, dtype=c2w.dtype) / width).view(1, 1, width)
+    v = (torch.arange(height, device=dev, dtype=c2w.dtype) / height).view(1, height, 1)
     u = u.expand(1, height, width)
     v = v.expand(1, height, width)
     rot = c2w[:, None, None, :3, :3]
@@ -130,7 +131,7 @@ def coarse_depths(near: torch.Tensor, far: torch.Tensor, num_samples: int,
 
     lib/nerf_utils.py:101-114.  ``noise_t`` replaces ``torch.rand_like``.
     """
-    frac = torch.arange(num_samples, device=near.device) / num_samples
+    frac = torch.arange(num_samples, device=near.device, dtype=near.dtype) / num_samples
     t = torch.lerp(near.unsqueeze(-1), far.unsqueeze(-1), frac)
     if noise_t is not None:
         t = t + noise_t * ((far - near).unsqueeze(-1) / num_samples)
@@ -171,7 +172,7 @@ def field(points, planes, w1, b1, w2, b2, palette, beta, alpha, scene_range,
         points = points.detach().requires_grad_()
     x = points / scene_range
     with torch.no_grad():
-        outside = (x.abs() > 1).any(dim=-1).float()
+        outside = (x.abs() > 1).any(dim=-1).to(x.dtype)
     out = triplane_decoder(planes, x, w1, b1, w2, b2)
     dist = out[..., 0]
     feat = out[..., 1:]
@@ -209,7 +210,7 @@ def sampler(x_in, planes, w1, b1, w2, b2, palette, beta, alpha, scene_range,
         pts = pts.detach().requires_grad_()
     x = pts / scene_range
     with torch.no_grad():
-        outside = (x.abs() > 1).any(dim=-1).float()
+        outside = (x.abs() > 1).any(dim=-1).to(x.dtype)
     dec = triplane_decoder(planes, x, w1, b1, w2, b2)
     dist, feat = dec[..., :1], dec[..., 1:]
     if 'normals' in request:
@@ -230,7 +231,7 @@ def sampler(x_in, planes, w1, b1, w2, b2, palette, beta, alpha, scene_range,
             inside = a < scene_range - 5e-2
             m = torch.ones_like(sigma)
             for i, j in ((0, 1), (0, 2), (1, 2), (1, 2)):
-                m = m * (1 - (inside[..., i] & inside[..., j]).float())
+                m = m * (1 - (inside[..., i] & inside[..., j]).to(m.dtype))
             sigma = sigma + 100 * (m * (1 - outside))
         out['sigma'] = sigma
     if 'coords' in request:
@@ -266,7 +267,7 @@ def composite_weights(sigma, dirs_unit, depths):
 
 def smooth_weights(w):
     """run.py:266-272: max over (i-1, i), mean over (i, i+1), + 0.01."""
-    w = F.max_pool1d(w.unsqueeze(1).float(), 2, 1, padding=1)
+    w = F.max_pool1d(w.unsqueeze(1), 2, 1, padding=1)
     w = F.avg_pool1d(w, 2, 1).squeeze(1)
     return w + 0.01
 

@@ -4,7 +4,7 @@ mkdir -p gpurun_out
 LIBDIR=$PWD/nerf_from_image_b200/csrc
 for a in "$@"; do
   case $a in
-    tests) timeout 1500 python -m pytest tests -m gpu -q -x 2>&1 | tail -15 > gpurun_out/r2_pytest_gpu.log; cat gpurun_out/r2_pytest_gpu.log;;
+    tests) timeout 1500 python -m pytest tests -m gpu -q --maxfail=12 2>&1 | tail -40 > gpurun_out/r2_pytest_gpu.log; cat gpurun_out/r2_pytest_gpu.log;;
     bench) timeout 400 python bench.py > gpurun_out/r2_bench.json 2> gpurun_out/r2_bench.err; cat gpurun_out/r2_bench.json; tail -3 gpurun_out/r2_bench.err;;
     ab) for l in $LIBDIR/libnfi_render.so $LIBDIR/libnfi_render_*.so; do NFI_LIB_PATH=$l timeout 120 python tools/ab_forward.py 32 10 2>&1 | grep -v Warn | tail -1; done > gpurun_out/r2_ab_forward.txt; cat gpurun_out/r2_ab_forward.txt;;
     ab_bwd) for l in $LIBDIR/libnfi_render.so $LIBDIR/libnfi_render_*.so; do NFI_LIB_PATH=$l timeout 200 python tools/time_backward.py 32 cam 2>&1 | grep -v Warn; done > gpurun_out/r2_ab_backward.txt; cat gpurun_out/r2_ab_backward.txt;;
@@ -17,6 +17,7 @@ for a in "$@"; do
              ncu -i gpurun_out/r2_bwd.ncu-rep --page source --csv > gpurun_out/r2_bwd_src.csv 2>/dev/null
              rm -f gpurun_out/r2_bwd.ncu-rep; tail -2 gpurun_out/r2_ncu_bwd.log | cut -c1-200;;
     ncu_list) timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 80 --csv --log-file gpurun_out/r2_launches.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-e2e > gpurun_out/r2_ncu_list.log 2>&1; tail -14 gpurun_out/r2_launches.csv | cut -c1-200;;
+    diag) timeout 600 python tools/grad_diag.py > gpurun_out/r2_grad_diag.txt 2>&1; cat gpurun_out/r2_grad_diag.txt;;
     *) echo "unknown job $a";;
   esac
 done
