@@ -70,7 +70,30 @@ class SampleParams(ctypes.Structure):
         'sdf_distance', 'sigma', 'rgb', 'semantics', 'normals')]
 
 
-# every symbol include/nfi_render.h declares (tests/test_abi.py checks the
+SYNTH_MAX_BLOCKS = 9
+
+
+class SynthLayer(ctypes.Structure):
+    """struct nfi_synth_layer (include/nfi_synth.h)."""
+    _fields_ = [(n, ctypes.c_void_p) for n in ('weight', 'affine_w', 'affine_b', 'bias', 'noise')]
+
+
+class SynthParams(ctypes.Structure):
+    """struct nfi_synth_params."""
+    _fields_ = [
+        ('batch', ctypes.c_int32), ('img_resolution', ctypes.c_int32),
+        ('img_channels', ctypes.c_int32), ('w_dim', ctypes.c_int32),
+        ('num_blocks', ctypes.c_int32), ('num_ws', ctypes.c_int32),
+        ('channels', ctypes.c_int32 * SYNTH_MAX_BLOCKS),
+        ('ws', ctypes.c_void_p), ('const_input', ctypes.c_void_p),
+        ('conv0', SynthLayer * SYNTH_MAX_BLOCKS), ('conv1', SynthLayer * SYNTH_MAX_BLOCKS),
+        ('torgb', SynthLayer * SYNTH_MAX_BLOCKS),
+        ('planes', ctypes.c_void_p), ('workspace', ctypes.c_void_p),
+        ('workspace_bytes', ctypes.c_size_t),
+    ]
+
+
+# every symbol include/nfi_render.h and include/nfi_synth.h declare (tests/test_abi.py checks the
 # header against this table and the table against the built library)
 EXPORTS = {
     'nfi_abi_version': (ctypes.c_int, []),
@@ -98,6 +121,8 @@ EXPORTS = {
     'nfi_fill_uniform': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int64, ctypes.c_uint64,
                                         ctypes.c_uint32, ctypes.c_int64, ctypes.c_void_p]),
     'nfi_sample_field': (ctypes.c_int, [ctypes.POINTER(SampleParams), ctypes.c_void_p]),
+    'nfi_synthesis_workspace_bytes': (ctypes.c_size_t, [ctypes.POINTER(SynthParams)]),
+    'nfi_synthesis_forward': (ctypes.c_int, [ctypes.POINTER(SynthParams), ctypes.c_void_p]),
     'nfi_pose_to_matrix': (ctypes.c_int, [
         ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int32,
         ctypes.c_int32, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]),

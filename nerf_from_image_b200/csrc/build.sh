@@ -1,7 +1,8 @@
 #!/bin/bash
 # Builds libnfi_render.so in-tree for sm_100a (cross-compiles without a GPU).
-# Three translation units compiled in parallel: the pipelined tcgen05 kernels (nfi_pipe.cu),
-# the sampler seam and pose kernels (nfi_field.cu), and everything else (nfi_render.cu: C ABI,
+# Four translation units compiled in parallel: the pipelined tcgen05 kernels (nfi_pipe.cu),
+# the sampler seam and pose kernels (nfi_field.cu), the synthesis network (nfi_synth.cu), and
+# everything else (nfi_render.cu: C ABI,
 # re-layout, SIMT and lockstep kernels).  Only nfi_render.cu takes --split-compile 0 (its many
 # kernels are optimised in parallel); the pipelined forward kernel schedules ~3 % slower with
 # it (measured).
@@ -14,8 +15,11 @@ $NVCC $FLAGS -c -o nfi_pipe.o nfi_pipe.cu "$@" &
 pipe_pid=$!
 $NVCC $FLAGS -c -o nfi_field.o nfi_field.cu "$@" &
 field_pid=$!
+$NVCC $FLAGS -c -o nfi_synth.o nfi_synth.cu "$@" &
+synth_pid=$!
 $NVCC $FLAGS --split-compile 0 -c -o nfi_render.o nfi_render.cu "$@"
 wait $pipe_pid
 wait $field_pid
+wait $synth_pid
 $NVCC -shared -cudart static -gencode arch=compute_100a,code=sm_100a \
-  -Xcompiler -fPIC -o libnfi_render.so nfi_render.o nfi_pipe.o nfi_field.o
+  -Xcompiler -fPIC -o libnfi_render.so nfi_render.o nfi_pipe.o nfi_field.o nfi_synth.o

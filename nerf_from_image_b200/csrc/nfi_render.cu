@@ -13,6 +13,8 @@
 #include "nfi_field_launch.h"
 #include "nfi_pipe_launch.h"
 #include "nfi_render.h"
+#include "nfi_synth.h"
+#include "nfi_synth_launch.h"
 
 #define NFI_STR_(x) #x
 #define NFI_STR(x) NFI_STR_(x)
@@ -554,6 +556,17 @@ int nfi_pose_to_matrix_backward(const float* z0, const float* t2, const float* s
   return nfi::launch_pose_to_matrix_backward(z0, t2, s, q, camera_flipped, batch, g_c2w, g_focal,
                                              g_z0, g_t2, g_s, g_q, (cudaStream_t)stream, g_err,
                                              sizeof(g_err));
+}
+
+size_t nfi_synthesis_workspace_bytes(const nfi_synth_params* params) {
+  if (params == nullptr) return 0;
+  return nfi::synth::workspace_bytes(*params);
+}
+
+int nfi_synthesis_forward(const nfi_synth_params* params, void* stream) {
+  if (params == nullptr) return fail("params is NULL");
+  if (params->batch <= 0) return fail("empty batch");
+  return nfi::synth::forward(*params, (cudaStream_t)stream, g_err, sizeof(g_err));
 }
 
 int nfi_render_forward_host(const nfi_render_params* hp, int32_t device) {

@@ -1,4 +1,4 @@
-/* Plain-C consumer of include/nfi_render.h: proves the header is valid C99 (no C++-isms, no
+/* Plain-C consumer of include/nfi_render.h and include/nfi_synth.h: proves the header is valid C99 (no C++-isms, no
  * torch types), that the structs have the layout the ctypes mirror assumes, and that the
  * library links and reports errors through return codes without a GPU.
  * Built and run by tests/test_abi.py::test_header_is_plain_c_and_links. */
@@ -7,11 +7,14 @@
 #include <string.h>
 
 #include "nfi_render.h"
+#include "nfi_synth.h"
 
 int main(void) {
   nfi_render_params p;
   nfi_render_grads g;
   nfi_sample_params s;
+  nfi_synth_params y;
+  memset(&y, 0, sizeof y);
   memset(&p, 0, sizeof p);
   memset(&g, 0, sizeof g);
   memset(&s, 0, sizeof s);
@@ -21,7 +24,11 @@ int main(void) {
   printf("offsets planes %zu workspace %zu noise_seed %zu points %zu\n",
          offsetof(nfi_render_params, planes), offsetof(nfi_render_params, workspace),
          offsetof(nfi_render_params, noise_seed), offsetof(nfi_sample_params, points));
+  printf("synth sizeof %zu layer %zu offsets ws %zu conv1 %zu planes %zu\n", sizeof y,
+         sizeof(nfi_synth_layer), offsetof(nfi_synth_params, ws), offsetof(nfi_synth_params, conv1),
+         offsetof(nfi_synth_params, planes));
   if (nfi_abi_version() != NFI_ABI_VERSION) return 10;
+  if (nfi_synthesis_forward(&y, NULL) == 0 || nfi_synthesis_workspace_bytes(&y) != 0) return 19;
   /* every entry point rejects an empty request with a non-zero code and a message */
   if (nfi_render_forward(&p, NULL) == 0 || strlen(nfi_last_error()) == 0) return 11;
   if (nfi_render_backward(&p, &g, NULL) == 0) return 12;

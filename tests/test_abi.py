@@ -1,4 +1,4 @@
-"""The C-ABI library builds, loads and exports what include/nfi_render.h declares
+"""The C-ABI library builds, loads and exports what include/*.h declare
 (no compute calls: this file runs without a GPU)."""
 import ctypes
 import os
@@ -8,10 +8,11 @@ from nerf_from_image_b200 import _lib
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 HEADER = os.path.join(ROOT, 'include', 'nfi_render.h')
+SYNTH_HEADER = os.path.join(ROOT, 'include', 'nfi_synth.h')
 
 
 def header_functions():
-    src = open(HEADER).read()
+    src = open(HEADER).read() + open(SYNTH_HEADER).read()
     return re.findall(r'NFI_API\s+[\w\s\*]+?\b(nfi_\w+)\s*\(', src)
 
 
@@ -32,13 +33,15 @@ def test_library_exports_every_declared_symbol():
 
 def test_struct_layout_matches_header():
     """Field order / count of the ctypes mirrors vs the C structs."""
-    src = open(HEADER).read()
+    src = open(HEADER).read() + open(SYNTH_HEADER).read()
     for cname, cls in (('nfi_render_params', _lib.RenderParams),
                        ('nfi_render_grads', _lib.RenderGrads),
-                       ('nfi_sample_params', _lib.SampleParams)):
+                       ('nfi_sample_params', _lib.SampleParams),
+                       ('nfi_synth_layer', _lib.SynthLayer),
+                       ('nfi_synth_params', _lib.SynthParams)):
         body = re.search(r'typedef struct %s \{(.*?)\} %s;' % (cname, cname), src, re.S).group(1)
         body = re.sub(r'/\*.*?\*/', '', body, flags=re.S)
-        fields = [re.search(r'(\w+)\s*$', d.strip()).group(1)
+        fields = [re.search(r'(\w+)\s*(?:\[\w+\])?$', d.strip()).group(1)
                   for d in body.split(';') if d.strip()]
         assert fields == [f[0] for f in cls._fields_], cname
 
@@ -85,6 +88,11 @@ def test_header_is_plain_c_and_links(tmp_path):
     assert [int(x) for x in sizes] == [ctypes.sizeof(_lib.RenderParams),
                                        ctypes.sizeof(_lib.RenderGrads),
                                        ctypes.sizeof(_lib.SampleParams)]
+    synth = re.search(r'synth sizeof (\d+) layer (\d+) offsets ws (\d+) conv1 (\d+) planes (\d+)',
+                      out).groups()
+    assert [int(x) for x in synth] == [ctypes.sizeof(_lib.SynthParams), ctypes.sizeof(_lib.SynthLayer),
+                                       _lib.SynthParams.ws.offset, _lib.SynthParams.conv1.offset,
+                                       _lib.SynthParams.planes.offset]
     offs = re.search(r'offsets planes (\d+) workspace (\d+) noise_seed (\d+) points (\d+)', out).groups()
     assert [int(x) for x in offs] == [_lib.RenderParams.planes.offset,
                                       _lib.RenderParams.workspace.offset,

@@ -47,11 +47,15 @@ def test_backward_at_benchmark_geometry(cuda_lib, case, mode):
     cam_names = [k for k in ('c2w', 'focal', 'bbox', 'center') if cams[k] is not None]
     wr, wm = _weights((B, H, W, 3), (B, H, W), 'cuda')
 
-    sc, cm = _leaves(scene, cams, names, cam_names)
-    ref = Hh.run_oracle(sc, cm, H, W, S, nt, nu)
-    loss = (ref['rgb'] * wr).sum() + (ref['mask'] * wm).sum()
+    # Ground truth = the oracle in float64.  (Its float32 run -- what the reference's autograd
+    # computes -- is itself 2.3e-3 away from that on the plane gradient of the orthographic
+    # case: tools/grad_diag.py, profiles/r2_grad_diag.txt; it is only used for the image.)
+    dbl = lambda d: {k: (v.double() if torch.is_tensor(v) else v) for k, v in d.items()}
+    sc, cm = _leaves(dbl(scene), dbl(cams), names, cam_names)
+    ref = Hh.run_oracle(sc, cm, H, W, S, nt.double(), nu.double())
+    loss = (ref['rgb'] * wr.double()).sum() + (ref['mask'] * wm.double()).sum()
     gref = torch.autograd.grad(loss, [sc[n] for n in names] + [cm[n] for n in cam_names])
-    ref_rgb = ref['rgb'].detach()
+    ref_rgb = ref['rgb'].detach().float()
     del ref, loss
 
     sc2, cm2 = _leaves(scene, cams, names, cam_names)
@@ -59,9 +63,10 @@ def test_backward_at_benchmark_geometry(cuda_lib, case, mode):
     assert Hh.rel_l2(rgb.detach(), ref_rgb) < 2e-4
     loss = (rgb * wr).sum() + (mask * wm).sum()
     got = torch.autograd.grad(loss, [sc2[n] for n in names] + [cm2[n] for n in cam_names])
+    tol = 2e-4 if mode == 1 else 3e-3     # fp32 SIMT / 3xTF32 tensor-core backward
     for n, a, b in zip(names + cam_names, got, gref):
-        err = Hh.rel_l2(a, b)
-        assert err < 2e-3, (n, err)
+        err = Hh.rel_l2(a.double(), b)
+        assert err < tol, (n, err)
 
 
 @pytest.mark.parametrize('mode', [1, 4])
@@ -86,7 +91,10 @@ def test_force_no_cam_grad_on_cuda(cuda_lib, mode):
     gr = torch.autograd.grad((ref['rgb'] * wr).sum() + (ref['mask'] * wm).sum(),
                              [sc3[n] for n in names] + [cm3[n] for n in cam_names],
                              allow_unused=True)
-    assert all(x is None for x in gr[2:])
+    # (the reference detaches the coarse points, the depths and the directions, run.py:210-214,
+    # but builds the FINE points from the attached origins, run.py:286-288, so its autograd
+    # still sends a fine-pass-only gradient to the camera position; the fused path cuts the
+    # cameras completely -- DESIGN.md section 6.  The field gradients are unaffected.)
     for n, a, b in zip(names, g, gr):
         assert Hh.rel_l2(a, b) < 2e-3, n
 

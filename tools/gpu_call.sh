@@ -17,6 +17,7 @@ for a in "$@"; do
              ncu -i gpurun_out/r2_bwd.ncu-rep --page source --csv > gpurun_out/r2_bwd_src.csv 2>/dev/null
              rm -f gpurun_out/r2_bwd.ncu-rep; tail -2 gpurun_out/r2_ncu_bwd.log | cut -c1-200;;
     ncu_list) timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 80 --csv --log-file gpurun_out/r2_launches.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-e2e > gpurun_out/r2_ncu_list.log 2>&1; tail -14 gpurun_out/r2_launches.csv | cut -c1-200;;
+    synth) timeout 900 python -m pytest tests/test_synthesis_gpu.py -m gpu -q --maxfail=12 2>&1 | tail -40 > gpurun_out/r2_pytest_synth.log; cat gpurun_out/r2_pytest_synth.log;;
     diag) timeout 600 python tools/grad_diag.py > gpurun_out/r2_grad_diag.txt 2>&1; cat gpurun_out/r2_grad_diag.txt;;
     *) echo "unknown job $a";;
   esac

@@ -46,3 +46,14 @@ for case in (sys.argv[1:] or ['p3d_plain', 'cub_ortho', 'p3d_bbox']):
         if n in res['tc']:
             line += '  | tc vs f32 %.2e' % rel(res['tc'][n], res['f32'][n])
         print(line)
+    # where does the tensor-core kernel's plane-gradient error sit?
+    gt, g64 = res['tc']['planes'].double(), res['f64']['planes']
+    err = (gt - g64)
+    e2 = err.square().flatten()
+    top = e2.topk(1000).values.sum() / e2.sum()
+    print('  planes tc: share of squared error in the 1000 worst texel-channels %.3f (of %d), max|err|/max|g| %.2e'
+          % (top.item(), e2.numel(), (err.abs().max() / g64.abs().max()).item()))
+    print('  per plane     :', ' '.join('%.2e' % rel(gt[:, i], g64[:, i]) for i in range(3)))
+    print('  per channel/4 :', ' '.join('%.1e' % rel(gt[:, :, c:c + 4], g64[:, :, c:c + 4]) for c in range(0, 32, 4)))
+    gs = res['simt']['planes'].double()
+    print('  tc vs simt    : %.2e' % rel(gt, gs))
