@@ -1,31 +1,34 @@
 #!/usr/bin/env python
-"""Benchmark of the fused tri-plane render (BASELINE.json metric: rays/s at
-128x128, 64 coarse + 64 fine samples per ray).
+"""Benchmark of the fused tri-plane render (BASELINE.json metric: rays/s at 128x128, 64 coarse +
+64 fine samples per ray).
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+                    [--config 2|3|4|5] [--scaling weak|strong]
 
-One "step" = one pass of the hot path over one batch of config 2
-(p3d_car geometry, batch 32 per GPU): planes [32,3,32,256,256] fp32 as the
-synthesis network leaves them -> channel-last re-layout -> fused forward render
--> rgb/depth/mask.  Inputs (805 MB of planes + 268 MB of noise per GPU) are far
-larger than the 126 MB L2, so consecutive steps cannot be served from cache.
+Workloads (BASELINE.json `configs`):
+  --config 2 (default)  p3d_car generator forward: batch 32 per GPU, 256^2 x 32ch fp32 tri-planes
+             -> 128x128 rays x (64 + 64) samples -> rgb / depth / mask.
+               value     render with the planes resident in HBM in the layout the sm_100a plane
+                         producer emits (channel-last), CUDA events, max over ranks
+               e2e       w -> image through the public API: latents in pinned host memory -> H2D
+                         -> synthesis network (tcgen05 kernels) -> render -> D2H of rgb/depth/mask
+               roofline  render_forward_pipe against the algorithmic tensor-FLOP bound
+               cpu_baseline / --impl reference: the reference's own render on the host cores
+  --config 3  cub --run_inversion: orthographic, scene_range 2, GLOBAL batch 16 sharded over the
+             GPUs (4 images per GPU at N=4), 30 steps of forward + backward (gradients to planes,
+             palette, pose), rays/s of forward+backward.
+  --config 4  shapenet_chairs GAN generator step on the path: global batch 32, forward + backward
+             with decoder-weight / beta / alpha gradients too, all-reduce of those gradients.
+  --config 5  inversion sweep: resolution {128, 256} x samples/ray {32, 64, 128}, forward and
+             forward+backward, 8 images per GPU; one JSON line with a `sweep` list.
+--scaling strong (config 2): global batch 32 split over the GPUs instead of 32 per GPU.
 
-  value      rays/s with inputs resident in HBM (CUDA events, max over ranks)
-  e2e        same metric through the C-ABI host entry point
-             nfi_render_forward_host with PINNED HOST buffers: H2D of every
-             input and D2H of rgb/depth/mask inside the timed region
-  roofline   dominant kernel (render_forward_*) against the algorithmic
-             tensor-FLOP bound of SURVEY.md section 8d
-  cpu_baseline   the oracle port (oracle/render_oracle.py, same torch ops as the
-             reference) on this box's host cores, bounded sample, rank 0, N=1
-
---impl reference times only the CPU oracle port (the reference's own CPU
-PyTorch path cannot travel to the GPU box) on the same config.
+Inputs (>= 0.8 GB per GPU at config 2) are far larger than the 126 MB L2, so consecutive steps
+cannot be served from cache.
 """
 import argparse
 import ctypes
 import json
-import math
 import os
 import subprocess
 import sys
@@ -42,6 +45,18 @@ UNIT = 'rays/s'
 CFG = dict(batch=32, height=128, width=128, samples=64, plane_res=256, attention_values=10,
            dataset='p3d_car')
 FLOPS_PER_POINT = 2 * 32 * 64 + 2 * 64 * 11 + 2 * 10 * 3  # 5,564
+WORKLOADS = {
+    2: 'config 2: p3d_car generator forward, render 128x128, 64 coarse + 64 fine samples/ray, '
+       'batch %d per GPU, 256^2x32ch fp32 tri-planes -> rgb/depth/mask',
+    3: 'config 3: cub --run_inversion step (orthographic, scene_range 2.0): render forward + '
+       'backward (grads to planes, palette, tform_cam2world), 128x128, 64+64 samples/ray, GLOBAL '
+       'batch %d sharded over the GPUs',
+    4: 'config 4: shapenet_chairs GAN generator step on the render path: forward + backward incl. '
+       'decoder-weight / beta / alpha gradients + their all-reduce, 128x128, 64+64 samples/ray, '
+       'GLOBAL batch %d sharded over the GPUs',
+    5: 'config 5: p3d_car inversion sweep, resolution {128,256} x samples/ray {32,64,128}, %d '
+       'images per GPU, forward and forward+backward',
+}
 
 
 def peaks():
@@ -53,9 +68,22 @@ def peaks():
     return dict(hbm_gbs=6650.0, tflops=1590.0, source='fallback (B200_PROFILING.md)')
 
 
+def measured_traffic(kernel, batch):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of `kernel` from the committed
+    `ncu --set full` capture (profiles/traffic.json: written from the raw csv by
+    tools/ncu_summary.py); None when no capture of this batch size exists."""
+    path = os.path.join(ROOT, 'profiles', 'traffic.json')
+    if not os.path.isfile(path):
+        return None, None
+    for row in json.load(open(path)):
+        if row['kernel'] == kernel and row['batch'] == batch:
+            return row['dram_bytes'], row['source']
+    return None, None
+
+
 class ClockSampler(threading.Thread):
-    """SM clock and throttle reasons sampled DURING the timed region (NVML, every
-    ~10 ms; falls back to nvidia-smi if pynvml is missing)."""
+    """SM clock and throttle reasons sampled DURING the timed region (NVML, every ~10 ms; falls
+    back to nvidia-smi if pynvml is missing)."""
 
     def __init__(self, index):
         super().__init__(daemon=True)
@@ -95,7 +123,6 @@ class ClockSampler(threading.Thread):
         if not self.rows:
             return dict(sm_mhz=None, sm_max_mhz=self.max_mhz, reasons=['unsampled'])
         sm = sorted(r[0] for r in self.rows)
-        # NVML clocks-event-reason bits
         names = {0x8: 'hw_slowdown', 0x40: 'hw_thermal_slowdown', 0x20: 'sw_thermal_slowdown',
                  0x4: 'sw_power_cap'}
         seen = 0
@@ -105,10 +132,63 @@ class ClockSampler(threading.Thread):
                     reasons=[n for b, n in names.items() if seen & b], samples=len(self.rows))
 
 
-def best_cpu_threads():
-    """The reference's CPU path is plain PyTorch; its intra-op scaling saturates
-    well before all cores of a big host, so probe a few thread counts on a small
-    sample of the same workload and keep the fastest (reported as `cores`)."""
+# ------------------------------------------------------------------ the reference on the host
+def _cpu_case(n_images):
+    from fixtures import synthetic
+    ds = synthetic.DATASET_CONFIGS[CFG['dataset']]
+    scene = synthetic.make_scene(1234, n_images, plane_res=CFG['plane_res'],
+                                 attention_values=CFG['attention_values'],
+                                 scene_range=ds['scene_range'],
+                                 white_background=ds['white_background'])
+    cams = synthetic.make_cameras(1234, n_images, radius=ds['radius'])
+    nt, nu = synthetic.make_noise(1234, n_images, CFG['height'], CFG['width'], CFG['samples'])
+    return scene, cams, nt, nu
+
+
+def reference_kind():
+    """'reference' when the unmodified reference can run here (staged into baseline/_ref by
+    tools/stage_reference.py, or /root/reference itself), else 'port' (the oracle)."""
+    from oracle import reference_lift as RL
+    return 'reference' if RL.available() else 'port'
+
+
+def cpu_render(case, kind, seed=77):
+    """One pass of the reference's render on the host cores; returns (seconds, rgb)."""
+    scene, cams, nt, nu = case
+    H, W, S = CFG['height'], CFG['width'], CFG['samples']
+    t0 = time.perf_counter()
+    with torch.no_grad():
+        if kind == 'reference':
+            # run.py:176-350 lifted by AST, reference Generator carrying the scene's decoder,
+            # planes given (its synthesis network is the NEXT row of SURVEY.md section 8)
+            from oracle import reference_lift as RL
+            out, _, _ = RL.reference_render(scene, cams, H, W, S, seed=seed, generator=case_generator(case))
+            rgb = out[0]
+        else:
+            from oracle import render_oracle as O
+            rgb = O.render_oracle(scene['planes'], scene['w1'], scene['b1'], scene['w2'],
+                                  scene['b2'], scene['palette'], scene['beta'], scene['alpha'],
+                                  cams['c2w'], cams['focal'], None, None, H, W, S, nt, nu,
+                                  scene_range=scene['scene_range'],
+                                  white_background=scene['white_background'])['rgb']
+    return time.perf_counter() - t0, rgb
+
+
+_GEN = {}
+
+
+def case_generator(case):
+    from oracle import reference_lift as RL
+    key = id(case[0])
+    if key not in _GEN:
+        _GEN[key] = RL.build_reference_generator(case[0])
+    return _GEN[key]
+
+
+def best_cpu_threads(kind):
+    """The reference's CPU path is plain PyTorch; its intra-op scaling saturates well before all
+    cores of a big host, so probe a few thread counts on a small sample of the same workload and
+    keep the fastest (reported as `cores`)."""
     from fixtures import synthetic
     from oracle import render_oracle as O
     ds = synthetic.DATASET_CONFIGS[CFG['dataset']]
@@ -130,173 +210,363 @@ def best_cpu_threads():
             ts.append(time.perf_counter() - t0)
         if best_t is None or min(ts) < best_t:
             best, best_t = th, min(ts)
+    torch.set_num_threads(best)
     return best
 
 
-def cpu_oracle_rate(n_images, threads=None, grad=False):
-    """Times the oracle port on the host cores; returns (rays/s, seconds, outputs, inputs)."""
-    from fixtures import synthetic
-    from oracle import render_oracle as O
-    threads = threads or os.cpu_count()
-    torch.set_num_threads(threads)
-    ds = synthetic.DATASET_CONFIGS[CFG['dataset']]
-    scene = synthetic.make_scene(1234, n_images, plane_res=CFG['plane_res'],
-                                 attention_values=CFG['attention_values'],
-                                 scene_range=ds['scene_range'],
-                                 white_background=ds['white_background'])
-    cams = synthetic.make_cameras(1234, n_images, radius=ds['radius'])
-    nt, nu = synthetic.make_noise(1234, n_images, CFG['height'], CFG['width'], CFG['samples'])
-    t0 = time.perf_counter()
-    with torch.no_grad():
-        out = O.render_oracle(scene['planes'], scene['w1'], scene['b1'], scene['w2'],
-                              scene['b2'], scene['palette'], scene['beta'], scene['alpha'],
-                              cams['c2w'], cams['focal'], None, None, CFG['height'],
-                              CFG['width'], CFG['samples'], nt, nu,
-                              scene_range=scene['scene_range'],
-                              white_background=scene['white_background'])
-    dt = time.perf_counter() - t0
-    rays = n_images * CFG['height'] * CFG['width']
-    return rays / dt, dt, out, (scene, cams, nt, nu)
+def config_block(args, world, batch_per_gpu, global_batch):
+    """The same for both arms (the driver compares the two lines' `config`)."""
+    return {'workload': WORKLOADS[args.config] % (global_batch if args.config in (3, 4) else batch_per_gpu),
+            'global_batch': global_batch, 'scaling': args.scaling,
+            'parallelism': 'images sharded over the GPUs, all_gather of [rgb,depth,mask] tiles '
+                           'when N > 1 (the reference arm runs on host CPU cores, rank 0 only)',
+            'cache': 'inputs larger than L2; no flush needed', 'randomize': True}
 
 
 def run_reference(args):
-    """--impl reference: the CPU path of the reference (oracle port), bounded sample."""
+    """--impl reference: the reference's own CPU path on the host cores, bounded sample."""
     rank = int(os.environ.get('RANK', '0'))
     if rank != 0:
         return
+    kind = reference_kind()
+    threads = best_cpu_threads(kind)
     n_img = 1
-    threads = best_cpu_threads()
-    for _ in range(args.warmup):
-        cpu_oracle_rate(n_img, threads)
-    times = []
-    for _ in range(args.steps):
-        _, dt, _, _ = cpu_oracle_rate(n_img, threads)
-        times.append(dt)
+    case = _cpu_case(n_img)
+    for _ in range(max(1, args.warmup)):
+        cpu_render(case, kind)
+    times = [cpu_render(case, kind)[0] for _ in range(args.steps)]
     rays = n_img * CFG['height'] * CFG['width']
     total = sum(times)
     value = rays * len(times) / total
+    B = args.batch or CFG['batch']
     line = {
         'impl': 'reference', 'metric': METRIC, 'value': value, 'unit': UNIT,
         'n_gpus': args.gpus, 'steps': args.steps, 'warmup': args.warmup,
-        'ms_per_step': 1e3 * total / len(times), 'higher_is_better': True, 'scaling': 'weak',
+        'ms_per_step': 1e3 * total / len(times), 'higher_is_better': True, 'scaling': args.scaling,
         'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-        # same workload as the b200 arm; each step times a bounded sample of it (see cpu_baseline)
-        'config': {'workload': 'config 2: p3d_car render 128x128, 64 coarse + 64 fine '
-                               'samples/ray, batch %d per GPU, 256^2x32ch fp32 tri-planes given '
-                               '(channel-first) -> rgb/depth/mask' % CFG['batch'],
-                   'global_batch': args.gpus * CFG['batch'],
-                   'parallelism': 'host CPU cores (reference CPU path), rank 0 only',
-                   'randomize': True},
-        'cpu_baseline': {'value': value, 'unit': UNIT, 'cores': threads, 'host_cores': os.cpu_count(), 'kind': 'port',
-                         'sample': '%d image(s) of the 32-image batch per step, torch CPU fp32, '
-                                   'no_grad' % n_img},
+        'config': config_block(args, args.gpus, B, args.gpus * B if args.scaling == 'weak' else B),
+        'cpu_baseline': {'value': value, 'unit': UNIT, 'cores': threads,
+                         'host_cores': os.cpu_count(), 'kind': kind,
+                         'sample': '%d image(s) of the batch per step (same geometry; images are '
+                                   'independent, the rate is per ray), torch CPU fp32, no_grad; %s'
+                                   % (n_img, 'unmodified reference render (run.py:176-350 lifted '
+                                      'from baseline/_ref), planes given' if kind == 'reference'
+                                      else 'oracle port of the reference ops')},
         'e2e': {'value': value, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
         'gpu_launches': 0,
     }
     print(json.dumps(line))
 
 
-def main():
-    ap = argparse.ArgumentParser()
-    ap.add_argument('--gpus', type=int, default=1)
-    ap.add_argument('--steps', type=int, default=20)
-    ap.add_argument('--warmup', type=int, default=3)
-    ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
-    ap.add_argument('--batch', type=int, default=CFG['batch'])
-    ap.add_argument('--no-cpu-baseline', action='store_true')
-    ap.add_argument('--no-e2e', action='store_true')
-    ap.add_argument('--no-backward', action='store_true')
-    ap.add_argument('--e2e-steps', type=int, default=3)
-    ap.add_argument('--mlp-mode', type=lambda x: int(x, 0), default=0)
-    args = ap.parse_args()
-    args.warmup = max(args.warmup, 3) if args.impl == 'b200' else args.warmup
-    if args.impl == 'reference':
-        return run_reference(args)
+# ------------------------------------------------------------------ the B200 arm
+class Bench:
+    def __init__(self, args):
+        import torch.distributed as dist
+        from nerf_from_image_b200 import _lib, fused, parallel
+        from fixtures import synthetic
+        self.args, self.dist, self.fused, self.parallel, self.synthetic = args, dist, fused, parallel, synthetic
+        self._lib = _lib
+        self.world = int(os.environ.get('WORLD_SIZE', '1'))
+        self.rank = int(os.environ.get('RANK', '0'))
+        self.local_rank = int(os.environ.get('LOCAL_RANK', '0'))
+        if not torch.cuda.is_available():
+            raise SystemExit('bench.py needs a CUDA device: the fused renderer has no CPU path')
+        torch.cuda.set_device(self.local_rank)
+        self.dev = torch.device('cuda', self.local_rank)
+        if self.world > 1:
+            dist.init_process_group('nccl', device_id=self.dev)
+        self.lib = _lib.load()
 
-    import torch.distributed as dist
-    from nerf_from_image_b200 import _lib, fused, parallel
-    from fixtures import synthetic
+    # -------------------------------------------------------------- helpers
+    def barrier(self):
+        torch.cuda.synchronize()
+        if self.world > 1:
+            self.dist.barrier()
 
-    world = int(os.environ.get('WORLD_SIZE', '1'))
-    rank = int(os.environ.get('RANK', '0'))
-    local_rank = int(os.environ.get('LOCAL_RANK', '0'))
-    if not torch.cuda.is_available():
-        raise SystemExit('bench.py needs a CUDA device: the fused renderer has no CPU path')
-    torch.cuda.set_device(local_rank)
-    dev = torch.device('cuda', local_rank)
-    if world > 1:
-        dist.init_process_group('nccl', device_id=dev)
-    lib = _lib.load()
+    def max_over_ranks(self, x):
+        if self.world == 1:
+            return x
+        t = torch.tensor([x], device=self.dev, dtype=torch.float64)
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return t.item()
 
-    B, H, W, S = args.batch, CFG['height'], CFG['width'], CFG['samples']
-    ds = synthetic.DATASET_CONFIGS[CFG['dataset']]
-    # every rank renders its own 32 images (weak scaling; images are independent)
-    scene = synthetic.make_scene(1234 + rank, B, plane_res=CFG['plane_res'],
-                                 attention_values=CFG['attention_values'],
-                                 scene_range=ds['scene_range'],
-                                 white_background=ds['white_background'], device=dev)
-    cams = synthetic.make_cameras(1234 + rank, B, radius=ds['radius'], device=dev)
-    nt, nu = synthetic.make_noise(1234 + rank, B, H, W, S, device=dev)
-    cfg = fused.RenderConfig(scene_range=scene['scene_range'],
-                             white_background=scene['white_background'],
-                             attention_values=CFG['attention_values'], mlp_mode=args.mlp_mode)
+    def min_over_ranks(self, x):
+        if self.world == 1:
+            return x
+        t = torch.tensor([float(x)], device=self.dev, dtype=torch.float64)
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.MIN)
+        return t.item()
 
-    kernel_events = []
+    def timed(self, fn, steps, warmup):
+        for _ in range(warmup):
+            fn()
+        self.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        self.barrier()
+        return self.max_over_ranks(e0.elapsed_time(e1)) / steps
 
-    def step(time_kernel=False):
-        with torch.no_grad():
-            if time_kernel:
-                fused.KERNEL_EVENTS = kernel_events
-            out = full = None
-            if world > 1:
-                # the path's one exchange step, in place: the kernel writes this rank's tiles
-                # into its slice of the full-batch buffers, NCCL all-gathers them where they lie
-                full = parallel.gathered_buffers(world * B, H, W, dev)
-                out = parallel.shard_views(full, world * B, world, rank)
-            rgb, depth, mask, _ = fused.fused_render(
-                scene['planes'], scene['w1'], scene['b1'], scene['w2'], scene['b2'],
-                scene['palette'], scene['beta'], scene['alpha'], cams['c2w'], cams['focal'],
-                None, None, cfg, H, W, S, nt, nu, out=out)
-            fused.KERNEL_EVENTS = None
-            if world > 1:
-                rgb, depth, mask = parallel.all_gather_inplace(full, world * B)
-        return rgb, depth, mask
+    def scene(self, dataset, batch, seed, H, W, S, res=None, layout='channel_last'):
+        syn = self.synthetic
+        ds = syn.DATASET_CONFIGS[dataset]
+        sc = syn.make_scene(seed, batch, plane_res=res or CFG['plane_res'],
+                            attention_values=CFG['attention_values'], scene_range=ds['scene_range'],
+                            white_background=ds['white_background'],
+                            object_radius=ds['object_radius'], device=self.dev)
+        if layout == 'channel_last':   # what the sm_100a plane producer emits
+            sc['planes'] = sc['planes'].permute(0, 1, 3, 4, 2).contiguous()
+        cams = syn.make_cameras(seed, batch, ortho=ds['ortho'], radius=ds['radius'], device=self.dev)
+        nt, nu = syn.make_noise(seed, batch, H, W, S, device=self.dev)
+        cfg = self.fused.RenderConfig(scene_range=sc['scene_range'],
+                                      white_background=sc['white_background'],
+                                      attention_values=CFG['attention_values'],
+                                      mlp_mode=self.args.mlp_mode)
+        return sc, cams, nt, nu, cfg
 
-    for _ in range(args.warmup):
-        out = step()
-    torch.cuda.synchronize()
-    if world > 1:
-        dist.barrier()
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
-    torch.cuda.synchronize()
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    ev0.record()
-    for _ in range(args.steps):
-        out = step(time_kernel=True)
-    ev1.record()
-    torch.cuda.synchronize()
-    if world > 1:
-        dist.barrier()
-    clocks = sampler.summary() if rank == 0 else None
-    ms_total = ev0.elapsed_time(ev1)
-    if world > 1:
-        t = torch.tensor([ms_total], device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms_total = t.item()
-    ms_step = ms_total / args.steps
-    rays_step = world * B * H * W
-    value = rays_step / (ms_step * 1e-3)
-    k_ms = sum(a.elapsed_time(b) for a, b in kernel_events) / max(1, len(kernel_events))
+    def render(self, sc, cams, nt, nu, cfg, H, W, S, out=None, layout='channel_last', **leaves):
+        g = lambda k: leaves.get(k, sc[k] if k in sc else cams[k])
+        return self.fused.fused_render(
+            g('planes'), g('w1'), g('b1'), g('w2'), g('b2'), g('palette'), g('beta'), g('alpha'),
+            g('c2w'), cams['focal'], None, None, cfg, H, W, S, nt, nu, out=out,
+            planes_layout=layout)
 
-    # ------------------------------------------------------------ e2e (host buffers)
-    e2e = None
-    if not args.no_e2e:
-        host = {}
+    # -------------------------------------------------------------- config 2
+    def config2(self):
+        a, world, rank, dev = self.args, self.world, self.rank, self.dev
+        fused, parallel, dist = self.fused, self.parallel, self.dist
+        H, W, S = CFG['height'], CFG['width'], CFG['samples']
+        if a.scaling == 'strong':
+            gb = a.batch or CFG['batch']
+            if gb % world:
+                raise SystemExit('--scaling strong needs batch %% gpus == 0')
+            B = gb // world
+        else:
+            B = a.batch or CFG['batch']
+            gb = world * B
+        sc, cams, nt, nu, cfg = self.scene(CFG['dataset'], B, 1234 + rank, H, W, S)
+        kernel_events = []
+        gather_events = []
+
+        def step(time_kernel=False):
+            with torch.no_grad():
+                if time_kernel:
+                    fused.KERNEL_EVENTS = kernel_events
+                out = full = None
+                if world > 1:
+                    # the path's one exchange step, in place: the kernel writes this rank's tiles
+                    # into its slice of the full-batch buffers, one NCCL launch all-gathers them
+                    full = parallel.gathered_buffers(gb, H, W, dev)
+                    out = parallel.shard_views(full, gb, world, rank)
+                res = self.render(sc, cams, nt, nu, cfg, H, W, S, out=out)
+                fused.KERNEL_EVENTS = None
+                if world > 1:
+                    if time_kernel:
+                        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                        g0.record()
+                    res = parallel.all_gather_inplace(full, gb)
+                    if time_kernel:
+                        g1.record()
+                        gather_events.append((g0, g1))
+            return res[:3]
+
+        for _ in range(a.warmup):
+            step()
+        self.barrier()
+        sampler = ClockSampler(self.local_rank)
+        if rank == 0:
+            sampler.start()
+        torch.cuda.synchronize()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record()
+        for _ in range(a.steps):
+            last = step(time_kernel=True)
+        ev1.record()
+        self.barrier()
+        clocks = sampler.summary() if rank == 0 else None
+        ms_step = self.max_over_ranks(ev0.elapsed_time(ev1)) / a.steps
+        rays_step = gb * H * W
+        value = rays_step / (ms_step * 1e-3)
+        k_ms = sum(x.elapsed_time(y) for x, y in kernel_events) / max(1, len(kernel_events))
+        coll_ms = (self.max_over_ranks(sum(x.elapsed_time(y) for x, y in gather_events)
+                                       / max(1, len(gather_events))) if world > 1 else None)
+
+        # ---- N > 1: the gathered buffers are checked, not assumed
+        gathered = None
+        if world > 1:
+            with torch.no_grad():
+                mine = self.render(sc, cams, nt, nu, cfg, H, W, S)
+                a0, b0 = parallel.shard_range(gb, world, rank)
+                own_ok = all(torch.equal(x[a0:b0], y) for x, y in zip(last, mine[:3]))
+                # every rank re-renders its right-hand neighbour's images from that rank's seed
+                peer = (rank + 1) % world
+                scp, cmp_, ntp, nup, cfgp = self.scene(CFG['dataset'], B, 1234 + peer, H, W, S)
+                theirs = self.render(scp, cmp_, ntp, nup, cfgp, H, W, S)
+                a1, b1 = parallel.shard_range(gb, world, peer)
+                peer_ok = all(torch.equal(x[a1:b1], y) for x, y in zip(last, theirs[:3]))
+                del scp, ntp, nup, theirs
+            gathered = {'own_slice_bit_exact_on_every_rank': bool(self.min_over_ranks(own_ok)),
+                        'neighbour_slice_bit_exact_on_every_rank': bool(self.min_over_ranks(peer_ok)),
+                        'how': 'after the timed steps each rank compares its slice of the '
+                               'all-gathered rgb/depth/mask with a private render, and the slice of '
+                               'rank+1 with a local render of that rank\'s seeded inputs'}
+
+        # ---- e2e: w -> image through the public API, host latents in, host image out
+        e2e = self.e2e_generator_forward(B, gb, H, W, S) if not a.no_e2e else None
+        e2e_planes = self.e2e_planes_from_host(sc, cams, cfg, B, gb, H, W, S) \
+            if not (a.no_e2e or a.quick) else None
+
+        # ---- render with channel-first planes (the reference module's layout): re-layout pass
+        cf = None
+        if not a.quick:
+            sc_cf = dict(sc, planes=sc['planes'].permute(0, 1, 4, 2, 3).contiguous())
+            with torch.no_grad():
+                ms_cf = self.timed(lambda: self.render(sc_cf, cams, nt, nu, cfg, H, W, S,
+                                                       layout='channel_first'), 5, 2)
+            cf = {'value': B * world * H * W / (ms_cf * 1e-3) if a.scaling == 'weak'
+                  else gb * H * W / (ms_cf * 1e-3), 'unit': UNIT, 'ms_per_step': ms_cf,
+                  'what': 'same render fed with [B,3,32,R,R] planes as the reference synthesis '
+                          'module leaves them: + nfi_planes_to_channel_last (1.6 GB moved)'}
+            del sc_cf
+            torch.cuda.empty_cache()
+
+        fwd_bwd = self.fwd_bwd(sc, cams, nt, nu, cfg, H, W, S, gb) if not a.no_backward else None
+        if rank != 0:
+            return
+        pk = peaks()
+        flops_launch = float(B * H * W) * (2 * S) * FLOPS_PER_POINT
+        hbm_bytes_launch = float(B) * 3 * 32 * CFG['plane_res'] ** 2 * 4 + B * H * W * 20.0
+        achieved_tf = flops_launch / (k_ms * 1e-3) / 1e12 if k_ms > 0 else 0.0
+        traffic, traffic_src = measured_traffic('render_forward_pipe', B)
+        roofline = {
+            'bound': 'tensor', 'achieved': achieved_tf, 'peak': pk['tflops'], 'unit': 'TFLOP/s',
+            'frac': achieved_tf / pk['tflops'], 'traffic': traffic, 'traffic_source': traffic_src,
+            'kernel': 'render_forward_pipe (dominant kernel of the step)', 'kernel_ms': k_ms,
+            'kernel_share_of_step': k_ms / ms_step if ms_step > 0 else None,
+            'algorithmic_flops_per_launch': flops_launch,
+            'algorithmic_hbm_bytes_per_launch': hbm_bytes_launch,
+            'hbm_achieved_gbs': hbm_bytes_launch / (k_ms * 1e-3) / 1e9 if k_ms > 0 else 0.0,
+            'hbm_peak_gbs': pk['hbm_gbs'], 'peak_source': pk['source'],
+        }
+        cpu_baseline = parity = eager = None
+        if world == 1 and not a.no_cpu_baseline:
+            cpu_baseline, parity = self.cpu_baseline_and_parity(cfg, H, W, S)
+            eager = self.eager_gpu(H, W, S)
+        line = {
+            'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': a.steps,
+            'warmup': a.warmup, 'ms_per_step': ms_step, 'higher_is_better': True,
+            'scaling': a.scaling, 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+            'config': config_block(a, world, B, gb),
+            'clocks': clocks, 'e2e': e2e,
+            # per step: prep_weight_image, render_forward_pipe
+            'gpu_launches': 2 * a.steps,
+            'roofline': roofline, 'fwd_bwd': fwd_bwd, 'cpu_baseline': cpu_baseline,
+            'torch_eager_gpu': eager, 'parity': parity, 'gathered_check': gathered,
+            'collective_ms': coll_ms, 'render_from_channel_first_planes': cf,
+            'e2e_planes_from_host': e2e_planes,
+        }
+        print(json.dumps(line))
+
+    def e2e_generator_forward(self, B, gb, H, W, S):
+        """w -> image end to end: the per-step inputs (latents, cameras) start in pinned host
+        memory, the image ends in pinned host memory; synthesis network and render both on the
+        sm_100a kernels.  With the reference files staged the call is the public drop-in
+        ``render()`` on the reference's own Generator; otherwise the same two stages are called
+        directly on seeded synthesis parameters."""
+        from nerf_from_image_b200 import render as R
+        from nerf_from_image_b200.synthesis import FusedSynthesis
+        from oracle import reference_lift as RL  # availability probe only
+        dev, rank, world = self.dev, self.rank, self.world
+        syn = self.synthetic
+        ds = syn.DATASET_CONFIGS[CFG['dataset']]
+        cams = syn.make_cameras(99 + rank, B, radius=ds['radius'], device='cpu')
+        host = {'c2w': cams['c2w'].pin_memory(), 'focal': cams['focal'].pin_memory(),
+                'ws': torch.randn(B, 15, 512, generator=torch.Generator().manual_seed(5 + rank)).pin_memory(),
+                'rgb': torch.empty(B, H, W, 3).pin_memory(), 'depth': torch.empty(B, H, W).pin_memory(),
+                'mask': torch.empty(B, H, W).pin_memory()}
+        api = None
+        try:
+            if not RL.available():
+                raise RuntimeError('reference files not staged')
+            import types
+            _, generator = RL._import_reference()
+            torch.manual_seed(1234)
+            g = generator.Generator(512, ds['scene_range'], attention_values=CFG['attention_values'],
+                                    use_sdf=True, disable_stylegan_noise=True).to(dev).eval()
+            g.requires_grad_(False)
+            with torch.no_grad():
+                g.decoder.net[2].bias[0] = -1.15   # random-init SDF head shifted to cross zero
+            R.configure(types.SimpleNamespace(use_viewdir=False, use_sdf=True,
+                                              attention_values=CFG['attention_values'],
+                                              fine_sampling=True, mlp_mode=self.args.mlp_mode),
+                        {'scene_range': ds['scene_range'], 'white_background': ds['white_background']})
+            R.enable_fused_synthesis(g)
+
+            def step():
+                with torch.no_grad():
+                    ws = host['ws'].to(dev, non_blocking=True)
+                    c2w = host['c2w'].to(dev, non_blocking=True)
+                    focal = host['focal'].to(dev, non_blocking=True)
+                    out = R.render(g, H, W, c2w, focal, None, None, ws, S)
+                    host['rgb'].copy_(out[0], non_blocking=True)
+                    host['depth'].copy_(out[1], non_blocking=True)
+                    host['mask'].copy_(out[2], non_blocking=True)
+                torch.cuda.synchronize()
+            api = ('nerf_from_image_b200.render.render (drop-in of run.py:176-350) on the reference '
+                   'Generator with enable_fused_synthesis: mapping-free w input -> texture mapper -> '
+                   'FusedSynthesis (tcgen05) -> fused render')
+        except Exception as exc:
+            why = repr(exc)[:80]
+            chans = [min(32768 // r, 512) for r in (4, 8, 16, 32, 64, 128, 256)]
+            fs = FusedSynthesis.from_params(syn.make_synthesis_params(3, 256, chans, 512, dev))
+            sc, _, _, _, cfg = self.scene(CFG['dataset'], B, 7, H, W, S)
+
+            def step():
+                with torch.no_grad():
+                    ws = host['ws'].to(dev, non_blocking=True)
+                    c2w = host['c2w'].to(dev, non_blocking=True)
+                    focal = host['focal'].to(dev, non_blocking=True)
+                    planes = fs(ws[:, :14])
+                    nt = torch.rand(B, H, W, S, device=dev)
+                    nu = torch.rand(B * H * W, S, device=dev)
+                    out = self.fused.fused_render(planes, sc['w1'], sc['b1'], sc['w2'], sc['b2'],
+                                                  sc['palette'], sc['beta'], sc['alpha'], c2w, focal,
+                                                  None, None, cfg, H, W, S, nt, nu,
+                                                  planes_layout='channel_last')
+                    host['rgb'].copy_(out[0], non_blocking=True)
+                    host['depth'].copy_(out[1], non_blocking=True)
+                    host['mask'].copy_(out[2], non_blocking=True)
+                torch.cuda.synchronize()
+            api = ('FusedSynthesis + fused_render called directly on seeded parameters (%s)' % why)
+        for _ in range(2):
+            step()
+        self.barrier()
+        n = max(2, self.args.e2e_steps)
+        t0 = time.perf_counter()
+        for _ in range(n):
+            step()
+        dt = self.max_over_ranks((time.perf_counter() - t0) / n)
+        R._FRONTS.clear()
+        h2d = sum(host[k].numel() * 4 for k in ('ws', 'c2w', 'focal'))
+        d2h = sum(host[k].numel() * 4 for k in ('rgb', 'depth', 'mask'))
+        torch.cuda.empty_cache()
+        return {'value': gb * H * W / dt, 'unit': UNIT, 'h2d_bytes_per_step': h2d,
+                'd2h_bytes_per_step': d2h, 'ms_per_step': dt * 1e3,
+                'mask_mean': host['mask'].mean().item(), 'api': api,
+                'what': 'generator forward, w -> image: latents + cameras H2D from pinned memory, '
+                        'synthesis network and render on the sm_100a kernels (both random draws '
+                        'made on the device like the reference), rgb/depth/mask D2H; wall clock '
+                        'incl. synchronisation, max over ranks'}
+
+    def e2e_planes_from_host(self, sc, cams, cfg, B, gb, H, W, S):
+        """Round 1's end-to-end figure, kept for continuity: PLANES from the host (805 MB per
+        step over PCIe) through the C-ABI host entry point."""
+        _lib, lib = self._lib, self.lib
         pin = lambda t: t.detach().cpu().contiguous().pin_memory()
-        for k in ('planes', 'w1', 'b1', 'w2', 'b2', 'palette', 'beta', 'alpha'):
-            host[k] = pin(scene[k])
+        host = {k: pin(sc[k]) for k in ('w1', 'b1', 'w2', 'b2', 'palette', 'beta', 'alpha')}
+        host['planes'] = pin(sc['planes'].permute(0, 1, 4, 2, 3))   # channel-first, as the ABI takes
         host['c2w'], host['focal'] = pin(cams['c2w']), pin(cams['focal'])
         host['rgb'] = torch.empty(B, H, W, 3).pin_memory()
         host['depth'] = torch.empty(B, H, W).pin_memory()
@@ -304,214 +574,225 @@ def main():
         p = _lib.RenderParams()
         p.batch, p.height, p.width, p.num_samples = B, H, W, S
         p.plane_res, p.n_attention = CFG['plane_res'], CFG['attention_values']
-        p.scene_range = scene['scene_range']
-        p.white_background = int(scene['white_background'])
-        # The two random draws of the path (torch.rand_like / torch.rand on the device in the
-        # reference, lib/nerf_utils.py:112,201) are generated on the device from a seed:
-        # they are not inputs that exist on the host in the reference either.
+        p.scene_range = sc['scene_range']
+        p.white_background = int(sc['white_background'])
         p.use_sdf, p.fine_sampling, p.noise_mode = 1, 1, _lib.NOISE_PHILOX
-        p.noise_seed = 1234 + rank
-        p.mlp_mode = args.mlp_mode
+        p.noise_seed = 1234 + self.rank
+        p.mlp_mode = self.args.mlp_mode
         in_keys = ('planes', 'w1', 'b1', 'w2', 'b2', 'palette', 'beta', 'alpha', 'c2w', 'focal')
         for k in in_keys + ('rgb', 'depth', 'mask'):
             setattr(p, k, ctypes.c_void_p(host[k].data_ptr()))
         h2d = sum(host[k].numel() * 4 for k in in_keys)
         d2h = sum(host[k].numel() * 4 for k in ('rgb', 'depth', 'mask'))
-        _lib.check(lib.nfi_render_forward_host(ctypes.byref(p), local_rank))  # warm-up
-        if world > 1:
-            dist.barrier()
+        _lib.check(lib.nfi_render_forward_host(ctypes.byref(p), self.local_rank))
+        self.barrier()
         t0 = time.perf_counter()
-        for _ in range(args.e2e_steps):
-            _lib.check(lib.nfi_render_forward_host(ctypes.byref(p), local_rank))
-        dt = (time.perf_counter() - t0) / args.e2e_steps
-        if world > 1:
-            t = torch.tensor([dt], device=dev)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            dt = t.item()
-        # same render through the device path with the same device-generated noise
-        nt2, nu2 = torch.empty_like(nt), torch.empty_like(nu)
-        st_ = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
-        _lib.check(lib.nfi_fill_uniform(ctypes.c_void_p(nt2.data_ptr()), nt2.numel(),
-                                        p.noise_seed, 0, 0, st_))
-        _lib.check(lib.nfi_fill_uniform(ctypes.c_void_p(nu2.data_ptr()), nu2.numel(),
-                                        p.noise_seed, 1, 0, st_))
-        with torch.no_grad():
-            rgb_d = fused.fused_render(
-                scene['planes'], scene['w1'], scene['b1'], scene['w2'], scene['b2'],
-                scene['palette'], scene['beta'], scene['alpha'], cams['c2w'], cams['focal'],
-                None, None, cfg, H, W, S, nt2, nu2)[0]
-        e2e_err = (host['rgb'] - rgb_d[:B].cpu()).abs().max().item()
-        del nt2, nu2, rgb_d
-        e2e = {'value': rays_step / dt, 'unit': UNIT, 'h2d_bytes_per_step': h2d,
-               'd2h_bytes_per_step': d2h, 'ms_per_step': dt * 1e3,
-               'max_abs_diff_vs_device_path': e2e_err,
-               'api': 'nfi_render_forward_host (C ABI, pinned host buffers; planes, decoder, '
-                      'palette, cameras H2D every step, the two uniform draws generated on the '
-                      'device from a seed (NFI_NOISE_PHILOX), rgb/depth/mask D2H)'}
+        for _ in range(2):
+            _lib.check(lib.nfi_render_forward_host(ctypes.byref(p), self.local_rank))
+        dt = self.max_over_ranks((time.perf_counter() - t0) / 2)
+        return {'value': gb * H * W / dt, 'unit': UNIT, 'h2d_bytes_per_step': h2d,
+                'd2h_bytes_per_step': d2h, 'ms_per_step': dt * 1e3,
+                'api': 'nfi_render_forward_host (C ABI): planes H2D every step -- PCIe-bound'}
 
-    # ------------------------------------------------------------ forward + backward
-    # (the inversion loop's use of the path, run.py:2202-2299: grads to planes, palette and
-    # cameras with the decoder frozen).  Reported beside the headline, not instead of it.
-    fwd_bwd = None
-    if not args.no_backward:
-        planes_g = scene['planes'].detach().clone().requires_grad_()
-        pal_g = scene['palette'].detach().clone().requires_grad_()
-        c2w_g = cams['c2w'].detach().clone().requires_grad_()
+    def fwd_bwd(self, sc, cams, nt, nu, cfg, H, W, S, gb, weights=False, steps=None):
+        """Forward + backward through the autograd.Function (grads to planes, palette, pose;
+        with `weights` also the decoder, beta, alpha)."""
+        leaves = {k: sc[k].detach().clone().requires_grad_() for k in ('planes', 'palette')}
+        leaves['c2w'] = cams['c2w'].detach().clone().requires_grad_()
+        if weights:
+            for k in ('w1', 'b1', 'w2', 'b2', 'beta', 'alpha'):
+                leaves[k] = sc[k].detach().clone().requires_grad_()
 
-        def step_bwd():
-            rgb, depth, mask, _ = fused.fused_render(
-                planes_g, scene['w1'], scene['b1'], scene['w2'], scene['b2'], pal_g,
-                scene['beta'], scene['alpha'], c2w_g, cams['focal'], None, None, cfg, H, W, S,
-                nt, nu)
+        def step():
+            rgb, depth, mask, _ = self.render(sc, cams, nt, nu, cfg, H, W, S, **leaves)
             (rgb.square().mean() + mask.mean()).backward()
-            planes_g.grad = pal_g.grad = c2w_g.grad = None
+            if weights and self.world > 1:
+                self.parallel.all_reduce_grads([leaves[k] for k in ('w1', 'b1', 'w2', 'b2', 'beta', 'alpha')])
+            for v in leaves.values():
+                v.grad = None
 
-        # start from a clean caching-allocator state (the legs above leave blocks of other
-        # sizes behind), then warm up: the timed steps must not contain cudaMalloc / cudaFree
         torch.cuda.synchronize()
         torch.cuda.empty_cache()
-        for _ in range(3):
-            step_bwd()
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-        b0, b1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        nb = max(2, min(5, args.steps))
-        b0.record()
-        for _ in range(nb):
-            step_bwd()
-        b1.record()
-        torch.cuda.synchronize()
-        ms_b = b0.elapsed_time(b1) / nb
-        if world > 1:
-            t = torch.tensor([ms_b], device=dev)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            ms_b = t.item()
-        fwd_bwd = {'value': rays_step / (ms_b * 1e-3), 'unit': UNIT, 'ms_per_step': ms_b,
-                   'what': 'fused_render forward + backward through the autograd.Function '
-                           '(grads to planes, palette, tform_cam2world; decoder frozen), '
-                           'incl. both re-layouts'}
-        del planes_g, pal_g, c2w_g
+        nb = steps or max(2, min(5, self.args.steps))
+        ms_b = self.timed(step, nb, 3)
         torch.cuda.empty_cache()
+        return {'value': gb * H * W / (ms_b * 1e-3), 'unit': UNIT, 'ms_per_step': ms_b,
+                'what': 'fused_render forward + backward through the autograd.Function (grads to '
+                        'planes, palette, tform_cam2world%s)' % (
+                            '; decoder weights, beta, alpha too (+ their all-reduce)' if weights
+                            else '; decoder frozen')}
 
-    if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
-        return
-
-    pk = peaks()
-    flops_launch = float(B * H * W) * (2 * S) * FLOPS_PER_POINT
-    hbm_bytes_launch = float(B) * 3 * 32 * CFG['plane_res'] ** 2 * 4 + B * H * W * 20.0
-    achieved_tf = flops_launch / (k_ms * 1e-3) / 1e12 if k_ms > 0 else 0.0
-    roofline = {
-        'bound': 'tensor', 'achieved': achieved_tf, 'peak': pk['tflops'], 'unit': 'TFLOP/s',
-        'frac': achieved_tf / pk['tflops'], 'traffic': TRAFFIC_BYTES_PER_IMAGE * B,
-        'kernel': 'render_forward (dominant kernel of the step)', 'kernel_ms': k_ms,
-        'kernel_share_of_step': k_ms / ms_step if ms_step > 0 else None,
-        'algorithmic_flops_per_launch': flops_launch,
-        'algorithmic_hbm_bytes_per_launch': hbm_bytes_launch,
-        'hbm_achieved_gbs': hbm_bytes_launch / (k_ms * 1e-3) / 1e9 if k_ms > 0 else 0.0,
-        'hbm_peak_gbs': pk['hbm_gbs'], 'peak_source': pk['source'],
-    }
-
-    cpu_baseline = None
-    parity = None
-    if world == 1 and not args.no_cpu_baseline:
+    def cpu_baseline_and_parity(self, cfg, H, W, S):
+        kind = reference_kind()
         n_img = 2
-        cores = best_cpu_threads()
-        # bounded sample: the same 2 images rendered repeatedly until >= 10 s of CPU work
-        # (first pass untimed: thread pool and allocator warm-up)
-        _, _, ref, (sc_c, cm_c, nt_c, nu_c) = cpu_oracle_rate(n_img, cores)
-        reps, dt = 0, 0.0
+        cores = best_cpu_threads(kind)
+        case = _cpu_case(n_img)
+        cpu_render(case, kind)          # untimed: thread pool and allocator warm-up
+        reps, dt, ref_rgb = 0, 0.0, None
         while dt < 10.0 and reps < 8:
-            dt += cpu_oracle_rate(n_img, cores)[1]
+            t, ref_rgb = cpu_render(case, kind)
+            dt += t
             reps += 1
         rate = reps * n_img * H * W / dt
-        cpu_baseline = {'value': rate, 'unit': UNIT, 'cores': cores, 'host_cores': os.cpu_count(), 'kind': 'port',
-                        'sample': '%d of the 32 images (same geometry) x %d passes, %.1f s, torch '
-                                  'CPU fp32 no_grad' % (n_img, reps, dt)}
-        # parity of the CUDA path on exactly those images
-        sc_g = {k: (v.to(dev) if torch.is_tensor(v) else v) for k, v in sc_c.items()}
+        cpu = {'value': rate, 'unit': UNIT, 'cores': cores, 'host_cores': os.cpu_count(), 'kind': kind,
+               'sample': '%d of the 32 images (same geometry) x %d passes, %.1f s, torch CPU fp32 '
+                         'no_grad, %s' % (n_img, reps, dt, 'unmodified reference render lifted from '
+                                          'baseline/_ref' if kind == 'reference' else 'oracle port')}
+        # parity of the CUDA path on exactly those images, against the oracle with the same
+        # injected noise (the reference draws its own: same distribution, different numbers)
+        from oracle import render_oracle as O
+        scene, cams, nt, nu = case
         with torch.no_grad():
-            rgb_g, dep_g, msk_g, _ = fused.fused_render(
-                sc_g['planes'], sc_g['w1'], sc_g['b1'], sc_g['w2'], sc_g['b2'], sc_g['palette'],
-                sc_g['beta'], sc_g['alpha'], cm_c['c2w'].to(dev), cm_c['focal'].to(dev), None,
-                None, cfg, H, W, S, nt_c.to(dev), nu_c.to(dev))
-        from oracle.render_oracle import psnr, rel_l2
-        parity = {'rgb_rel_l2': rel_l2(rgb_g.cpu(), ref['rgb']),
-                  'rgb_psnr_db': psnr(rgb_g.cpu(), ref['rgb']),
-                  'mask_rel_l2': rel_l2(msk_g.cpu(), ref['mask']),
-                  'depth_rel_l2': rel_l2(dep_g.cpu(), ref['depth']),
-                  'against': 'CPU oracle, identical injected noise, %d images' % n_img}
+            ref = O.render_oracle(scene['planes'], scene['w1'], scene['b1'], scene['w2'],
+                                  scene['b2'], scene['palette'], scene['beta'], scene['alpha'],
+                                  cams['c2w'], cams['focal'], None, None, H, W, S, nt, nu,
+                                  scene_range=scene['scene_range'],
+                                  white_background=scene['white_background'])
+            dev = self.dev
+            sg = {k: (v.to(dev) if torch.is_tensor(v) else v) for k, v in scene.items()}
+            rgb_g, dep_g, msk_g, _ = self.fused.fused_render(
+                sg['planes'], sg['w1'], sg['b1'], sg['w2'], sg['b2'], sg['palette'], sg['beta'],
+                sg['alpha'], cams['c2w'].to(dev), cams['focal'].to(dev), None, None, cfg, H, W, S,
+                nt.to(dev), nu.to(dev))
+        parity = {'rgb_rel_l2': O.rel_l2(rgb_g.cpu(), ref['rgb']),
+                  'rgb_psnr_db': O.psnr(rgb_g.cpu(), ref['rgb']),
+                  'mask_rel_l2': O.rel_l2(msk_g.cpu(), ref['mask']),
+                  'depth_rel_l2': O.rel_l2(dep_g.cpu(), ref['depth']),
+                  'against': 'CPU oracle (pinned to the reference), identical injected noise, '
+                             '%d images' % n_img}
+        return cpu, parity
 
-    # ------------------------------------------------------------ PyTorch eager on this GPU
-    # The same torch ops as the reference's render (the oracle port), fp32 with TF32 off like
-    # run.py:59-60, on a sample that fits (the unfused path materialises ~2 GB per image).
-    eager = None
-    if world == 1 and not args.no_cpu_baseline:
+    def eager_gpu(self, H, W, S):
+        """The same torch ops as the reference's render (the oracle port), fp32 with TF32 off like
+        run.py:59-60, on this GPU -- the number the fused kernel has to beat."""
         try:
             from oracle import render_oracle as O
             torch.backends.cuda.matmul.allow_tf32 = False
             torch.backends.cudnn.allow_tf32 = False
             n_img = 2
-            sc_e = synthetic.make_scene(77, n_img, plane_res=CFG['plane_res'],
-                                        attention_values=CFG['attention_values'],
-                                        scene_range=ds['scene_range'],
-                                        white_background=ds['white_background'], device=dev)
-            cm_e = synthetic.make_cameras(77, n_img, radius=ds['radius'], device=dev)
-            nt_e, nu_e = synthetic.make_noise(77, n_img, H, W, S, device=dev)
+            sc, cm, nt, nu, _ = self.scene(CFG['dataset'], n_img, 77, H, W, S, layout='channel_first')
 
-            def eager_step():
+            def fn():
                 with torch.no_grad():
-                    return O.render_oracle(sc_e['planes'], sc_e['w1'], sc_e['b1'], sc_e['w2'],
-                                           sc_e['b2'], sc_e['palette'], sc_e['beta'],
-                                           sc_e['alpha'], cm_e['c2w'], cm_e['focal'], None, None,
-                                           H, W, S, nt_e, nu_e, scene_range=sc_e['scene_range'],
-                                           white_background=sc_e['white_background'])
-            for _ in range(2):
-                eager_step()
-            torch.cuda.synchronize()
-            g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            g0.record()
-            for _ in range(3):
-                eager_step()
-            g1.record()
-            torch.cuda.synchronize()
-            ms_e = g0.elapsed_time(g1) / 3
-            eager = {'value': n_img * H * W / (ms_e * 1e-3), 'unit': UNIT, 'ms_per_step': ms_e,
-                     'sample': '%d images per step (same geometry), torch eager fp32 on this GPU, '
-                               'no_grad, oracle port of the reference ops' % n_img}
-            del sc_e, cm_e, nt_e, nu_e
+                    O.render_oracle(sc['planes'], sc['w1'], sc['b1'], sc['w2'], sc['b2'],
+                                    sc['palette'], sc['beta'], sc['alpha'], cm['c2w'], cm['focal'],
+                                    None, None, H, W, S, nt, nu, scene_range=sc['scene_range'],
+                                    white_background=sc['white_background'])
+            ms = self.timed(fn, 3, 2)
             torch.cuda.empty_cache()
-        except Exception as exc:  # out of memory on a smaller part: report, do not fail the bench
-            eager = {'unavailable': repr(exc)[:200]}
+            return {'value': n_img * H * W / (ms * 1e-3), 'unit': UNIT, 'ms_per_step': ms,
+                    'sample': '%d images per step (same geometry), torch eager fp32 on this GPU, '
+                              'no_grad, oracle port of the reference ops' % n_img}
+        except Exception as exc:
+            return {'unavailable': repr(exc)[:200]}
 
-    line = {
-        'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps,
-        'warmup': args.warmup, 'ms_per_step': ms_step, 'higher_is_better': True,
-        'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-        'config': {'workload': 'config 2: p3d_car render 128x128, 64 coarse + 64 fine '
-                               'samples/ray, batch %d per GPU, 256^2x32ch fp32 tri-planes given '
-                               '(channel-first) -> rgb/depth/mask' % B,
-                   'global_batch': world * B, 'parallelism': 'images sharded over %d GPU(s)'
-                   % world + (', all_gather of [rgb,depth,mask] tiles' if world > 1 else ''),
-                   'cache': 'inputs (1.07 GB per GPU) larger than L2; no flush needed',
-                   'randomize': True},
-        'clocks': clocks, 'e2e': e2e,
-        # per step: planes_to_cl_kernel, prep_weight_image, render_forward_pipe
-        'gpu_launches': 3 * args.steps,
-        'roofline': roofline, 'fwd_bwd': fwd_bwd, 'cpu_baseline': cpu_baseline,
-        'torch_eager_gpu': eager, 'parity': parity,
-    }
-    print(json.dumps(line))
-    if world > 1:
-        dist.destroy_process_group()
+    # -------------------------------------------------------------- configs 3 / 4
+    def config34(self):
+        a, world, rank = self.args, self.world, self.rank
+        H, W, S = CFG['height'], CFG['width'], CFG['samples']
+        inv = a.config == 3
+        gb = a.batch or (16 if inv else 32)
+        if gb % world:
+            raise SystemExit('global batch %d is not divisible by %d GPUs' % (gb, world))
+        B = gb // world
+        ds = 'cub' if inv else 'shapenet_chairs'
+        sc, cams, nt, nu, cfg = self.scene(ds, B, 1234 + rank, H, W, S)
+        steps = a.steps if a.steps_given else (30 if inv else 20)
+        sampler = ClockSampler(self.local_rank)
+        if rank == 0:
+            sampler.start()
+        res = self.fwd_bwd(sc, cams, nt, nu, cfg, H, W, S, gb, weights=not inv, steps=steps)
+        clocks = sampler.summary() if rank == 0 else None
+        with torch.no_grad():
+            ms_f = self.timed(lambda: self.render(sc, cams, nt, nu, cfg, H, W, S), 10, 3)
+        if rank != 0:
+            return
+        tiles = B * (H // 8) * (W // 16)
+        line = {
+            'metric': 'rays_per_sec_fwd_bwd_128x128_64+64spp', 'value': res['value'], 'unit': UNIT,
+            'n_gpus': world, 'steps': steps, 'warmup': 3, 'ms_per_step': res['ms_per_step'],
+            'higher_is_better': True, 'scaling': 'strong', 'vs_baseline': None, 'dtype': 'f32',
+            'data': 'synthetic', 'config': config_block(a, world, B, gb), 'clocks': clocks,
+            'forward_only': {'value': gb * H * W / (ms_f * 1e-3), 'unit': UNIT, 'ms_per_step': ms_f},
+            'images_per_gpu': B,
+            'tiles_per_gpu': tiles, 'waves_of_148_ctas': tiles / 148.0,
+            'what': res['what'], 'gpu_launches': 4 * steps,
+        }
+        print(json.dumps(line))
+
+    # -------------------------------------------------------------- config 5
+    def config5(self):
+        a, world, rank = self.args, self.world, self.rank
+        B = a.batch or 8
+        rows = []
+        for res in (128, 256):
+            for S in (32, 64, 128):
+                sc, cams, nt, nu, cfg = self.scene(CFG['dataset'], B, 1234 + rank, res, res, S)
+                with torch.no_grad():
+                    ms_f = self.timed(lambda: self.render(sc, cams, nt, nu, cfg, res, res, S), 5, 3)
+                fb = self.fwd_bwd(sc, cams, nt, nu, cfg, res, res, S, world * B, steps=3)
+                rays = world * B * res * res
+                flops = float(rays) * 2 * S * FLOPS_PER_POINT
+                rows.append({'resolution': res, 'samples_per_ray': S,
+                             'forward_rays_per_s': rays / (ms_f * 1e-3), 'forward_ms': ms_f,
+                             'forward_points_per_s': rays * 2 * S / (ms_f * 1e-3),
+                             'forward_tensor_tflops': flops / (ms_f * 1e-3) / 1e12,
+                             'fwd_bwd_rays_per_s': fb['value'], 'fwd_bwd_ms': fb['ms_per_step']})
+                del sc, nt, nu
+                torch.cuda.empty_cache()
+        if rank != 0:
+            return
+        pk = peaks()
+        for r in rows:
+            r['forward_roofline_frac'] = r['forward_tensor_tflops'] / world / pk['tflops']
+        base = [r for r in rows if r['resolution'] == 128 and r['samples_per_ray'] == 64][0]
+        print(json.dumps({
+            'metric': METRIC, 'value': base['forward_rays_per_s'], 'unit': UNIT, 'n_gpus': world,
+            'steps': 5, 'warmup': 3, 'ms_per_step': base['forward_ms'], 'higher_is_better': True,
+            'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+            'config': config_block(a, world, B, world * B), 'sweep': rows,
+            'roofline_peak': pk, 'gpu_launches': 2 * 5}))
+
+    def close(self):
+        if self.world > 1:
+            self.dist.destroy_process_group()
 
 
-# dram__bytes_read.sum + dram__bytes_write.sum of the render kernel from the
-# committed `ncu --set full` capture (profiles/), per launch; None until captured.
-# (269.0 + 118.2) MB for the 8 images of profiles/r1_ncu_v5_pipe_B8.txt; a launch moves this per image
-TRAFFIC_BYTES_PER_IMAGE = (269012736 + 118194688) / 8
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=None)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
+    ap.add_argument('--config', type=int, default=2, choices=[2, 3, 4, 5])
+    ap.add_argument('--scaling', default='weak', choices=['weak', 'strong'])
+    ap.add_argument('--batch', type=int, default=None)
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-e2e', action='store_true')
+    ap.add_argument('--no-backward', action='store_true')
+    ap.add_argument('--quick', action='store_true', help='skip the side legs (ncu, A/B runs)')
+    ap.add_argument('--e2e-steps', type=int, default=3)
+    ap.add_argument('--mlp-mode', type=lambda x: int(x, 0), default=0)
+    args = ap.parse_args()
+    args.steps_given = args.steps is not None
+    if args.steps is None:
+        args.steps = 20 if args.impl == 'b200' else 3
+    if args.impl == 'reference':
+        return run_reference(args)
+    args.warmup = max(args.warmup, 3)
+    if args.quick:
+        args.no_cpu_baseline = args.no_backward = True
+    b = Bench(args)
+    try:
+        if args.config == 2:
+            b.config2()
+        elif args.config in (3, 4):
+            b.config34()
+        else:
+            b.config5()
+    finally:
+        b.close()
+
 
 if __name__ == '__main__':
     main()

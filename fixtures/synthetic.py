@@ -125,3 +125,37 @@ def make_noise(seed, batch, height, width, num_samples, fine=True,
     noise_u = torch.rand(batch * height * width, num_samples,
                          generator=gen) if fine else None
     return noise_t.to(device), (noise_u.to(device) if fine else None)
+
+
+def make_synthesis_params(seed, res, channels, w_dim, device='cpu'):
+    """Parameters of a synthesis network (models/stylegan.py:438-490) under the reference's
+    state_dict names, drawn directly from a seed (no module needed): the flat dict
+    ``oracle.synthesis_oracle`` and ``synthesis.FusedSynthesis.from_params`` take."""
+    g = torch.Generator().manual_seed(seed)
+    rn = lambda *s: torch.randn(*s, generator=g).to(device)
+    p, layers = {}, {}
+    resolutions = [4 << i for i in range(len(channels))]
+    assert resolutions[-1] == res
+    for i, (r, c) in enumerate(zip(resolutions, channels)):
+        pre = 'b%d' % r
+        if i == 0:
+            p[pre + '.const'] = rn(c, 4, 4)
+        for name, cin in (('conv0', channels[i - 1] if i else None), ('conv1', c)):
+            if cin is None:
+                continue
+            key = pre + '.' + name
+            p[key + '.weight'] = rn(c, cin, 3, 3)
+            p[key + '.affine.weight'] = rn(cin, w_dim)
+            p[key + '.affine.bias'] = 1 + 0.1 * rn(cin)
+            p[key + '.bias'] = 0.2 * rn(c)
+            p[key + '.noise_strength'] = torch.tensor(0.07, device=device)
+            p[key + '.noise_const'] = rn(r, r)
+            layers[key] = dict(use_noise=True, up=(name == 'conv0'))
+        key = pre + '.torgb'
+        p[key + '.weight'] = rn(96, c, 1, 1)
+        p[key + '.affine.weight'] = rn(c, w_dim)
+        p[key + '.affine.bias'] = 1 + 0.1 * rn(c)
+        p[key + '.bias'] = 0.2 * rn(96)
+    p['meta'] = dict(img_resolution=res, img_channels=96, w_dim=w_dim, resolutions=resolutions,
+                     layers=layers)
+    return p

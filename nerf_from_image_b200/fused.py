@@ -99,11 +99,15 @@ def _make_params(cfg, planes_cl, w1, b1, w2, b2, palette, beta, alpha, c2w,
 
 
 def _check_shapes(cfg, planes, w1, b1, w2, b2, palette, c2w, focal, center,
-                  bbox, height, width, S, noise_t, noise_u):
+                  bbox, height, width, S, noise_t, noise_u, channel_last=False):
     B = planes.shape[0]
     A = cfg.attention_values
     nout = 1 + (A if A > 0 else 3)
-    assert planes.dim() == 5 and planes.shape[1:3] == (3, 32), planes.shape
+    if channel_last:
+        assert (planes.dim() == 5 and planes.shape[1] == 3 and planes.shape[4] == 32
+                and planes.shape[2] == planes.shape[3]), planes.shape
+    else:
+        assert planes.dim() == 5 and planes.shape[1:3] == (3, 32), planes.shape
     assert tuple(w1.shape) == (64, 32) and tuple(b1.shape) == (64,)
     assert tuple(w2.shape) == (nout, 64) and tuple(b2.shape) == (nout,), \
         (w2.shape, nout)
@@ -142,14 +146,18 @@ class FusedTriplaneRender(torch.autograd.Function):
     @staticmethod
     def forward(ctx, planes, w1, b1, w2, b2, palette, beta, alpha, c2w, focal,
                 center, bbox, cfg, height, width, S, noise_t, noise_u,
-                extra_mode, cam_grad, compute_normals=False, out=None):
+                extra_mode, cam_grad, compute_normals=False, out=None,
+                planes_layout='channel_first'):
+        channel_last = planes_layout == 'channel_last'
         _check_shapes(cfg, planes, w1, b1, w2, b2, palette, c2w, focal, center,
-                      bbox, height, width, S, noise_t, noise_u)
+                      bbox, height, width, S, noise_t, noise_u, channel_last)
         lib = _lib.load()
         dev = planes.device
         with torch.cuda.device(dev):
             stream = ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
-            planes_cl = planes_to_channel_last(planes.detach())
+            # [B,3,R,R,32] as synthesis.FusedSynthesis emits it: no re-layout pass
+            planes_cl = (_f32c(planes.detach(), 'planes') if channel_last
+                         else planes_to_channel_last(planes.detach()))
             t = dict(w1=_f32c(w1.detach(), 'w1'), b1=_f32c(b1.detach(), 'b1'),
                      w2=_f32c(w2.detach(), 'w2'), b2=_f32c(b2.detach(), 'b2'),
                      palette=_f32c(palette.detach(), 'palette') if palette is not None else None,
@@ -220,6 +228,7 @@ class FusedTriplaneRender(torch.autograd.Function):
             # silently corrupting the total L that backward rebuilds from rgb / mask / extra.
             ctx.cfg, ctx.dims, ctx.extra_mode = cfg, (height, width, S), extra_mode
             ctx.cam_grad = cam_grad
+            ctx.channel_last = channel_last
             # caller-owned outputs are slices of buffers an in-place all-gather completes
             # afterwards (parallel.py); it rewrites this rank's slice with the values it
             # already holds, so those are saved as aliases with their own version counter
@@ -289,7 +298,9 @@ class FusedTriplaneRender(torch.autograd.Function):
             ws = torch.empty(65536, dtype=torch.uint8, device=dev)
             p.workspace, p.workspace_bytes = _ptr(ws), 65536
             _lib.check(lib.nfi_render_backward(ctypes.byref(p), ctypes.byref(g), stream))
-            gplanes = planes_from_channel_last(gp_cl) if n_planes else None
+            gplanes = None
+            if n_planes:  # gradient in the layout the planes came in
+                gplanes = gp_cl if ctx.channel_last else planes_from_channel_last(gp_cl)
             gc2w = gfocal = gcenter = gbbox = None
             if cam:
                 # chain (dL/d origin, dL/d unit dir) to the camera parameters
@@ -319,16 +330,20 @@ class FusedTriplaneRender(torch.autograd.Function):
                 if t['bbox'] is not None and n_bbox:
                     gbbox = res.pop(0)
         return (gplanes, gw1, gb1, gw2, gb2, gpal, gbeta, galpha, gc2w, gfocal,
-                gcenter, gbbox, None, None, None, None, None, None, None, None, None, None)
+                gcenter, gbbox, None, None, None, None, None, None, None, None, None, None,
+                None)
 
 
 def fused_render(planes, w1, b1, w2, b2, palette, beta, alpha, c2w, focal,
                  center, bbox, cfg, height, width, num_samples, noise_t=None,
                  noise_u=None, extra_mode=_lib.EXTRA_NONE, cam_grad=True,
-                 compute_normals=False, out=None):
+                 compute_normals=False, out=None, planes_layout='channel_first'):
     """Functional form; returns (rgb, depth, mask, extra|None), with
     ``compute_normals`` (rgb, depth, mask, extra|None, normals).  ``out=(rgb, depth,
     mask)`` makes the kernel write into caller-owned tensors (see parallel.py).
+    ``planes_layout``: 'channel_first' = [B,3,32,R,R] as the reference's synthesis network
+    leaves them (re-laid-out here), 'channel_last' = [B,3,R,R,32] as synthesis.FusedSynthesis
+    emits them (used as they are; a plane gradient comes back in the same layout).
 
     The kernels compute in fp32 like the reference's render (run.py:59-60).  Under
     autocast (BASELINE config 4 trains the synthesis network in bf16) the field tensors
@@ -342,7 +357,7 @@ def fused_render(planes, w1, b1, w2, b2, palette, beta, alpha, c2w, focal,
     rgb, depth, mask, extra, normals = FusedTriplaneRender.apply(
         planes, w1, b1, w2, b2, palette, beta, alpha, c2w, focal, center, bbox,
         cfg, height, width, num_samples, noise_t, noise_u, extra_mode, cam_grad,
-        compute_normals, out)
+        compute_normals, out, planes_layout)
     extra = extra if extra_mode != _lib.EXTRA_NONE else None
     if compute_normals:
         return rgb, depth, mask, extra, normals

@@ -92,9 +92,40 @@ def all_gather_inplace(full, batch, group=None):
         raise ValueError('in-place all-gather needs batch %% world == 0 (got %d, %d)'
                          % (batch, world))
     a, b = shard_range(batch, world, rank)
-    for t in full:
-        dist.all_gather_into_tensor(t, t[a:b], group=group)
+    if dist.get_backend(group) == 'nccl':
+        # the three collectives as ONE NCCL group launch (one kernel, one ring/tree set-up):
+        # at 1.3 MB per rank they are latency-bound, three back-to-back launches cost ~3x
+        with dist._coalescing_manager(group=group, device=full[0].device, async_ops=False):
+            for t in full:
+                dist.all_gather_into_tensor(t, t[a:b], group=group)
+    else:
+        for t in full:
+            dist.all_gather_into_tensor(t, t[a:b], group=group)
     return full
+
+
+def all_reduce_grads(params, group=None, average=False):
+    """Sums (or averages) the ``.grad`` of ``params`` over the ranks with ONE all-reduce of a
+    flat bucket -- what nn.DataParallel's replica reduction does for the generator parameters
+    in the reference's GAN step (run.py:636-644,1044).  Parameters without a gradient
+    contribute zeros, so that every rank sends the same bucket layout."""
+    if not dist.is_initialized() or dist.get_world_size(group) == 1:
+        return
+    params = list(params)
+    flat = torch.cat([(p.grad if p.grad is not None else torch.zeros_like(p)).reshape(-1).float()
+                      for p in params])
+    dist.all_reduce(flat, group=group)
+    if average:
+        flat /= dist.get_world_size(group)
+    off = 0
+    for p in params:
+        n = p.numel()
+        g = flat[off:off + n].view_as(p).to(p.dtype)
+        if p.grad is None:
+            p.grad = g.clone()
+        else:
+            p.grad.copy_(g)
+        off += n
 
 
 def render_sharded(render_fn, batch_inputs, batch, gather=True, group=None, inplace=False,

@@ -54,6 +54,21 @@ def configure(new_args, new_dataset_config, samples_per_ray=None):
         depth_samples_per_ray = samples_per_ray
 
 
+_FRONTS = {}
+
+
+def enable_fused_synthesis(target_model, enabled=True):
+    """Makes ``render`` produce ``target_model``'s tri-planes with the sm_100a synthesis
+    kernels (generator.FusedGeneratorFront) for the calls inside their envelope: under
+    ``torch.no_grad()`` and without regulariser outputs.  Every other call keeps running the
+    reference module's own forward (it needs autograd through the synthesis network)."""
+    from .generator import FusedGeneratorFront
+    if enabled:
+        _FRONTS[id(target_model)] = FusedGeneratorFront(target_model)
+    else:
+        _FRONTS.pop(id(target_model), None)
+
+
 def _closure_vars(fn):
     out = {}
     for name, cell in zip(fn.__code__.co_freevars, fn.__closure__ or ()):
@@ -89,7 +104,7 @@ def extract_field(target_model, sampler):
     if isinstance(sampler, dict):
         f = sampler
         return (f['planes'], f.get('palette'), f['w1'], f['b1'], f['w2'],
-                f['b2'], f.get('beta'), f.get('alpha'))
+                f['b2'], f.get('beta'), f.get('alpha'))  # layout: f.get('planes_layout')
     cv = _closure_vars(sampler)
     for k in ('xy', 'xz', 'yz'):
         if cv.get(k) is None:
@@ -156,12 +171,18 @@ def render(target_model,
     if randomize:
         noise_t = torch.rand(B, height, width, S, device=dev)
 
-    model_outputs = target_model(None, model_input,
-                                 ['sampler'] + list(extra_model_outputs),
-                                 extra_model_inputs)
+    requests = ['sampler'] + list(extra_model_outputs)
+    front = _FRONTS.get(id(target_model))
+    if front is not None and front.supports(requests, extra_model_inputs):
+        # plane producer on sm_100a too (generator.FusedGeneratorFront; no_grad calls only)
+        model_outputs = front(None, model_input, requests, extra_model_inputs)
+    else:
+        model_outputs = target_model(None, model_input, requests, extra_model_inputs)
     sampler = model_outputs.pop('triplane', None) or model_outputs['sampler']
     model_outputs.pop('sampler', None)
     planes, palette, w1, b1, w2, b2, beta, alpha = extract_field(target_model, sampler)
+    layout = sampler.get('planes_layout', 'channel_first') if isinstance(sampler, dict) \
+        else 'channel_first'
 
     if randomize and fine:
         noise_u = torch.rand(B * height * width, S, device=dev)
@@ -181,7 +202,7 @@ def render(target_model,
         planes, w1, b1, w2, b2, palette, beta, alpha, tform_cam2world,
         focal_length, center, bbox, cfg, height, width, S, noise_t, noise_u,
         extra_mode, cam_grad=not force_no_cam_grad,
-        compute_normals=bool(compute_normals))
+        compute_normals=bool(compute_normals), planes_layout=layout)
     rgb, depth, mask, extra = out[:4]
     normals = out[4] if compute_normals else None
     return rgb, depth, mask, normals, extra, model_outputs

@@ -149,3 +149,27 @@ def test_step_buffers_are_released_with_the_graph(cuda_lib):
         assert torch.cuda.memory_allocated() - base < 1 << 20
     finally:
         gc.enable()
+
+
+def test_channel_last_planes_are_used_as_they_are(cuda_lib):
+    """planes_layout='channel_last' ([B,3,R,R,32], what synthesis.FusedSynthesis emits): same
+    image bit for bit as the channel-first call, gradient returned in the same layout."""
+    from nerf_from_image_b200.fused import RenderConfig, fused_render
+    B, H, W, S = 2, 24, 32, 16
+    scene, cams = Hh.make_case('p3d_bbox', batch=B, plane_res=64, device='cuda')
+    nt, nu = synthetic.make_noise(61, B, H, W, S, device='cuda')
+    cfg = RenderConfig(scene_range=scene['scene_range'], white_background=scene['white_background'])
+    common = (scene['w1'], scene['b1'], scene['w2'], scene['b2'], scene['palette'], scene['beta'],
+              scene['alpha'], cams['c2w'], cams['focal'], cams['center'], cams['bbox'], cfg, H, W, S,
+              nt, nu)
+    pf = scene['planes'].clone().requires_grad_()
+    pl = scene['planes'].permute(0, 1, 3, 4, 2).contiguous().requires_grad_()
+    a = fused_render(pf, *common)
+    b = fused_render(pl, *common, planes_layout='channel_last')
+    assert torch.equal(a[0], b[0]) and torch.equal(a[2], b[2])
+    wr, wm = _weights((B, H, W, 3), (B, H, W), 'cuda')
+    ga, = torch.autograd.grad((a[0] * wr).sum() + (a[2] * wm).sum(), pf)
+    gb, = torch.autograd.grad((b[0] * wr).sum() + (b[2] * wm).sum(), pl)
+    assert gb.shape == pl.shape
+    # (plane-gradient atomics are order-dependent: equal to rounding, not bitwise)
+    assert Hh.rel_l2(gb.permute(0, 1, 4, 2, 3), ga) < 1e-5

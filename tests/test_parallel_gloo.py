@@ -85,3 +85,33 @@ def test_sharded_render_equals_single_process(tmp_path, world, batch, inplace):
         assert torch.equal(rgb, ref['rgb'])
         assert torch.equal(depth, ref['depth'])
         assert torch.equal(mask, ref['mask'])
+
+
+def _grad_worker(rank, world, port, out_dir):
+    os.environ['MASTER_ADDR'] = '127.0.0.1'
+    os.environ['MASTER_PORT'] = str(port)
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    torch.manual_seed(0)
+    params = [torch.nn.Parameter(torch.zeros(3, 4)), torch.nn.Parameter(torch.zeros(5)),
+              torch.nn.Parameter(torch.zeros(1))]
+    params[0].grad = torch.full((3, 4), float(rank + 1))
+    params[1].grad = torch.arange(5.) * (rank + 1)
+    # params[2] has no gradient on rank 0 (a leaf the rank's shard did not touch)
+    if rank > 0:
+        params[2].grad = torch.tensor([10.0 * rank])
+    parallel.all_reduce_grads(params)
+    torch.save([p.grad for p in params], os.path.join(out_dir, 'g%d.pt' % rank))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_gradient_all_reduce(tmp_path):
+    """GAN generator step (BASELINE config 4): decoder / beta / alpha gradients of the shards
+    are summed with one bucketed all-reduce (run.py:636-644 DataParallel reduce)."""
+    world = 3
+    mp.spawn(_grad_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    for r in range(world):
+        g0, g1, g2 = torch.load(os.path.join(str(tmp_path), 'g%d.pt' % r))
+        assert torch.equal(g0, torch.full((3, 4), 6.0))
+        assert torch.equal(g1, torch.arange(5.) * 6)
+        assert torch.equal(g2, torch.tensor([30.0]))

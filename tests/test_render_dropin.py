@@ -29,7 +29,8 @@ def oracle_core(calls):
     """Stand-in for fused.fused_render with the same signature, on the CPU oracle."""
     def core(planes, w1, b1, w2, b2, palette, beta, alpha, c2w, focal, center, bbox, cfg,
              height, width, num_samples, noise_t=None, noise_u=None, extra_mode=0,
-             cam_grad=True, compute_normals=False, out=None):
+             cam_grad=True, compute_normals=False, out=None, planes_layout='channel_first'):
+        assert planes_layout == 'channel_first'   # the reference Generator's own planes
         calls.append(dict(planes=planes, cfg=cfg, extra_mode=extra_mode, cam_grad=cam_grad,
                           noise_t=noise_t, noise_u=noise_u))
         o = O.render_oracle(planes, w1, b1, w2, b2, palette, beta, alpha, c2w, focal, center,

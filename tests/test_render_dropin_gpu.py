@@ -114,3 +114,34 @@ def test_parallel_model_on_cuda(cuda_lib):
     cv = _closure_vars(mo['sampler'])
     joined = _join_planes(cv['xy'], cv['xz'], cv['yz'])
     assert joined.data_ptr() == cv['xy'].data_ptr() and joined.shape[1:3] == (3, 32)
+
+
+@pytest.mark.parametrize('input_kind', ['ws', 'z', 'w1'])
+def test_render_with_the_fused_plane_producer(cuda_lib, input_kind):
+    """w (or z) -> image entirely on the sm_100a kernels: ``enable_fused_synthesis`` routes the
+    no_grad calls through generator.FusedGeneratorFront (synthesis network on tcgen05, planes
+    channel-last into the render kernels); the reference render, eager fp32, is the yardstick."""
+    R, g, cams, ws, ref_render = _setup('p3d_car')
+    model_input = {'ws': ws, 'z': torch.randn(ws.shape[0], 512, device='cuda'),
+                   'w1': ws[:, :1].contiguous()}[input_kind]
+    a = (g, H, W, cams['c2w'], cams['focal'], None, cams['bbox'], model_input, S)
+    R.enable_fused_synthesis(g)
+    try:
+        with torch.no_grad():
+            torch.manual_seed(21)
+            ref = ref_render(*a, extra_model_outputs=['attention_values'])
+            s_ref = torch.cuda.get_rng_state()
+            torch.manual_seed(21)
+            got = R.render(*a, extra_model_outputs=['attention_values'])
+            s_got = torch.cuda.get_rng_state()
+        assert torch.equal(s_ref, s_got)
+        for i in (0, 1, 2):
+            assert _rel(got[i], ref[i]) < 1e-3, (i, _rel(got[i], ref[i]))
+        assert torch.equal(got[5]['attention_values'], ref[5]['attention_values'])
+        # a call that needs autograd through the synthesis network keeps the reference module
+        w = ws.clone().requires_grad_()
+        out = R.render(g, H, W, cams['c2w'], cams['focal'], None, cams['bbox'], w, S)
+        out[0].mean().backward()
+        assert w.grad is not None and w.grad.abs().sum() > 0
+    finally:
+        R.enable_fused_synthesis(g, False)

@@ -7,6 +7,7 @@ about 1e-6, the asserts use 5e-5."""
 import pytest
 import torch
 
+from fixtures import synthetic
 from oracle import reference_lift as RL
 from oracle import synthesis_oracle as SO
 from tests import helpers_synth as HS
@@ -35,38 +36,6 @@ def test_fixtures(cuda_lib, case):
     assert _rel(_cf(planes), img) < TOL, _rel(_cf(planes), img)
 
 
-def _random_params(seed, res, channels, w_dim, device):
-    """A parameter dict with the reference's naming, drawn directly (no module needed)."""
-    g = torch.Generator().manual_seed(seed)
-    rn = lambda *s: torch.randn(*s, generator=g).to(device)
-    p, layers = {}, {}
-    resolutions = [4 << i for i in range(len(channels))]
-    assert resolutions[-1] == res
-    for i, (r, c) in enumerate(zip(resolutions, channels)):
-        pre = 'b%d' % r
-        if i == 0:
-            p[pre + '.const'] = rn(c, 4, 4)
-        for name, cin in (('conv0', channels[i - 1] if i else None), ('conv1', c)):
-            if cin is None:
-                continue
-            key = pre + '.' + name
-            p[key + '.weight'] = rn(c, cin, 3, 3)
-            p[key + '.affine.weight'] = rn(cin, w_dim)
-            p[key + '.affine.bias'] = 1 + 0.1 * rn(cin)
-            p[key + '.bias'] = 0.2 * rn(c)
-            p[key + '.noise_strength'] = torch.tensor(0.07, device=device)
-            p[key + '.noise_const'] = rn(r, r)
-            layers[key] = dict(use_noise=True, up=(name == 'conv0'))
-        key = pre + '.torgb'
-        p[key + '.weight'] = rn(96, c, 1, 1)
-        p[key + '.affine.weight'] = rn(c, w_dim)
-        p[key + '.affine.bias'] = 1 + 0.1 * rn(c)
-        p[key + '.bias'] = 0.2 * rn(96)
-    p['meta'] = dict(img_resolution=res, img_channels=96, w_dim=w_dim, resolutions=resolutions,
-                     layers=layers)
-    return p
-
-
 @pytest.mark.parametrize('channels,batch', [((128, 128, 64, 32), 3), ((256, 128, 128, 96, 64), 2)])
 def test_against_the_oracle(cuda_lib, channels, batch):
     """Ragged tile grids (4x4 .. 64x64 positions, batch 3), N tiles of 128 / 96 / 64 / 32,
@@ -75,7 +44,7 @@ def test_against_the_oracle(cuda_lib, channels, batch):
     torch.backends.cuda.matmul.allow_tf32 = False
     torch.backends.cudnn.allow_tf32 = False
     res = 4 << (len(channels) - 1)
-    p = _random_params(5, res, channels, 512, 'cuda')
+    p = synthetic.make_synthesis_params(5, res, channels, 512, 'cuda')
     ws = torch.randn(batch, 2 * len(channels), 512, generator=torch.Generator().manual_seed(6)).cuda()
     with torch.no_grad():
         ref = SO.synthesis_forward(p, ws, HS.const_noises(p))
@@ -102,9 +71,15 @@ def test_full_size_against_the_reference_module(cuda_lib):
     with torch.no_grad():
         ref = net(ws)
         got = FusedSynthesis(net)(ws)
+        truth = net.double()(ws.double())     # the module's own arithmetic in float64
+        net.float()
     assert got.shape == (2, 3, 256, 256, 32)
-    err = _rel(_cf(got), ref)
-    assert err < TOL, err
+    # the stated bar, against the reference as it runs (eager fp32, cuDNN)
+    assert _rel(_cf(got), ref) < 1e-3, _rel(_cf(got), ref)
+    # and against ground truth: 3xTF32 with fp32 accumulation over K = 9 x 512 stays at 1e-5
+    # (measured r2: cuDNN's fp32 result is 1.4e-4 away from this kernel's)
+    e_ours, e_ref = _rel(_cf(got).double(), truth), _rel(ref.double(), truth)
+    assert e_ours < TOL, (e_ours, e_ref)
 
 
 @staged

@@ -18,6 +18,11 @@ for a in "$@"; do
              rm -f gpurun_out/r2_bwd.ncu-rep; tail -2 gpurun_out/r2_ncu_bwd.log | cut -c1-200;;
     ncu_list) timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 80 --csv --log-file gpurun_out/r2_launches.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-e2e > gpurun_out/r2_ncu_list.log 2>&1; tail -14 gpurun_out/r2_launches.csv | cut -c1-200;;
     synth) timeout 900 python -m pytest tests/test_synthesis_gpu.py -m gpu -q --maxfail=12 2>&1 | tail -40 > gpurun_out/r2_pytest_synth.log; cat gpurun_out/r2_pytest_synth.log;;
+    diag2) (timeout 300 python tools/grad_diag2.py p3d_plain; timeout 300 python tools/grad_diag2.py cub_ortho; timeout 300 python tools/grad_diag2.py p3d_bbox) > gpurun_out/r2_grad_diag2.txt 2>&1; cat gpurun_out/r2_grad_diag2.txt;;
+    tsynth) (timeout 400 python tools/time_synthesis.py 32 5; timeout 300 python tools/time_synthesis.py 4 5) > gpurun_out/r2_time_synthesis.txt 2>&1; cat gpurun_out/r2_time_synthesis.txt;;
+    ncu_synth) timeout 600 ncu --set full --clock-control none --import-source on -k regex:conv_tc_kernel -s 30 -c 3 -f -o gpurun_out/r2_synth python tools/time_synthesis.py 8 1 > gpurun_out/r2_ncu_synth.log 2>&1
+             ncu -i gpurun_out/r2_synth.ncu-rep --page raw --csv > gpurun_out/r2_synth_raw.csv 2>/dev/null
+             rm -f gpurun_out/r2_synth.ncu-rep; tail -2 gpurun_out/r2_ncu_synth.log | cut -c1-200;;
     diag) timeout 600 python tools/grad_diag.py > gpurun_out/r2_grad_diag.txt 2>&1; cat gpurun_out/r2_grad_diag.txt;;
     *) echo "unknown job $a";;
   esac
