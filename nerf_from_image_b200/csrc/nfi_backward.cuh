@@ -239,7 +239,8 @@ render_backward_simt(const nfi_render_params p, const nfi_render_grads g) {
       const float e = expf(-fabsf(nd) * fc.inv_beta);
       const float sg = (nd > 0.f) ? 1.f : ((nd < 0.f) ? -1.f : 0.f);
       // sigma = inv_alpha * keep * (0.5 + 0.5 sg (1 - e))
-      dOut[0] = dsig * (-(fc.inv_alpha * keep) * 0.5f * e * fc.inv_beta * (sg * sg));
+      // (analytic derivative also at nd == 0.0 exactly, see nfi_backward_pipe.cuh)
+      dOut[0] = dsig * (-(fc.inv_alpha * keep) * 0.5f * e * fc.inv_beta);
       acc_beta = fmaf(dsig, fc.inv_alpha * keep * (-0.5f * sg * e * fabsf(nd) * fc.inv_beta *
                                                    fc.inv_beta),
                       acc_beta);
@@ -376,6 +377,15 @@ render_backward_simt(const nfi_render_params p, const nfi_render_grads g) {
             make_float4(df[0], df[1], df[2], df[3]);
       }
       __syncwarp();
+      // debug trace of one ray (tools/grad_trace.py): mlp_mode bit 0x4000, ray id in noise_seed,
+      // buffer in p.normals: [n_total][8] scalars then [n_total][32] dL/d(feature)
+      if ((p.mlp_mode & 0x4000) && p.normals != nullptr && ray == (size_t)p.noise_seed && valid) {
+        float* q8 = p.normals + (size_t)i * 8;
+        q8[0] = z; q8[1] = sigma; q8[2] = w; q8[3] = T; q8[4] = dsig; q8[5] = dOut[0];
+        q8[6] = s_i; q8[7] = delta;
+        float* d32 = p.normals + (size_t)n_total * 8 + (size_t)i * 32;
+        for (int k = 0; k < 32; ++k) d32[k] = Fw[lane * kFRow + k];
+      }
       // ---- bilinear fetch, reverse: 8 lanes per texel, vector reductions
       {
         const int q = lane >> 3, kq = lane & 7;

@@ -346,6 +346,14 @@ render_backward_pipe(const nfi_render_params p, const nfi_render_grads g,
           tc::tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(&slot_free[sl]);
+          if ((p.mlp_mode & 0x4000) && p.normals != nullptr && ray == (size_t)p.noise_seed && valid) {
+            float* d32 = p.normals + (size_t)n_total * 8 + (size_t)i * 32;   // debug trace
+#pragma unroll
+            for (int k = 0; k < 16; ++k) {
+              d32[k] = __uint_as_float(ra[k]);
+              d32[16 + k] = __uint_as_float(rb[k]);
+            }
+          }
 #pragma unroll
           for (int c4 = 0; c4 < 4; ++c4) {
             *reinterpret_cast<float4*>(Dw + lane * 36 + 4 * c4) =
@@ -655,7 +663,11 @@ render_backward_pipe(const nfi_render_params p, const nfi_render_grads g,
           e_sdf = tc::ex2_approx(-fabsf(nd) * (fc.inv_beta * kLog2e));
           sg = (nd > 0.f) ? 1.f : ((nd < 0.f) ? -1.f : 0.f);
           sigma = fc.inv_alpha * ((0.5f + 0.5f * sg * (1.f - e_sdf)) * keep);
-          dsig_dout0 = -(fc.inv_alpha * keep) * 0.5f * e_sdf * fc.inv_beta * (sg * sg);
+          // d cdf / d(-d) = e / (2 beta), also AT the zero crossing: autograd of the reference's
+          // 0.5 + 0.5 sign(x)(1 - exp(-|x|/beta)) returns 0 for x == 0.0 exactly (sign(0) = 0),
+          // which fp32 does produce (out[0] = D2 + b2 cancels to 0.0 on a few samples per
+          // million: profiles/r2_grad_trace_exact_zero_sdf.txt); the analytic limit is used
+          dsig_dout0 = -(fc.inv_alpha * keep) * 0.5f * e_sdf * fc.inv_beta;
         } else {
           const float x = out[0] - 1.f;
           sigma = (x > 20.f ? x : log1pf(expf(x))) * keep;
@@ -731,6 +743,11 @@ render_backward_pipe(const nfi_render_params p, const nfi_render_grads g,
           dOut[1] = wr * 2.004f * sr * (1.f - sr);
           dOut[2] = wg2 * 2.004f * sg2 * (1.f - sg2);
           dOut[3] = wb * 2.004f * sb * (1.f - sb);
+        }
+        if ((p.mlp_mode & 0x4000) && p.normals != nullptr && ray == (size_t)p.noise_seed && valid) {
+          float* q8 = p.normals + (size_t)i * 8;   // debug trace, see nfi_backward.cuh
+          q8[0] = z; q8[1] = sigma; q8[2] = w; q8[3] = T; q8[4] = dsig; q8[5] = dOut[0];
+          q8[6] = s_i; q8[7] = delta;
         }
         // ---- hand dOut to the tensor core (hi/lo split)
         {

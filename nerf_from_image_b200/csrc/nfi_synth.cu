@@ -1,20 +1,25 @@
 // Tri-plane producer on sm_100a: the StyleGAN2 synthesis network of
 // /root/reference/models/stylegan.py:293-490 as tcgen05 implicit GEMMs (C ABI: include/nfi_synth.h).
 //
-// Data layout.  Activations are channel-last ([B,H,W,C] fp32) and exist as a PAIR of tensors,
-// hi = the value with its low 13 mantissa bits cleared (exactly a TF32 number) and lo = value - hi,
-// already multiplied by the style of the layer that will consume them (conv_modulated2d scales the
-// activations, not the weights: stylegan.py:131).  Weights are re-laid-out per call to
-// [tap][Cout][Cin] (K-major rows for the B operand), also as hi / lo.  One 3x3 tap of one 32-channel
-// block is then ONE TMA box per operand: a [1 x 8 x 16 x 32] box of the activation tensor at the
-// tile origin shifted by the tap (out-of-range rows / columns arrive as zeros = the conv padding)
-// is a 128-row x 128-byte SWIZZLE_128B tile = the K-major A operand of a 128 x BN x 32 UMMA; no
-// im2col buffer, no register staging.  D accumulates over taps x channel blocks in TMEM
-// (3xTF32: A_lo W_hi + A_hi W_lo + A_hi W_hi, fp32 accumulate).
+// Data layout.  Activations are channel-last ([B,H,W,C]) and exist as a PAIR of bf16 tensors,
+// hi = bf16(value) and lo = bf16(value - hi) (16 significant bits between them, 4 bytes per element
+// like the fp32 they stand for), already multiplied by the style of the layer that will consume
+// them (conv_modulated2d scales the activations, not the weights: stylegan.py:131).  Weights are
+// re-laid-out per call to [tap][Cout][Cin] (K-major rows for the B operand), also as hi / lo.  One
+// 3x3 tap of one 64-channel block is then ONE TMA box per operand: a [1 x 8 x 16 x 64] box of the
+// activation tensor at the tile origin shifted by the tap (out-of-range rows / columns / channels
+// arrive as zeros = the conv padding) is a 128-row x 128-byte SWIZZLE_128B tile = the K-major A
+// operand of a 128 x BN x 64 UMMA; no im2col buffer, no register staging.  D accumulates over taps
+// x channel blocks in TMEM as A_lo W_hi + A_hi W_lo + A_hi W_hi (kind::f16 on bf16 operands, fp32
+// accumulate): the dropped lo x lo term is 2^-18 of a product.  [The first version of this kernel
+// ran the same three products as 3xTF32 (kind::tf32, fp32 hi/lo pairs): twice the tensor time for
+// operands exact to 2^-22 -- but the result was no more accurate (1.35e-4 vs the fp64 network at
+// K = 9 x 512): the tensor core adds the products of one output into its fp32
+// accumulator with truncation, and that bias, which grows with K, dominates either way.]
 //
 // conv_tc_kernel (persistent, 192 threads):
 //   warp 0    TMA producer   : 4 boxes per k-iteration (A_hi, A_lo, W_hi, W_lo) into a 3-stage ring
-//   warp 1    MMA issuer     : 12 tcgen05.mma (kind::tf32, M128 N<=128 K8) per stage,
+//   warp 1    MMA issuer     : 12 tcgen05.mma (kind::f16 / bf16, M128 N<=128 K16) per stage,
 //                              tcgen05.commit -> stage free / accumulator full
 //   warps 2-5 epilogue       : tcgen05.ld of one of the two TMEM accumulators (the other is being
 //                              filled) -> fused epilogue -> global
@@ -27,6 +32,7 @@
 //            RGB  ToRGB: + bias + FIR-upsampled running image (stylegan.py:71-75,430-433); the
 //                 last block writes the tri-planes channel-last [B,3,R,R,32]
 #include <cuda.h>
+#include <cuda_bf16.h>
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdio.h>
@@ -40,7 +46,7 @@ namespace nfi {
 namespace synth {
 
 constexpr int kTileH = 8, kTileW = 16;  // 128 output positions = the UMMA M
-constexpr int kKBlock = 32;             // channels per k-iteration: 128-byte rows
+constexpr int kKBlock = 64;             // bf16 channels per k-iteration: 128-byte rows
 constexpr int kStages = 3;
 constexpr int kATile = 128 * 128;       // bytes of one A box
 constexpr int kConvThreads = 192;
@@ -54,11 +60,11 @@ struct ActEpilogue {   // shared by conv_tc_kernel (stride-1 layers) and fir_act
   const float* bias;   // [N]
   float gain;          // sqrt(2)
   const float* style_a;  // [B,N] style of consumer a (or nullptr: plain value)
-  float* a_hi;           // [B,H,W,N]
-  float* a_lo;
+  __nv_bfloat16* a_hi;   // [B,H,W,N]
+  __nv_bfloat16* a_lo;
   const float* style_b;  // second consumer or nullptr
-  float* b_hi;
-  float* b_lo;
+  __nv_bfloat16* b_hi;
+  __nv_bfloat16* b_lo;
 };
 
 struct ConvArgs {
@@ -114,6 +120,23 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tc::smem_u32(bar)) : "memory");
 }
 
+// Instruction descriptor, kind::f16 with bf16 operands, fp32 accumulate, A and B K-major:
+//   [4,6) c_format=1 (F32)  [7,10) a_format=1 (BF16)  [10,13) b_format=1  [17,23) N>>3  [24,29) M>>4
+__device__ __forceinline__ uint32_t umma_idesc_bf16(int M, int N) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+__device__ __forceinline__ void umma_bf16_ss(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc,
+                                             uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(d_tmem),
+      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+
 struct TileCoord {
   int phase, img, ty, tx, nt;
 };
@@ -134,12 +157,21 @@ __device__ __forceinline__ TileCoord decode_tile(const ConvArgs& a, int tile) {
   return t;
 }
 
-// value -> (value * style) as a TF32 hi / lo pair, 4 channels at a time
-__device__ __forceinline__ void store_split4(float* hi, float* lo, size_t idx, float4 v, float4 s) {
-  const float4 t = make_float4(v.x * s.x, v.y * s.y, v.z * s.z, v.w * s.w);
-  const float4 h = make_float4(tc::tf32_hi(t.x), tc::tf32_hi(t.y), tc::tf32_hi(t.z), tc::tf32_hi(t.w));
-  *reinterpret_cast<float4*>(hi + idx) = h;
-  *reinterpret_cast<float4*>(lo + idx) = make_float4(t.x - h.x, t.y - h.y, t.z - h.z, t.w - h.w);
+// t = hi + lo with hi = bf16(t), lo = bf16(t - hi)
+__device__ __forceinline__ void split_bf16(float t, __nv_bfloat16& hi, __nv_bfloat16& lo) {
+  hi = __float2bfloat16_rn(t);
+  lo = __float2bfloat16_rn(t - __bfloat162float(hi));
+}
+// value -> (value * style) as a bf16 hi / lo pair, 4 channels (8 bytes per tensor) at a time
+__device__ __forceinline__ void store_split4(__nv_bfloat16* hi, __nv_bfloat16* lo, size_t idx,
+                                             float4 v, float4 s) {
+  __align__(8) __nv_bfloat16 h[4], l[4];
+  split_bf16(v.x * s.x, h[0], l[0]);
+  split_bf16(v.y * s.y, h[1], l[1]);
+  split_bf16(v.z * s.z, h[2], l[2]);
+  split_bf16(v.w * s.w, h[3], l[3]);
+  *reinterpret_cast<uint2*>(hi + idx) = *reinterpret_cast<const uint2*>(h);
+  *reinterpret_cast<uint2*>(lo + idx) = *reinterpret_cast<const uint2*>(l);
 }
 __device__ __forceinline__ float lrelu(float x) { return x > 0.f ? x : 0.2f * x; }
 
@@ -201,7 +233,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
   __syncthreads();
   tc::tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
-  const int kblocks = a.C / kKBlock;
+  const int kblocks = (a.C + kKBlock - 1) / kKBlock;  // a partial last block is zero-filled by TMA
 
   if (warp == 0) {
     // ================================ TMA PRODUCER ================================
@@ -228,7 +260,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
     }
   } else if (warp == 1) {
     // ================================ MMA ISSUER ================================
-    const uint32_t idesc = tc::umma_idesc_tf32(128, a.BN);
+    const uint32_t idesc = umma_idesc_bf16(128, a.BN);
     const uint32_t smem_s = tc::smem_u32(smem);
     uint32_t st = 0, ph = 0, it = 0;
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
@@ -246,14 +278,14 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
           const uint64_t a_hi = tc::umma_desc_sw128(sb), a_lo = tc::umma_desc_sw128(sb + kATile);
           const uint64_t w_hi = tc::umma_desc_sw128(sb + 2 * kATile);
           const uint64_t w_lo = tc::umma_desc_sw128(sb + 2 * kATile + w_tile);
-          // small terms first; a K step of 8 tf32 = 32 bytes = +2 in the descriptor's address field
+          // small terms first; a K step of 16 bf16 = 32 bytes = +2 in the descriptor's address field
 #pragma unroll
           for (int ks = 0; ks < 4; ++ks)
-            tc::umma_tf32_ss(d_tmem, a_lo + 2 * ks, w_hi + 2 * ks, idesc, (k | ks) ? 1u : 0u);
+            umma_bf16_ss(d_tmem, a_lo + 2 * ks, w_hi + 2 * ks, idesc, (k | ks) ? 1u : 0u);
 #pragma unroll
-          for (int ks = 0; ks < 4; ++ks) tc::umma_tf32_ss(d_tmem, a_hi + 2 * ks, w_lo + 2 * ks, idesc, 1u);
+          for (int ks = 0; ks < 4; ++ks) umma_bf16_ss(d_tmem, a_hi + 2 * ks, w_lo + 2 * ks, idesc, 1u);
 #pragma unroll
-          for (int ks = 0; ks < 4; ++ks) tc::umma_tf32_ss(d_tmem, a_hi + 2 * ks, w_hi + 2 * ks, idesc, 1u);
+          for (int ks = 0; ks < 4; ++ks) umma_bf16_ss(d_tmem, a_hi + 2 * ks, w_hi + 2 * ks, idesc, 1u);
           tc::umma_commit(&empty[st]);
           if (k == iters - 1) tc::umma_commit(&acc_full[acc]);
         }
@@ -390,17 +422,15 @@ fir_act_kernel(const float* __restrict__ raw, int B, int OH, int OW, int N, ActE
 // weight [Cout,Cin,K,K] -> [K*K][Cout][Cin] hi / lo (K-major rows of the B operand) and
 // wsq[Cout][Cin] = sum over taps of W^2 (for the demodulation coefficients)
 __global__ void prep_weights_kernel(const float* __restrict__ w, int cout, int cin, int taps,
-                                    float* __restrict__ w_hi, float* __restrict__ w_lo,
-                                    float* __restrict__ wsq) {
+                                    __nv_bfloat16* __restrict__ w_hi,
+                                    __nv_bfloat16* __restrict__ w_lo, float* __restrict__ wsq) {
   const size_t total = (size_t)cout * cin;
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
        i += (size_t)gridDim.x * blockDim.x) {
     float sq = 0.f;
     for (int t = 0; t < taps; ++t) {
       const float v = w[i * taps + t];
-      const float h = tc::tf32_hi(v);
-      w_hi[(size_t)t * total + i] = h;
-      w_lo[(size_t)t * total + i] = v - h;
+      split_bf16(v, w_hi[(size_t)t * total + i], w_lo[(size_t)t * total + i]);
       sq = fmaf(v, v, sq);
     }
     if (wsq != nullptr) wsq[i] = sq;
@@ -442,14 +472,12 @@ __global__ void dcoef_kernel(const float* __restrict__ wsq, const float* __restr
 
 // b4.const [C,4,4] repeated over the batch (stylegan.py:422), scaled by conv1's style -> hi / lo
 __global__ void const_input_kernel(const float* __restrict__ cst, const float* __restrict__ style,
-                                   int B, int C, float* __restrict__ hi, float* __restrict__ lo) {
+                                   int B, int C, __nv_bfloat16* __restrict__ hi,
+                                   __nv_bfloat16* __restrict__ lo) {
   const int total = B * 16 * C;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
     const int c = i % C, p = (i / C) % 16, b = i / (16 * C);
-    const float t = cst[c * 16 + p] * style[b * C + c];
-    const float h = tc::tf32_hi(t);
-    hi[i] = h;
-    lo[i] = t - h;
+    split_bf16(cst[c * 16 + p] * style[b * C + c], hi[i], lo[i]);
   }
 }
 
@@ -471,23 +499,23 @@ static EncodeTiledFn encode_fn() {
   return fn;
 }
 
-// activation tensor [B,H,W,C] fp32 -> boxes of [1, 8, 16, 32]
-static bool make_act_map(CUtensorMap* tm, const float* base, int B, int H, int W, int C) {
+// activation tensor [B,H,W,C] bf16 -> boxes of [1, 8, 16, 64]
+static bool make_act_map(CUtensorMap* tm, const __nv_bfloat16* base, int B, int H, int W, int C) {
   const cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
-  const cuuint64_t strides[3] = {(cuuint64_t)C * 4, (cuuint64_t)W * C * 4, (cuuint64_t)H * W * C * 4};
+  const cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2};
   const cuuint32_t box[4] = {kKBlock, kTileW, kTileH, 1};
   const cuuint32_t es[4] = {1, 1, 1, 1};
-  return encode_fn()(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(base), dims, strides,
+  return encode_fn()(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<__nv_bfloat16*>(base), dims, strides,
                      box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
                      CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
-// weights [taps][N][C] fp32 -> boxes of [1, BN, 32]
-static bool make_w_map(CUtensorMap* tm, const float* base, int taps, int N, int C, int BN) {
+// weights [taps][N][C] bf16 -> boxes of [1, BN, 64]
+static bool make_w_map(CUtensorMap* tm, const __nv_bfloat16* base, int taps, int N, int C, int BN) {
   const cuuint64_t dims[3] = {(cuuint64_t)C, (cuuint64_t)N, (cuuint64_t)taps};
-  const cuuint64_t strides[2] = {(cuuint64_t)C * 4, (cuuint64_t)N * C * 4};
+  const cuuint64_t strides[2] = {(cuuint64_t)C * 2, (cuuint64_t)N * C * 2};
   const cuuint32_t box[3] = {kKBlock, (cuuint32_t)BN, 1};
   const cuuint32_t es[3] = {1, 1, 1};
-  return encode_fn()(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(base), dims, strides,
+  return encode_fn()(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<__nv_bfloat16*>(base), dims, strides,
                      box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
                      CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
@@ -500,8 +528,8 @@ static int pick_bn(int N) {
 }
 
 struct Pair {
-  float* hi;
-  float* lo;
+  __nv_bfloat16* hi;
+  __nv_bfloat16* lo;
 };
 
 #define NFI_SCUDA(expr)                                                              \
@@ -531,7 +559,7 @@ static int launch_conv(ConvArgs& a, Pair in, Pair wt, int w_taps, cudaStream_t s
     return 1;
   }
   a.BN = pick_bn(a.N);
-  if (a.BN == 0 || a.C % kKBlock != 0) {
+  if (a.BN == 0 || a.C % 8 != 0) {  // (TMA: row pitch a multiple of 16 bytes)
     snprintf(err, err_len, "synthesis conv: unsupported channel counts (Cin %d, Cout %d)", a.C, a.N);
     return 1;
   }
@@ -609,10 +637,10 @@ struct Bump {
     off += bytes;
     return p;
   }
-  Pair pair(size_t floats) {
+  Pair pair(size_t elems) {  // two bf16 tensors of `elems` elements
     Pair p;
-    p.hi = take(floats);
-    p.lo = take(floats);
+    p.hi = reinterpret_cast<__nv_bfloat16*>(take((elems + 1) / 2));
+    p.lo = reinterpret_cast<__nv_bfloat16*>(take((elems + 1) / 2));
     return p;
   }
 };

@@ -34,6 +34,8 @@ KERNEL_EVENTS = None
 # timing experiments: a float32 CUDA tensor of >= 16 elements the kernel fills with
 # per-phase cycle counts when mlp_mode has bit 0x1000 set
 DEBUG_BUF = None
+# backward trace of one ray (tools/grad_trace.py): ray index b*H*W + y*W + x, or None
+DEBUG_RAY = None
 
 
 def _ptr(t):
@@ -294,6 +296,9 @@ class FusedTriplaneRender(torch.autograd.Function):
             p.rgb, p.depth, p.mask = _ptr(rgb), _ptr(mask), _ptr(mask)  # unused
             p.extra = _ptr(extra)
             p.z_fine = _ptr(z_fine)
+            if DEBUG_RAY is not None and DEBUG_BUF is not None:
+                p.normals, p.noise_seed = _ptr(DEBUG_BUF), int(DEBUG_RAY)
+                p.mlp_mode = cfg.mlp_mode | 0x4000
             # the tensor-core backward keeps its two weight images here (64 KiB)
             ws = torch.empty(65536, dtype=torch.uint8, device=dev)
             p.workspace, p.workspace_bytes = _ptr(ws), 65536

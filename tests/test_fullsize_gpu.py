@@ -63,9 +63,13 @@ def test_backward_at_benchmark_geometry(cuda_lib, case, mode):
     assert Hh.rel_l2(rgb.detach(), ref_rgb) < 2e-4
     loss = (rgb * wr).sum() + (mask * wm).sum()
     got = torch.autograd.grad(loss, [sc2[n] for n in names] + [cm2[n] for n in cam_names])
-    tol = 2e-4 if mode == 1 else 3e-3     # fp32 SIMT / 3xTF32 tensor-core backward
+    # fp32 SIMT / 3xTF32 + MUFU tensor-core backward (measured r2: 3e-5 / 1.2e-4 .. 2.8e-4 on the
+    # plane gradient).  beta is ONE scalar: a sum over every sample of terms whose sign flips
+    # across the surface, so the per-sample 1e-4 shows up amplified by the cancellation
+    # (2e-3 on the bbox case; the fp32 reference autograd itself is at 1.3e-4 there).
     for n, a, b in zip(names + cam_names, got, gref):
         err = Hh.rel_l2(a.double(), b)
+        tol = 2e-4 if mode == 1 else (5e-3 if n == 'beta' else 1e-3)
         assert err < tol, (n, err)
 
 
