@@ -93,7 +93,20 @@ class SynthParams(ctypes.Structure):
     ]
 
 
-# every symbol include/nfi_render.h and include/nfi_synth.h declare (tests/test_abi.py checks the
+class SdfPointsParams(ctypes.Structure):
+    """struct nfi_sdf_points_params (include/nfi_heads.h)."""
+    _fields_ = [('batch', ctypes.c_int32), ('plane_res', ctypes.c_int32),
+                ('scene_range', ctypes.c_float), ('n_points', ctypes.c_int64)] + [
+        (n, ctypes.c_void_p) for n in ('planes', 'w1', 'b1', 'w2', 'b2', 'points', 'd', 'grad')]
+
+
+class SdfPointsGrads(ctypes.Structure):
+    """struct nfi_sdf_points_grads."""
+    _fields_ = [(n, ctypes.c_void_p) for n in (
+        'g_d', 'g_grad', 'grad_planes', 'grad_w1', 'grad_b1', 'grad_w2_row0', 'grad_b2_0')]
+
+
+# every symbol include/*.h declare (tests/test_abi.py checks the
 # header against this table and the table against the built library)
 EXPORTS = {
     'nfi_abi_version': (ctypes.c_int, []),
@@ -121,6 +134,9 @@ EXPORTS = {
     'nfi_fill_uniform': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int64, ctypes.c_uint64,
                                         ctypes.c_uint32, ctypes.c_int64, ctypes.c_void_p]),
     'nfi_sample_field': (ctypes.c_int, [ctypes.POINTER(SampleParams), ctypes.c_void_p]),
+    'nfi_sdf_points_forward': (ctypes.c_int, [ctypes.POINTER(SdfPointsParams), ctypes.c_void_p]),
+    'nfi_sdf_points_backward': (ctypes.c_int, [ctypes.POINTER(SdfPointsParams),
+                                               ctypes.POINTER(SdfPointsGrads), ctypes.c_void_p]),
     'nfi_synthesis_workspace_bytes': (ctypes.c_size_t, [ctypes.POINTER(SynthParams)]),
     'nfi_synthesis_forward': (ctypes.c_int, [ctypes.POINTER(SynthParams), ctypes.c_void_p]),
     'nfi_pose_to_matrix': (ctypes.c_int, [

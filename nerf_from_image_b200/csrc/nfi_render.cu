@@ -13,6 +13,8 @@
 #include "nfi_field_launch.h"
 #include "nfi_pipe_launch.h"
 #include "nfi_render.h"
+#include "nfi_heads.h"
+#include "nfi_heads_launch.h"
 #include "nfi_synth.h"
 #include "nfi_synth_launch.h"
 
@@ -556,6 +558,31 @@ int nfi_pose_to_matrix_backward(const float* z0, const float* t2, const float* s
   return nfi::launch_pose_to_matrix_backward(z0, t2, s, q, camera_flipped, batch, g_c2w, g_focal,
                                              g_z0, g_t2, g_s, g_q, (cudaStream_t)stream, g_err,
                                              sizeof(g_err));
+}
+
+static int check_sdf_points(const nfi_sdf_points_params* p) {
+  if (p == nullptr) return fail("params is NULL");
+  if (p->batch <= 0 || p->n_points <= 0 || p->plane_res < 2) return fail("empty batch / no points");
+  if (!p->planes || !p->w1 || !p->b1 || !p->w2 || !p->b2 || !p->points)
+    return fail("planes, decoder weights and points must be given");
+  if (!(p->scene_range > 0.f)) return fail("scene_range must be positive");
+  return 0;
+}
+
+int nfi_sdf_points_forward(const nfi_sdf_points_params* params, void* stream) {
+  if (const int rc = check_sdf_points(params)) return rc;
+  if (!params->d) return fail("output d must be given");
+  return nfi::heads::launch_forward(*params, (cudaStream_t)stream, g_err, sizeof(g_err));
+}
+
+int nfi_sdf_points_backward(const nfi_sdf_points_params* params, const nfi_sdf_points_grads* grads,
+                            void* stream) {
+  if (const int rc = check_sdf_points(params)) return rc;
+  if (grads == nullptr) return fail("grads is NULL");
+  if (!grads->g_d && !grads->g_grad) return fail("no upstream gradient");
+  if (grads->grad_w1 && (!grads->grad_b1 || !grads->grad_w2_row0 || !grads->grad_b2_0))
+    return fail("decoder gradients come as a set: grad_w1, grad_b1, grad_w2_row0, grad_b2_0");
+  return nfi::heads::launch_backward(*params, *grads, (cudaStream_t)stream, g_err, sizeof(g_err));
 }
 
 size_t nfi_synthesis_workspace_bytes(const nfi_synth_params* params) {

@@ -1,4 +1,4 @@
-/* Plain-C consumer of include/nfi_render.h and include/nfi_synth.h: proves the header is valid C99 (no C++-isms, no
+/* Plain-C consumer of include/nfi_render.h, nfi_synth.h and nfi_heads.h: proves the header is valid C99 (no C++-isms, no
  * torch types), that the structs have the layout the ctypes mirror assumes, and that the
  * library links and reports errors through return codes without a GPU.
  * Built and run by tests/test_abi.py::test_header_is_plain_c_and_links. */
@@ -7,6 +7,7 @@
 #include <string.h>
 
 #include "nfi_render.h"
+#include "nfi_heads.h"
 #include "nfi_synth.h"
 
 int main(void) {
@@ -28,6 +29,13 @@ int main(void) {
          sizeof(nfi_synth_layer), offsetof(nfi_synth_params, ws), offsetof(nfi_synth_params, conv1),
          offsetof(nfi_synth_params, planes));
   if (nfi_abi_version() != NFI_ABI_VERSION) return 10;
+  {
+    nfi_sdf_points_params hp;
+    nfi_sdf_points_grads hg;
+    memset(&hp, 0, sizeof hp);
+    memset(&hg, 0, sizeof hg);
+    if (nfi_sdf_points_forward(&hp, NULL) == 0 || nfi_sdf_points_backward(&hp, &hg, NULL) == 0) return 20;
+  }
   if (nfi_synthesis_forward(&y, NULL) == 0 || nfi_synthesis_workspace_bytes(&y) != 0) return 19;
   /* every entry point rejects an empty request with a non-zero code and a message */
   if (nfi_render_forward(&p, NULL) == 0 || strlen(nfi_last_error()) == 0) return 11;

@@ -9,10 +9,11 @@ from nerf_from_image_b200 import _lib
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 HEADER = os.path.join(ROOT, 'include', 'nfi_render.h')
 SYNTH_HEADER = os.path.join(ROOT, 'include', 'nfi_synth.h')
+HEADS_HEADER = os.path.join(ROOT, 'include', 'nfi_heads.h')
 
 
 def header_functions():
-    src = open(HEADER).read() + open(SYNTH_HEADER).read()
+    src = open(HEADER).read() + open(SYNTH_HEADER).read() + open(HEADS_HEADER).read()
     return re.findall(r'NFI_API\s+[\w\s\*]+?\b(nfi_\w+)\s*\(', src)
 
 
@@ -33,12 +34,14 @@ def test_library_exports_every_declared_symbol():
 
 def test_struct_layout_matches_header():
     """Field order / count of the ctypes mirrors vs the C structs."""
-    src = open(HEADER).read() + open(SYNTH_HEADER).read()
+    src = open(HEADER).read() + open(SYNTH_HEADER).read() + open(HEADS_HEADER).read()
     for cname, cls in (('nfi_render_params', _lib.RenderParams),
                        ('nfi_render_grads', _lib.RenderGrads),
                        ('nfi_sample_params', _lib.SampleParams),
                        ('nfi_synth_layer', _lib.SynthLayer),
-                       ('nfi_synth_params', _lib.SynthParams)):
+                       ('nfi_synth_params', _lib.SynthParams),
+                       ('nfi_sdf_points_params', _lib.SdfPointsParams),
+                       ('nfi_sdf_points_grads', _lib.SdfPointsGrads)):
         body = re.search(r'typedef struct %s \{(.*?)\} %s;' % (cname, cname), src, re.S).group(1)
         body = re.sub(r'/\*.*?\*/', '', body, flags=re.S)
         fields = [re.search(r'(\w+)\s*(?:\[\w+\])?$', d.strip()).group(1)

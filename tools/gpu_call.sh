@@ -23,6 +23,8 @@ for a in "$@"; do
     ncu_synth) timeout 600 ncu --set full --clock-control none --import-source on -k regex:conv_tc_kernel -s 30 -c 3 -f -o gpurun_out/r2_synth python tools/time_synthesis.py 8 1 > gpurun_out/r2_ncu_synth.log 2>&1
              ncu -i gpurun_out/r2_synth.ncu-rep --page raw --csv > gpurun_out/r2_synth_raw.csv 2>/dev/null
              rm -f gpurun_out/r2_synth.ncu-rep; tail -2 gpurun_out/r2_ncu_synth.log | cut -c1-200;;
+    list_synth) timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/r2_synth_launches.csv python tools/time_synthesis.py 32 1 > gpurun_out/r2_list_synth.log 2>&1; python tools/launch_table.py gpurun_out/r2_synth_launches.csv | tail -40;;
+    heads) timeout 600 python -m pytest tests/test_heads_gpu.py -m gpu -q --maxfail=12 2>&1 | tail -40 > gpurun_out/r2_pytest_heads.log; cat gpurun_out/r2_pytest_heads.log;;
     diag) timeout 600 python tools/grad_diag.py > gpurun_out/r2_grad_diag.txt 2>&1; cat gpurun_out/r2_grad_diag.txt;;
     *) echo "unknown job $a";;
   esac
