@@ -22,6 +22,53 @@ from . import _lib
 from .synthesis import FusedSynthesis
 
 SUPPORTED_OUTPUTS = ('sampler', 'attention_values')
+HEAD_OUTPUTS = ('sdf_eikonal_loss', 'sdf_distance_loss', 'total_variation_loss', 'entropy_loss')
+
+
+def resolve_ws(g, c):
+    """Model input -> ws [B,num_ws,512] (generator.py:423-446): z, w (broadcast from one row or
+    complete), (z, image) with the encoder, (z, label) with class embeddings."""
+    if g.use_encoder:
+        z, image = c
+        return g.mapping_network(z, g.emb(image)), z.shape[0]
+    label = None
+    if g.num_classes:
+        if isinstance(c, (list, tuple)):
+            c, label = c
+            assert len(c.shape) == 2
+            label = g.class_embedding(label)
+        else:
+            assert len(c.shape) == 3
+    if len(c.shape) == 3:
+        ws = (c.expand(-1, g.mapping_network.backbone.num_ws, -1).contiguous()
+              if c.shape[1] == 1 else c)
+    else:
+        ws = g.mapping_network(c, label)
+    return ws, c.shape[0]
+
+
+def resolve_palette(g, ws, request_model_outputs, model_inputs):
+    """(attention_values | None, w_synthesis) -- generator.py:452-468."""
+    if g.attention_values <= 0:
+        return None, ws
+    assert ws.shape[1] == 15
+    w_tex, w_synthesis = ws[:, 14], ws[:, :14]
+    if 'attention_values' in model_inputs:
+        attention_values = model_inputs['attention_values']
+    elif 'sampler' in request_model_outputs:
+        attention_values = g.texture_mapper(w_tex)
+        if 'attention_values_bias' in model_inputs:
+            attention_values = attention_values + model_inputs['attention_values_bias']
+    else:
+        attention_values = None
+    return attention_values, w_synthesis
+
+
+def decoder_weights(g):
+    """EFFECTIVE decoder weights (EqualizedLinear gains applied, differentiably)."""
+    l1, l2 = g.decoder.net[0], g.decoder.net[2]
+    return (l1.weight * l1.weight_gain, l1.bias * l1.bias_gain,
+            l2.weight * l2.weight_gain, l2.bias * l2.bias_gain)
 
 
 class FusedGeneratorFront:
@@ -43,52 +90,74 @@ class FusedGeneratorFront:
                                 'within %r)' % (SUPPORTED_OUTPUTS,))
         if g.use_viewdir and viewdir is not None:
             raise NotImplementedError('--use_viewdir is outside the fused path')
-        # ---- model input -> ws (generator.py:423-446)
-        if g.use_encoder:
-            z, image = c
-            batch = z.shape[0]
-            ws = g.mapping_network(z, g.emb(image))
-        else:
-            label = None
-            if g.num_classes:
-                if isinstance(c, (list, tuple)):
-                    c, label = c
-                    assert len(c.shape) == 2
-                    label = g.class_embedding(label)
-                else:
-                    assert len(c.shape) == 3
-            batch = c.shape[0]
-            if len(c.shape) == 3:
-                ws = (c.expand(-1, g.mapping_network.backbone.num_ws, -1).contiguous()
-                      if c.shape[1] == 1 else c)
-            else:
-                ws = g.mapping_network(c, label)
-        # ---- palette (generator.py:452-466)
-        attention_values = None
-        if g.attention_values > 0:
-            assert ws.shape[1] == 15
-            w_tex, w_synthesis = ws[:, 14], ws[:, :14]
-            if 'attention_values' in model_inputs:
-                attention_values = model_inputs['attention_values']
-            else:  # 'sampler' is always among the requests of render()
-                attention_values = g.texture_mapper(w_tex)
-                if 'attention_values_bias' in model_inputs:
-                    attention_values = attention_values + model_inputs['attention_values_bias']
-        else:
-            w_synthesis = ws
+        ws, batch = resolve_ws(g, c)
+        attention_values, w_synthesis = resolve_palette(g, ws, request_model_outputs, model_inputs)
         # ---- planes (generator.py:471-477), channel-last
         noise_mode = 'const' if model_inputs.get('freeze_noise') else 'random'
         planes_cl = self.synthesis(w_synthesis, noise_mode=noise_mode)
         assert planes_cl.shape[0] == batch
-        dec = g.decoder.net
-        l1, l2 = dec[0], dec[2]
+        w1, b1, w2, b2 = decoder_weights(g)
         out = {}
         if 'attention_values' in request_model_outputs:
             assert g.attention_values > 0
             out['attention_values'] = attention_values
         out['triplane'] = dict(
             planes=planes_cl, planes_layout='channel_last', palette=attention_values,
-            w1=l1.weight * l1.weight_gain, b1=l1.bias * l1.bias_gain,
-            w2=l2.weight * l2.weight_gain, b2=l2.bias * l2.bias_gain,
+            w1=w1, b1=b1, w2=w2, b2=b2,
             beta=getattr(g, 'beta', None), alpha=getattr(g, 'alpha', None))
+        return out
+
+
+class HeadsGeneratorFront:
+    """``Generator.forward`` with autograd intact and the regulariser heads on the fused point
+    evaluator (heads.regulariser_heads): the GAN generator step and the SDF pre-training loop
+    (run.py:824-868,1007-1044) request 'sdf_eikonal_loss' / 'sdf_distance_loss' /
+    'total_variation_loss' / 'entropy_loss' next to the render.  The synthesis network is the
+    reference module here (its autograd carries the gradients to the latents / parameters);
+    'path_length' (generator.py:484-499) is autograd through it, unchanged.  Same random draws in
+    the same order as the reference: synthesis noise, path-length noise, stratified points,
+    total-variation perturbation."""
+
+    def __init__(self, generator):
+        self.g = generator
+
+    @staticmethod
+    def supports(request_model_outputs, model_inputs):
+        return (any(o in HEAD_OUTPUTS for o in request_model_outputs)
+                and all(o in SUPPORTED_OUTPUTS + HEAD_OUTPUTS + ('path_length',)
+                        for o in request_model_outputs))
+
+    def __call__(self, viewdir, c, request_model_outputs=['sampler'], model_inputs={}):
+        import math
+        from .heads import regulariser_heads
+        g = self.g
+        if g.use_viewdir and viewdir is not None:
+            raise NotImplementedError('--use_viewdir is outside the fused path')
+        ws, batch = resolve_ws(g, c)
+        if 'path_length' in request_model_outputs:
+            assert torch.is_grad_enabled()
+            ws = ws.contiguous().requires_grad_()
+        attention_values, w_synthesis = resolve_palette(g, ws, request_model_outputs, model_inputs)
+        block_kwargs = {'noise_mode': 'const'} if model_inputs.get('freeze_noise') else {}
+        planes = g.synthesis_network(w_synthesis, **block_kwargs)
+        planes = planes.view(batch, 3, 32, planes.shape[-2], planes.shape[-1])
+        out = {}
+        if 'attention_values' in request_model_outputs:
+            assert g.attention_values > 0
+            out['attention_values'] = attention_values
+        if 'path_length' in request_model_outputs:   # generator.py:484-499
+            pl_noise = torch.randn_like(planes) / math.sqrt(planes.shape[-2] * planes.shape[-1])
+            target = (planes * pl_noise).sum()
+            if g.attention_values > 0:
+                target = target + (attention_values * torch.randn_like(attention_values)).sum()
+            pl_grad, = torch.autograd.grad(target, inputs=ws, create_graph=True)
+            out['path_length'] = pl_grad.square().sum(dim=-1).mean(dim=-1).sqrt()
+        w1, b1, w2, b2 = decoder_weights(g)
+        out.update(regulariser_heads(planes, w1, b1, w2, b2, getattr(g, 'beta', None),
+                                     g.scene_range, request_model_outputs, use_sdf=g.use_sdf,
+                                     training=g.training))
+        if 'sampler' in request_model_outputs:
+            out['triplane'] = dict(planes=planes, planes_layout='channel_first',
+                                   palette=attention_values, w1=w1, b1=b1, w2=w2, b2=b2,
+                                   beta=getattr(g, 'beta', None), alpha=getattr(g, 'alpha', None))
         return out

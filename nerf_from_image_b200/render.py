@@ -55,6 +55,19 @@ def configure(new_args, new_dataset_config, samples_per_ray=None):
 
 
 _FRONTS = {}
+_HEAD_FRONTS = {}
+
+
+def enable_fused_heads(target_model, enabled=True):
+    """Makes ``render`` (and ``ParallelModel``'s SDF pre-training branch) compute the regulariser
+    outputs of ``target_model`` -- 'sdf_eikonal_loss', 'sdf_distance_loss',
+    'total_variation_loss', 'entropy_loss' (generator.py:520-585) -- with the fused point
+    evaluator instead of the unfused decoder + double backward."""
+    from .generator import HeadsGeneratorFront
+    if enabled:
+        _HEAD_FRONTS[id(target_model)] = HeadsGeneratorFront(target_model)
+    else:
+        _HEAD_FRONTS.pop(id(target_model), None)
 
 
 def enable_fused_synthesis(target_model, enabled=True):
@@ -173,9 +186,13 @@ def render(target_model,
 
     requests = ['sampler'] + list(extra_model_outputs)
     front = _FRONTS.get(id(target_model))
+    hfront = _HEAD_FRONTS.get(id(target_model))
     if front is not None and front.supports(requests, extra_model_inputs):
         # plane producer on sm_100a too (generator.FusedGeneratorFront; no_grad calls only)
         model_outputs = front(None, model_input, requests, extra_model_inputs)
+    elif hfront is not None and hfront.supports(requests, extra_model_inputs):
+        # regulariser heads on the fused point evaluator (generator.HeadsGeneratorFront)
+        model_outputs = hfront(None, model_input, requests, extra_model_inputs)
     else:
         model_outputs = target_model(None, model_input, requests, extra_model_inputs)
     sampler = model_outputs.pop('triplane', None) or model_outputs['sampler']
@@ -239,8 +256,11 @@ class ParallelModel(nn.Module):
                 force_no_cam_grad=False):
         model_to_use = self.model_ema if use_ema else self.model
         if pretrain_sdf:
-            return model_to_use(None, c, request_model_outputs=[
-                'sdf_distance_loss', 'sdf_eikonal_loss'])
+            req = ['sdf_distance_loss', 'sdf_eikonal_loss']
+            hfront = _HEAD_FRONTS.get(id(model_to_use))
+            if hfront is not None:
+                return hfront(None, c, request_model_outputs=req)
+            return model_to_use(None, c, request_model_outputs=req)
         if encoder_output:
             return model_to_use.emb(c)
         res = int(self.resolution * res_multiplier)

@@ -145,3 +145,53 @@ def test_render_with_the_fused_plane_producer(cuda_lib, input_kind):
         assert w.grad is not None and w.grad.abs().sum() > 0
     finally:
         R.enable_fused_synthesis(g, False)
+
+
+def test_regulariser_outputs_through_render(cuda_lib):
+    """A GAN generator-step style call (run.py:1007-1044): render + the regulariser entries of
+    ``model_outputs``, gradients to the latents and the decoder.  With ``enable_fused_heads`` the
+    entries come from the fused point evaluator; the reference computes them with the unfused
+    decoder and a double backward."""
+    R, g, cams, ws, ref_render = _setup('p3d_car')
+    g.requires_grad_(True)
+    g.train()                                            # the eikonal head asserts self.training
+    extra = ['sdf_eikonal_loss', 'total_variation_loss', 'entropy_loss']
+    params = [g.decoder.net[0].weight, g.decoder.net[2].weight, g.beta]
+    res = []
+    try:
+        for fn, fused in ((ref_render, False), (R.render, True)):
+            R.enable_fused_heads(g, fused)
+            w = ws.clone().requires_grad_()
+            torch.manual_seed(31)
+            out = fn(g, H, W, cams['c2w'], cams['focal'], None, cams['bbox'], w, S,
+                     extra_model_outputs=list(extra))
+            mo = out[5]
+            loss = out[0].square().mean() + 0.1 * mo['sdf_eikonal_loss'].mean() \
+                + mo['total_variation_loss'].mean() + 0.01 * mo['entropy_loss'].mean()
+            grads = torch.autograd.grad(loss, [w] + params)
+            res.append((mo, grads, torch.cuda.get_rng_state()))
+    finally:
+        R.enable_fused_heads(g, False)
+        g.eval()
+        g.requires_grad_(False)
+    (mo_r, gr, s_r), (mo_f, gf, s_f) = res
+    assert torch.equal(s_r, s_f), 'RNG consumption differs'
+    for k in extra:
+        assert mo_f[k].shape == mo_r[k].shape
+        assert _rel(mo_f[k], mo_r[k]) < 1e-3, (k, _rel(mo_f[k], mo_r[k]))
+    for n, a, b in zip(('ws', 'w1', 'w2', 'beta'), gf, gr):
+        assert _rel(a, b) < 5e-3, (n, _rel(a, b))
+    # SDF pre-training branch of ParallelModel (run.py:598-600)
+    pm = R.ParallelModel(H, model=g, model_ema=g)
+    g.train()
+    try:
+        torch.manual_seed(3)
+        a = pm(None, None, None, None, ws, pretrain_sdf=True)
+        R.enable_fused_heads(g)
+        torch.manual_seed(3)
+        b = pm(None, None, None, None, ws, pretrain_sdf=True)
+    finally:
+        R.enable_fused_heads(g, False)
+        g.eval()
+    for k in ('sdf_distance_loss', 'sdf_eikonal_loss'):
+        assert _rel(b[k], a[k]) < 1e-3, k
