@@ -17,12 +17,14 @@
 // K = 9 x 512): the tensor core adds the products of one output into its fp32
 // accumulator with truncation, and that bias, which grows with K, dominates either way.]
 //
-// conv_tc_kernel (persistent, 192 threads):
+// conv_tc_kernel (persistent, 320 threads):
 //   warp 0    TMA producer   : 4 boxes per k-iteration (A_hi, A_lo, W_hi, W_lo) into a 3-stage ring
 //   warp 1    MMA issuer     : 12 tcgen05.mma (kind::f16 / bf16, M128 N<=128 K16) per stage,
 //                              tcgen05.commit -> stage free / accumulator full
-//   warps 2-5 epilogue       : tcgen05.ld of one of the two TMEM accumulators (the other is being
-//                              filled) -> fused epilogue -> global
+//   warps 2-9 epilogue       : tcgen05.ld of one of the two TMEM accumulators (the other is being
+//                              filled) -> fused epilogue -> global; two warps per TMEM lane quadrant,
+//                              half of the columns each (the ToRGB / ACT epilogues are bound by the
+//                              loads and stores in flight, not by arithmetic)
 // Epilogues: ACT  x*dcoef + noise + bias, *sqrt(2), leaky-relu 0.2, then for up to two consumers
 //                 (next conv, ToRGB) * their style -> hi / lo           (stylegan.py:137-142,349-356)
 //            RAW  plain store at (2a+py, 2b+px) of the (2H+1)x(2W+1) transposed-conv result; the
@@ -49,7 +51,7 @@ constexpr int kTileH = 8, kTileW = 16;  // 128 output positions = the UMMA M
 constexpr int kKBlock = 64;             // bf16 channels per k-iteration: 128-byte rows
 constexpr int kStages = 3;
 constexpr int kATile = 128 * 128;       // bytes of one A box
-constexpr int kConvThreads = 192;
+constexpr int kConvThreads = 320;      // TMA warp, MMA warp, 8 epilogue warps
 constexpr int kMaxPhases = 4, kMaxTaps = 9;
 
 enum { kModeRaw = 0, kModeAct = 1, kModeRgb = 2 };
@@ -220,7 +222,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
     }
     for (int i = 0; i < 2; ++i) {
       tc::mbar_init(&acc_full[i], 1);
-      tc::mbar_init(&acc_empty[i], 4);
+      tc::mbar_init(&acc_empty[i], 8);
     }
     tc::fence_mbar_init();
     prefetch_tmap(&tmAh);
@@ -296,6 +298,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
   } else {
     // ================================ EPILOGUE ================================
     const int q = warp & 3;                 // TMEM lane quadrant this warp may read
+    const int half = (warp - 2) >> 2;       // which half of the tile's columns this warp handles
+    const int chunks = a.BN / 32;           // 16-column chunks per half (BN = 32, 64, 96, 128)
     const int row = 32 * q + lane;          // tile row = position (row / 16, row % 16)
     const int py = row / kTileW, px = row % kTileW;
     uint32_t it = 0;
@@ -332,7 +336,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
           wsk[3] = wy1 * wx1;     psk[3] = ((size_t)t.img * hh + cy) * hw + cx;
         }
       }
-      for (int j = 0; j < a.BN / 16; ++j) {
+      for (int j = half * chunks; j < (half + 1) * chunks; ++j) {
         float v[16];
         tc::tmem_ld16(taddr + 16 * j, v);
         if (!valid) continue;
@@ -378,44 +382,57 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
 }
 
 // 4x4 FIR (outer([1,3,3,1]) / 16 = the reference's filter * gain 4, pad 1) over the (2H+1)x(2W+1)
-// transposed-conv result, then the ACT epilogue.  One thread per (position, 4 channels).
+// transposed-conv result, then the ACT epilogue.  One thread per (2x2 output block, 4 channels):
+// the block needs a 5x5 window of the raw tensor (25 loads for 4 outputs instead of 16 each), rows
+// filtered first (separable), then columns.
 __global__ void __launch_bounds__(256)
 fir_act_kernel(const float* __restrict__ raw, int B, int OH, int OW, int N, ActEpilogue e) {
   const int RH = OH + 1, RW = OW + 1;
-  const int groups = N >> 2;
-  const size_t total = (size_t)B * OH * OW * groups;
+  const int groups = N >> 2, bh = OH >> 1, bw = OW >> 1;
+  const size_t total = (size_t)B * bh * bw * groups;
   const float kf[4] = {0.25f, 0.75f, 0.75f, 0.25f};
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
        i += (size_t)gridDim.x * blockDim.x) {
     const int g = (int)(i % groups);
-    const size_t pos = i / groups;
-    const int v = (int)(pos % OW);
-    const int u = (int)((pos / OW) % OH);
-    const int img = (int)(pos / ((size_t)OW * OH));
-    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    const size_t blk = i / groups;
+    const int v0 = 2 * (int)(blk % bw);
+    const int u0 = 2 * (int)((blk / bw) % bh);
+    const int img = (int)(blk / ((size_t)bw * bh));
+    // horizontally filtered rows u0-1 .. u0+3 for the two output columns v0, v0+1
+    float4 h0[5], h1[5];
 #pragma unroll
-    for (int p = 0; p < 4; ++p) {
-      const int ry = u + p - 1;
-      if (ry < 0 || ry >= RH) continue;
-      float4 r = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int r = 0; r < 5; ++r) {
+      const int ry = u0 + r - 1;
+      float4 t[5];
 #pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        const int rx = v + q - 1;
-        if (rx < 0 || rx >= RW) continue;
-        const float4 t = __ldg(reinterpret_cast<const float4*>(
-            raw + (((size_t)img * RH + ry) * RW + rx) * N + 4 * g));
-        r.x = fmaf(kf[q], t.x, r.x);
-        r.y = fmaf(kf[q], t.y, r.y);
-        r.z = fmaf(kf[q], t.z, r.z);
-        r.w = fmaf(kf[q], t.w, r.w);
+      for (int c = 0; c < 5; ++c) {
+        const int rx = v0 + c - 1;
+        t[c] = (ry >= 0 && ry < RH && rx >= 0 && rx < RW)
+                   ? __ldg(reinterpret_cast<const float4*>(raw + (((size_t)img * RH + ry) * RW + rx) * N + 4 * g))
+                   : make_float4(0.f, 0.f, 0.f, 0.f);
       }
-      acc.x = fmaf(kf[p], r.x, acc.x);
-      acc.y = fmaf(kf[p], r.y, acc.y);
-      acc.z = fmaf(kf[p], r.z, acc.z);
-      acc.w = fmaf(kf[p], r.w, acc.w);
+#define NFI_H(cmp)                                                                              \
+  h0[r].cmp = fmaf(kf[3], t[3].cmp, fmaf(kf[2], t[2].cmp, fmaf(kf[1], t[1].cmp, kf[0] * t[0].cmp))); \
+  h1[r].cmp = fmaf(kf[3], t[4].cmp, fmaf(kf[2], t[3].cmp, fmaf(kf[1], t[2].cmp, kf[0] * t[1].cmp)));
+      NFI_H(x) NFI_H(y) NFI_H(z) NFI_H(w)
+#undef NFI_H
     }
-    const float noise = e.noise ? __ldg(e.noise + pos) : 0.f;
-    act_store4(e, img, pos, N, 4 * g, acc, noise);
+#pragma unroll
+    for (int du = 0; du < 2; ++du) {
+#pragma unroll
+      for (int dv = 0; dv < 2; ++dv) {
+        const float4* hh = dv ? h1 : h0;
+        float4 acc;
+#define NFI_V(cmp)                                                                  \
+  acc.cmp = fmaf(kf[3], hh[du + 3].cmp,                                             \
+                 fmaf(kf[2], hh[du + 2].cmp, fmaf(kf[1], hh[du + 1].cmp, kf[0] * hh[du].cmp)));
+        NFI_V(x) NFI_V(y) NFI_V(z) NFI_V(w)
+#undef NFI_V
+        const size_t pos = ((size_t)img * OH + (u0 + du)) * OW + (v0 + dv);
+        const float noise = e.noise ? __ldg(e.noise + pos) : 0.f;
+        act_store4(e, img, pos, N, 4 * g, acc, noise);
+      }
+    }
   }
 }
 
@@ -749,7 +766,7 @@ static int run(const nfi_synth_params& P, Bump& ws, cudaStream_t st, bool dry, c
         memset(&e, 0, sizeof(e));
         e.dcoef = dco0[i]; e.noise = P.conv0[i].noise; e.bias = P.conv0[i].bias; e.gain = sqrt2;
         e.style_a = style1[i]; e.a_hi = y.hi; e.a_lo = y.lo;
-        const size_t total = (size_t)B * res * res * (cout / 4);
+        const size_t total = (size_t)B * (res / 2) * (res / 2) * (cout / 4);
         unsigned grid = blocks(total, 256);
         if (grid > 148u * 16u) grid = 148u * 16u;
         fir_act_kernel<<<grid, 256, 0, st>>>(raw, B, res, res, cout, e);
