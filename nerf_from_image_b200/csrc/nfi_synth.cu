@@ -18,10 +18,10 @@
 // accumulator with truncation, and that bias, which grows with K, dominates either way.]
 //
 // conv_tc_kernel (persistent, 320 threads):
-//   warp 0    TMA producer   : 4 boxes per k-iteration (A_hi, A_lo, W_hi, W_lo) into a 3-stage ring
-//   warp 1    MMA issuer     : 12 tcgen05.mma (kind::f16 / bf16, M128 N<=128 K16) per stage,
+//   warp 0    TMA producer   : 4 boxes per k-iteration (A_hi, A_lo 32 KB each, W_hi, W_lo) into a 2-stage ring
+//   warp 1    MMA issuer     : 2 x 12 tcgen05.mma (kind::f16 / bf16, M128 N<=128 K16) per stage,
 //                              tcgen05.commit -> stage free / accumulator full
-//   warps 2-9 epilogue       : tcgen05.ld of one of the two TMEM accumulators (the other is being
+//   warps 2-9 epilogue       : tcgen05.ld of one of the two TMEM accumulator PAIRS (the other is being
 //                              filled) -> fused epilogue -> global; two warps per TMEM lane quadrant,
 //                              half of the columns each (the ToRGB / ACT epilogues are bound by the
 //                              loads and stores in flight, not by arithmetic)
@@ -47,10 +47,10 @@
 namespace nfi {
 namespace synth {
 
-constexpr int kTileH = 8, kTileW = 16;  // 128 output positions = the UMMA M
+constexpr int kTileH = 16, kTileW = 16;  // 256 output positions = two UMMA M = 128 halves (rows 0-7 / 8-15)
 constexpr int kKBlock = 64;             // bf16 channels per k-iteration: 128-byte rows
-constexpr int kStages = 3;
-constexpr int kATile = 128 * 128;       // bytes of one A box
+constexpr int kStages = 2;
+constexpr int kATile = 256 * 128;       // bytes of one A box: 256 rows of 128 bytes
 constexpr int kConvThreads = 320;      // TMA warp, MMA warp, 8 epilogue warps
 constexpr int kMaxPhases = 4, kMaxTaps = 9;
 
@@ -230,7 +230,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
     prefetch_tmap(&tmWh);
     prefetch_tmap(&tmWl);
   }
-  if (warp == 1) tc::tmem_alloc(tmem_ptr, 256);
+  if (warp == 1) tc::tmem_alloc(tmem_ptr, 512);
   tc::tc_fence_before();
   __syncthreads();
   tc::tc_fence_after();
@@ -270,24 +270,30 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
       const uint32_t acc = it & 1;
       tc::mbar_wait(&acc_empty[acc], ((it >> 1) & 1) ^ 1);
       tc::tc_fence_after();
-      const uint32_t d_tmem = tmem_base + acc * 128;
+      const uint32_t d_tmem = tmem_base + acc * 256;  // two 128-column accumulators: rows 0-127, 128-255
       const int iters = a.ph_taps[t.phase] * kblocks;
       for (int k = 0; k < iters; ++k) {
         tc::mbar_wait(&full[st], ph);
         tc::tc_fence_after();
         if (elect_one()) {
           const uint32_t sb = smem_s + st * stage_bytes;
-          const uint64_t a_hi = tc::umma_desc_sw128(sb), a_lo = tc::umma_desc_sw128(sb + kATile);
           const uint64_t w_hi = tc::umma_desc_sw128(sb + 2 * kATile);
           const uint64_t w_lo = tc::umma_desc_sw128(sb + 2 * kATile + w_tile);
-          // small terms first; a K step of 16 bf16 = 32 bytes = +2 in the descriptor's address field
+          // the W boxes of the stage serve both halves of the position tile
 #pragma unroll
-          for (int ks = 0; ks < 4; ++ks)
-            umma_bf16_ss(d_tmem, a_lo + 2 * ks, w_hi + 2 * ks, idesc, (k | ks) ? 1u : 0u);
+          for (int sub = 0; sub < 2; ++sub) {
+            const uint64_t a_hi = tc::umma_desc_sw128(sb + sub * (kATile / 2));
+            const uint64_t a_lo = tc::umma_desc_sw128(sb + kATile + sub * (kATile / 2));
+            const uint32_t d = d_tmem + sub * 128;
+            // small terms first; a K step of 16 bf16 = 32 bytes = +2 in the descriptor's address field
 #pragma unroll
-          for (int ks = 0; ks < 4; ++ks) umma_bf16_ss(d_tmem, a_hi + 2 * ks, w_lo + 2 * ks, idesc, 1u);
+            for (int ks = 0; ks < 4; ++ks)
+              umma_bf16_ss(d, a_lo + 2 * ks, w_hi + 2 * ks, idesc, (k | ks) ? 1u : 0u);
 #pragma unroll
-          for (int ks = 0; ks < 4; ++ks) umma_bf16_ss(d_tmem, a_hi + 2 * ks, w_hi + 2 * ks, idesc, 1u);
+            for (int ks = 0; ks < 4; ++ks) umma_bf16_ss(d, a_hi + 2 * ks, w_lo + 2 * ks, idesc, 1u);
+#pragma unroll
+            for (int ks = 0; ks < 4; ++ks) umma_bf16_ss(d, a_hi + 2 * ks, w_hi + 2 * ks, idesc, 1u);
+          }
           tc::umma_commit(&empty[st]);
           if (k == iters - 1) tc::umma_commit(&acc_full[acc]);
         }
@@ -300,18 +306,20 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
     const int q = warp & 3;                 // TMEM lane quadrant this warp may read
     const int half = (warp - 2) >> 2;       // which half of the tile's columns this warp handles
     const int chunks = a.BN / 32;           // 16-column chunks per half (BN = 32, 64, 96, 128)
-    const int row = 32 * q + lane;          // tile row = position (row / 16, row % 16)
+    const int row = 32 * q + lane;          // row of a half tile = position (row / 16, row % 16)
     const int py = row / kTileW, px = row % kTileW;
     uint32_t it = 0;
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
       const TileCoord t = decode_tile(a, tile);
       const uint32_t acc = it & 1;
-      const int y = t.ty * kTileH + py, x = t.tx * kTileW + px;
-      const bool valid = (y < a.ph_DH[t.phase]) && (x < a.ph_DW[t.phase]);
       const int n0 = t.nt * a.BN;
       tc::mbar_wait(&acc_full[acc], (it >> 1) & 1);
       tc::tc_fence_after();
-      const uint32_t taddr = tmem_base + acc * 128 + ((uint32_t)(32 * q) << 16);
+#pragma unroll 1
+      for (int sub = 0; sub < 2; ++sub) {
+      const int y = t.ty * kTileH + 8 * sub + py, x = t.tx * kTileW + px;
+      const bool valid = (y < a.ph_DH[t.phase]) && (x < a.ph_DW[t.phase]);
+      const uint32_t taddr = tmem_base + acc * 256 + sub * 128 + ((uint32_t)(32 * q) << 16);
       float noise = 0.f;
       size_t pos = 0;
       float wsk[4] = {0.f, 0.f, 0.f, 0.f};
@@ -371,6 +379,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
           }
         }
       }
+      }
       tc::tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&acc_empty[acc]);
@@ -378,7 +387,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
   }
   tc::tc_fence_before();
   __syncthreads();
-  if (warp == 1) tc::tmem_dealloc(tmem_base, 256);
+  if (warp == 1) tc::tmem_dealloc(tmem_base, 512);
 }
 
 // 4x4 FIR (outer([1,3,3,1]) / 16 = the reference's filter * gain 4, pad 1) over the (2H+1)x(2W+1)
@@ -516,7 +525,7 @@ static EncodeTiledFn encode_fn() {
   return fn;
 }
 
-// activation tensor [B,H,W,C] bf16 -> boxes of [1, 8, 16, 64]
+// activation tensor [B,H,W,C] bf16 -> boxes of [1, 16, 16, 64]
 static bool make_act_map(CUtensorMap* tm, const __nv_bfloat16* base, int B, int H, int W, int C) {
   const cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
   const cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2};
