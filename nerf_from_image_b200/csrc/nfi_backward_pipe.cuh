@@ -366,8 +366,13 @@ render_backward_pipe(const nfi_render_params p, const nfi_render_grads g,
         }
         __syncwarp();
         const ByteTaps& tp = cur;
+#ifdef NFI_BWD_NO_SCATTER   // timing experiment: D4 is read and dropped
+#pragma unroll 1
+        for (int gq = 0; gq < 0; ++gq) {
+#else
 #pragma unroll 1
         for (int gq = 0; gq < 8; ++gq) {
+#endif
           const int src = 4 * gq + q;
           const uint32_t in6 = CAM ? __shfl_sync(kFull, cur_in, src) : 0u;
           const float4 d4v = *reinterpret_cast<const float4*>(Dw + src * 36 + 4 * kq);
@@ -382,7 +387,11 @@ render_backward_pipe(const nfi_render_params p, const nfi_render_grads g,
             const uint32_t dy = (o & 2u) ? row_units : 0u;
             const float gx0 = 1.f - fx, gy0 = 1.f - fy;
             const float w00 = gx0 * gy0, w01 = fx * gy0, w10 = gx0 * fy, w11 = fx * fy;
+#ifdef NFI_BWD_NO_RED   // timing experiment: everything but the atomics themselves
+            if (false) {
+#else
             if (gplanes_b != nullptr) {
+#endif
               float* gp = gplanes_b;
               red_add_v4(gp + (size_t)a00 * 4, d4v.x * w00, d4v.y * w00, d4v.z * w00, d4v.w * w00);
               red_add_v4(gp + (size_t)(a00 + dx) * 4, d4v.x * w01, d4v.y * w01, d4v.z * w01,

@@ -7,7 +7,7 @@ for a in "$@"; do
     tests) timeout 1500 python -m pytest tests -m gpu -q --maxfail=12 2>&1 | tail -40 > gpurun_out/r2_pytest_gpu.log; cat gpurun_out/r2_pytest_gpu.log;;
     bench) timeout 400 python bench.py > gpurun_out/r2_bench.json 2> gpurun_out/r2_bench.err; cat gpurun_out/r2_bench.json; tail -3 gpurun_out/r2_bench.err;;
     ab) for l in $LIBDIR/libnfi_render.so $LIBDIR/libnfi_render_*.so; do NFI_LIB_PATH=$l timeout 120 python tools/ab_forward.py 32 10 2>&1 | grep -v Warn | tail -1; done > gpurun_out/r2_ab_forward.txt; cat gpurun_out/r2_ab_forward.txt;;
-    ab_bwd) for l in $LIBDIR/libnfi_render.so $LIBDIR/libnfi_render_*.so; do NFI_LIB_PATH=$l timeout 200 python tools/time_backward.py 32 cam 2>&1 | grep -v Warn; done > gpurun_out/r2_ab_backward.txt; cat gpurun_out/r2_ab_backward.txt;;
+    ab_bwd) for l in $LIBDIR/libnfi_render.so $LIBDIR/libnfi_render_*.so; do NFI_LIB_PATH=$l timeout 200 python tools/time_backward.py 32 cam 2>&1 | grep -v Warn; NFI_LIB_PATH=$l timeout 200 python tools/time_backward.py 32 2>&1 | grep -v Warn | tail -1; done > gpurun_out/r2_ab_backward.txt; cat gpurun_out/r2_ab_backward.txt;;
     ncu_fwd) timeout 600 ncu --set full --clock-control none --import-source on -k regex:render_forward_pipe -s 3 -c 1 -f -o gpurun_out/r2_fwd python tools/ab_forward.py 32 2 > gpurun_out/r2_ncu_fwd.log 2>&1
              ncu -i gpurun_out/r2_fwd.ncu-rep --page raw --csv > gpurun_out/r2_fwd_raw.csv 2>/dev/null
              ncu -i gpurun_out/r2_fwd.ncu-rep --page source --csv > gpurun_out/r2_fwd_src.csv 2>/dev/null
