@@ -433,6 +433,8 @@ class Bench:
             torch.cuda.empty_cache()
 
         fwd_bwd = self.fwd_bwd(sc, cams, nt, nu, cfg, H, W, S, gb) if not a.no_backward else None
+        pretrained = self.fixture_pretrained(B, H, W, S) if (world == 1 and not a.quick
+                                                             and not a.no_cpu_baseline) else None
         if rank != 0:
             return
         pk = peaks()
@@ -465,7 +467,7 @@ class Bench:
             'roofline': roofline, 'fwd_bwd': fwd_bwd, 'cpu_baseline': cpu_baseline,
             'torch_eager_gpu': eager, 'parity': parity, 'gathered_check': gathered,
             'collective_ms': coll_ms, 'render_from_channel_first_planes': cf,
-            'e2e_planes_from_host': e2e_planes,
+            'e2e_planes_from_host': e2e_planes, 'fixture_pretrained_generator': pretrained,
         }
         print(json.dumps(line))
 
@@ -559,6 +561,77 @@ class Bench:
                         'synthesis network and render on the sm_100a kernels (both random draws '
                         'made on the device like the reference), rgb/depth/mask D2H; wall clock '
                         'incl. synchronisation, max over ranks'}
+
+    def fixture_pretrained(self, B, H, W, S, steps=120):
+        """SURVEY.md section 8d's fixture, to show that `value` does not hinge on the analytic
+        scene: the reference Generator (seed 1234) SDF-pre-trained with the reference's own
+        objective (run.py:821-868: sdf_distance + 0.1 * sdf_eikonal, Adam 2.5e-3; `steps`
+        instead of 1000 steps, 4 latents each) -- its two losses computed by the fused point
+        evaluator (enable_fused_heads) -- then 32 latents -> planes (FusedSynthesis) -> render."""
+        from nerf_from_image_b200 import render as R
+        from nerf_from_image_b200.synthesis import FusedSynthesis
+        from oracle import reference_lift as RL  # availability probe + module import only
+        if not RL.available():
+            return {'unavailable': 'reference files not staged (tools/stage_reference.py)'}
+        try:
+            import types
+            dev = self.dev
+            syn = self.synthetic
+            ds = syn.DATASET_CONFIGS[CFG['dataset']]
+            _, generator = RL._import_reference()
+            torch.manual_seed(1234)
+            g = generator.Generator(512, ds['scene_range'], attention_values=CFG['attention_values'],
+                                    use_sdf=True, disable_stylegan_noise=True).to(dev).train()
+            R.configure(types.SimpleNamespace(use_viewdir=False, use_sdf=True,
+                                              attention_values=CFG['attention_values'],
+                                              fine_sampling=True, mlp_mode=self.args.mlp_mode),
+                        {'scene_range': ds['scene_range'], 'white_background': ds['white_background']})
+            R.enable_fused_heads(g)
+            pm = R.ParallelModel(H, model=g, model_ema=g)
+            opt = torch.optim.Adam(g.parameters(), lr=2.5e-3)
+            t0 = time.perf_counter()
+            first = last = None
+            for i in range(steps):
+                losses = pm(None, None, None, None, c=torch.randn(4, 512, device=dev), pretrain_sdf=True)
+                loss = losses['sdf_distance_loss'].mean() + 0.1 * losses['sdf_eikonal_loss'].mean()
+                loss.backward()
+                opt.step()
+                opt.zero_grad(set_to_none=True)
+                if i == 0:
+                    first = loss.item()
+                last = loss.item() if i == steps - 1 else last
+            torch.cuda.synchronize()
+            train_s = time.perf_counter() - t0
+            R.enable_fused_heads(g, False)
+            g.eval().requires_grad_(False)
+            cams = syn.make_cameras(4321, B, radius=ds['radius'], device=dev)
+            cfg = self.fused.RenderConfig(scene_range=ds['scene_range'], white_background=False,
+                                          attention_values=CFG['attention_values'],
+                                          mlp_mode=self.args.mlp_mode)
+            with torch.no_grad():
+                ws = g.mapping_network(torch.randn(B, 512, device=dev), None)
+                planes = FusedSynthesis(g.synthesis_network)(ws[:, :14])
+                palette = g.texture_mapper(ws[:, 14])
+                l1, l2 = g.decoder.net[0], g.decoder.net[2]
+                w = (l1.weight * l1.weight_gain, l1.bias * l1.bias_gain, l2.weight * l2.weight_gain,
+                     l2.bias * l2.bias_gain)
+                nt = torch.rand(B, H, W, S, device=dev)
+                nu = torch.rand(B * H * W, S, device=dev)
+                fn = lambda: self.fused.fused_render(planes, *w, palette, g.beta, g.alpha, cams['c2w'],
+                                                     cams['focal'], None, None, cfg, H, W, S, nt, nu,
+                                                     planes_layout='channel_last')
+                ms = self.timed(fn, 10, 3)
+                mask = fn()[2].mean().item()
+            del g, opt, planes
+            torch.cuda.empty_cache()
+            return {'value': B * H * W / (ms * 1e-3), 'unit': UNIT, 'ms_per_step': ms,
+                    'mask_mean': mask, 'pretrain_steps': steps, 'pretrain_seconds': train_s,
+                    'pretrain_loss_first_last': [first, last],
+                    'what': 'render of %d images whose planes come from the SDF-pre-trained reference '
+                            'Generator through FusedSynthesis (losses of the pre-training from the '
+                            'fused point evaluator); same kernel, same geometry as `value`' % B}
+        except Exception as exc:
+            return {'unavailable': repr(exc)[:200]}
 
     def e2e_planes_from_host(self, sc, cams, cfg, B, gb, H, W, S):
         """Round 1's end-to-end figure, kept for continuity: PLANES from the host (805 MB per

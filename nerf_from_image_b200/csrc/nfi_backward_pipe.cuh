@@ -382,9 +382,9 @@ render_backward_pipe(const nfi_render_params p, const nfi_render_grads g,
             const uint32_t o = __shfl_sync(kFull, tp.o[pl], src);
             const float fx = __shfl_sync(kFull, tp.fx[pl], src);
             const float fy = __shfl_sync(kFull, tp.fy[pl], src);
-            const uint32_t a00 = (o & 0xFFFFFFF8u) | (uint32_t)kq;
-            const uint32_t dx = (o & 1u) << 3;
-            const uint32_t dy = (o & 2u) ? row_units : 0u;
+            const uint32_t a00 = o | (uint32_t)kq;   // nw texel clamped to R-2: all four taps exist
+            const uint32_t dx = 8u;
+            const uint32_t dy = row_units;
             const float gx0 = 1.f - fx, gy0 = 1.f - fy;
             const float w00 = gx0 * gy0, w01 = fx * gy0, w10 = gx0 * fy, w11 = fx * fy;
 #ifdef NFI_BWD_NO_RED   // timing experiment: everything but the atomics themselves

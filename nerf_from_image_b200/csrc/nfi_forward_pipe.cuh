@@ -25,16 +25,17 @@
 //   TMEM    : three slots of 160 columns: [0,64) D1 then H_lo, [64,128) H_hi,
 //             [128,144) D2;  MMA1 --d1_full--> activation --h_ready--> MMA2
 //             --d2_full--> shading --slot_free--> MMA1
-//   softplus: one MUFU (ex2) per hidden unit, log1p is a degree-8 polynomial on
-//             the FMA pipe evaluated for 8 unit pairs side by side (the chains are
-//             4-cycle dependent FFMA2s); log2(e) is folded into W1/b1 by
-//             prep_weight_image;
+//   softplus: ln2 * (max(x', 0) + lg2(1 + 2^-|x'|)) with x' = x log2 e: two MUFU ops (ex2, lg2)
+//             per hidden unit, 8 unit pairs side by side; log2(e) is folded into W1/b1 by
+//             prep_weight_image (a degree-8 FMA-pipe log1p instead of lg2 was measured slower:
+//             DESIGN.md section 5);
 //   resample: the S uniforms of a ray are sorted by a bitonic network across the
 //             warp (2 per lane) and pushed through the inverse CDF with shuffle
 //             binary searches: one warp-pass per ray instead of a serial per-thread
 //             walk (run.py:259-281, lib/nerf_utils.py:183-222).
-// What bounds the kernel after this is the L2 -> SM fill bandwidth of the gather
-// (12 texel lines of 128 bytes per point).
+// What bounds the kernel after this: the L1 data pipe (12 texel lines of 128 bytes per point plus
+// the A-tile stores) at 65 %, issue slots at 55 %, and a consumer chain that alone needs two
+// thirds of a step.
 #pragma once
 #include <type_traits>
 

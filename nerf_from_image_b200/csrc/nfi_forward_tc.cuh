@@ -326,9 +326,14 @@ __device__ __forceinline__ void gather_to_tiles_deep(const float* __restrict__ p
 // widen (one IMAD.WIDE.U32 per address: x16 + base).
 // ---------------------------------------------------------------------------
 struct ByteTaps {
-  uint32_t o[3];  // offset of the nw texel in 16-byte units | (x+1 < R) | (y+1 < R) << 1
+  uint32_t o[3];  // offset of the nw texel in 16-byte units
   float fx[3], fy[3];
 };
+// The nw texel is clamped to R-2, so that all four taps always exist at fixed offsets (+128 B, +one
+// row): at the far edge the fraction becomes 1 instead of 0 on the next cell, the interpolated value
+// is the same bit for bit (0 * finite + 1 * v), and the serving lanes need two address computations
+// per plane instead of four (round 1 carried two "neighbour exists" flag bits: 8.75 -> 8.66 ms,
+// profiles/r2_ab_forward_fixed_offset_taps.txt).
 __device__ __forceinline__ void byte_taps(float gx, float gy, int R, uint32_t plane_units,
                                           uint32_t& o, float& fx, float& fy) {
   const float m = (float)(R - 1);
@@ -336,18 +341,23 @@ __device__ __forceinline__ void byte_taps(float gx, float gy, int R, uint32_t pl
   float iy = (gy + 1.f) * 0.5f * m;
   ix = fminf(m, fmaxf(ix, 0.f));
   iy = fminf(m, fmaxf(iy, 0.f));
-  const float x0 = floorf(ix), y0 = floorf(iy);
+  const float x0 = fminf(floorf(ix), m - 1.f), y0 = fminf(floorf(iy), m - 1.f);
   fx = ix - x0;
   fy = iy - y0;
-  const int xi = (int)x0, yi = (int)y0;
-  o = plane_units + (uint32_t)(yi * R + xi) * 8u + ((xi + 1 < R) ? 1u : 0u) +
-      ((yi + 1 < R) ? 2u : 0u);
+  o = plane_units + (uint32_t)((int)y0 * R + (int)x0) * 8u;
 }
 // base + 16 * off as ONE IMAD.WIDE.U32 (a plain 64-bit pointer add costs two)
 __device__ __forceinline__ const float4* texel_ptr(const unsigned char* base, uint32_t off16) {
   uint64_t r;
   asm("mad.wide.u32 %0, %1, 16, %2;" : "=l"(r) : "r"(off16), "l"(base));
   return reinterpret_cast<const float4*>(r);
+}
+__device__ __forceinline__ float4 ldg_nc_volatile_next(const float4* p) {  // the texel one to the east
+  float4 r;
+  asm volatile("ld.global.nc.v4.f32 {%0, %1, %2, %3}, [%4+128];"
+               : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w)
+               : "l"(p));
+  return r;
 }
 __device__ __forceinline__ void gather_to_tiles_lean(const unsigned char* __restrict__ planes_b,
                                                      int R, const ByteTaps& tp,
@@ -365,14 +375,13 @@ __device__ __forceinline__ void gather_to_tiles_lean(const unsigned char* __rest
       const uint32_t o = __shfl_sync(kFull, tp.o[pl], src);
       fx[pl] = __shfl_sync(kFull, tp.fx[pl], src);
       fy[pl] = __shfl_sync(kFull, tp.fy[pl], src);
-      const uint32_t a00 = (o & 0xFFFFFFF8u) | (uint32_t)k;
-      const uint32_t dx = (o & 1u) << 3;
-      const uint32_t dy = (o & 2u) ? row_units : 0u;
-      const uint32_t a10 = a00 + dy;
-      v[4 * pl + 0] = ldg_nc_volatile(texel_ptr(planes_b, a00));
-      v[4 * pl + 1] = ldg_nc_volatile(texel_ptr(planes_b, a00 + dx));
-      v[4 * pl + 2] = ldg_nc_volatile(texel_ptr(planes_b, a10));
-      v[4 * pl + 3] = ldg_nc_volatile(texel_ptr(planes_b, a10 + dx));
+      const uint32_t a00 = o | (uint32_t)k;
+      const float4* p0 = texel_ptr(planes_b, a00);
+      const float4* p1 = texel_ptr(planes_b, a00 + row_units);
+      v[4 * pl + 0] = ldg_nc_volatile(p0);
+      v[4 * pl + 1] = ldg_nc_volatile_next(p0);
+      v[4 * pl + 2] = ldg_nc_volatile(p1);
+      v[4 * pl + 3] = ldg_nc_volatile_next(p1);
     }
     float2 lo = make_float2(0.f, 0.f), hi = make_float2(0.f, 0.f);
 #pragma unroll
