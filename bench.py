@@ -326,12 +326,13 @@ class Bench:
                                       mlp_mode=self.args.mlp_mode)
         return sc, cams, nt, nu, cfg
 
-    def render(self, sc, cams, nt, nu, cfg, H, W, S, out=None, layout='channel_last', **leaves):
+    def render(self, sc, cams, nt, nu, cfg, H, W, S, out=None, layout='channel_last', peers=None,
+               **leaves):
         g = lambda k: leaves.get(k, sc[k] if k in sc else cams[k])
         return self.fused.fused_render(
             g('planes'), g('w1'), g('b1'), g('w2'), g('b2'), g('palette'), g('beta'), g('alpha'),
             g('c2w'), cams['focal'], None, None, cfg, H, W, S, nt, nu, out=out,
-            planes_layout=layout)
+            planes_layout=layout, peers=peers)
 
     # -------------------------------------------------------------- config 2
     def config2(self):
@@ -350,23 +351,34 @@ class Bench:
         kernel_events = []
         gather_events = []
 
+        peer_ex = (parallel.PeerExchange(gb, H, W, dev) if (world > 1 and a.exchange == 'peer')
+                   else None)
+
         def step(time_kernel=False):
             with torch.no_grad():
                 if time_kernel:
                     fused.KERNEL_EVENTS = kernel_events
-                out = full = None
-                if world > 1:
+                out = full = peers = None
+                if peer_ex is not None:
+                    # the exchange fused into the kernel: tiles stored into every rank's buffers
+                    # over NVLink (symmetric memory), one device-side barrier, no collective call
+                    full, out, peers = peer_ex.begin()
+                elif world > 1:
                     # the path's one exchange step, in place: the kernel writes this rank's tiles
                     # into its slice of the full-batch buffers, one NCCL launch all-gathers them
                     full = parallel.gathered_buffers(gb, H, W, dev)
                     out = parallel.shard_views(full, gb, world, rank)
-                res = self.render(sc, cams, nt, nu, cfg, H, W, S, out=out)
+                res = self.render(sc, cams, nt, nu, cfg, H, W, S, out=out, peers=peers)
                 fused.KERNEL_EVENTS = None
                 if world > 1:
                     if time_kernel:
                         g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                         g0.record()
-                    res = parallel.all_gather_inplace(full, gb)
+                    if peer_ex is not None:
+                        peer_ex.finish()
+                        res = full
+                    else:
+                        res = parallel.all_gather_inplace(full, gb)
                     if time_kernel:
                         g1.record()
                         gather_events.append((g0, g1))
@@ -466,7 +478,8 @@ class Bench:
             'gpu_launches': 2 * a.steps,
             'roofline': roofline, 'fwd_bwd': fwd_bwd, 'cpu_baseline': cpu_baseline,
             'torch_eager_gpu': eager, 'parity': parity, 'gathered_check': gathered,
-            'collective_ms': coll_ms, 'render_from_channel_first_planes': cf,
+            'collective_ms': coll_ms, 'exchange': (a.exchange if world > 1 else None),
+            'render_from_channel_first_planes': cf,
             'e2e_planes_from_host': e2e_planes, 'fixture_pretrained_generator': pretrained,
         }
         print(json.dumps(line))
@@ -839,6 +852,8 @@ def main():
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
     ap.add_argument('--config', type=int, default=2, choices=[2, 3, 4, 5])
     ap.add_argument('--scaling', default='weak', choices=['weak', 'strong'])
+    ap.add_argument('--exchange', default='nccl', choices=['nccl', 'peer'],
+                    help='N > 1: in-place NCCL all-gather, or stores into the peers\' buffers from the kernel')
     ap.add_argument('--batch', type=int, default=None)
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-e2e', action='store_true')

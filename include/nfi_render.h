@@ -35,7 +35,7 @@
 extern "C" {
 #endif
 
-#define NFI_ABI_VERSION 3
+#define NFI_ABI_VERSION 4
 
 #if defined(__GNUC__)
 #define NFI_API __attribute__((visibility("default")))
@@ -46,6 +46,7 @@ extern "C" {
 #define NFI_PLANE_CHANNELS 32 /* TriplanarDecoder(32, .)  models/generator.py:383 */
 #define NFI_HIDDEN 64         /* hidden_dim             models/generator.py:293 */
 #define NFI_MAX_ATTENTION 15  /* decoder outputs 1+A, padded to <= 16 */
+#define NFI_MAX_PEERS 7       /* other GPUs of one NVSwitch domain */
 
 /* what the 5th output of render() carries (run.py:227-257,337-338) */
 enum nfi_extra_mode {
@@ -124,6 +125,17 @@ typedef struct nfi_render_params {
   void *workspace;        /* >= nfi_render_workspace_bytes(params) */
   size_t workspace_bytes;
   uint64_t noise_seed;    /* NFI_NOISE_PHILOX */
+  /* ---- multi-GPU exchange fused into the render (ABI 4; nfi_render_forward, pipelined kernel) ----
+   * The render's last step in the reference's multi-GPU form is the gather of every replica's
+   * rgb / depth / mask tiles (nn.DataParallel, run.py:636-644).  With n_peers > 0 the kernel
+   * stores each ray's outputs not only to rgb / depth / mask above but also, through NVLink peer
+   * mappings, to the same ray of peer_*[q] for q < n_peers: THIS rank's slice inside peer q's
+   * full-batch buffers (symmetric memory).  No collective call remains, only a barrier. */
+  int32_t n_peers;        /* 0 .. NFI_MAX_PEERS */
+  int32_t peer_reserved;
+  float *peer_rgb[7];     /* [B,H,W,3] slices in the peers' address spaces */
+  float *peer_depth[7];   /* [B,H,W] */
+  float *peer_mask[7];    /* [B,H,W] */
 } nfi_render_params;
 
 /* Upstream gradients in, parameter gradients out (all device pointers).

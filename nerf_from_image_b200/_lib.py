@@ -16,7 +16,8 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get('NFI_LIB_PATH') or os.path.join(_HERE, 'csrc', 'libnfi_render.so')
 
 c_float_p = ctypes.POINTER(ctypes.c_float)
-ABI_VERSION = 3  # NFI_ABI_VERSION of include/nfi_render.h
+ABI_VERSION = 4  # NFI_ABI_VERSION of include/nfi_render.h
+MAX_PEERS = 7
 
 EXTRA_NONE, EXTRA_COORDS, EXTRA_SEMANTICS = 0, 1, 2
 NOISE_DETERMINISTIC, NOISE_EXPLICIT, NOISE_PHILOX = 0, 1, 2
@@ -46,6 +47,9 @@ class RenderParams(ctypes.Structure):
         ('normals', ctypes.c_void_p), ('z_fine', ctypes.c_void_p),
         ('workspace', ctypes.c_void_p), ('workspace_bytes', ctypes.c_size_t),
         ('noise_seed', ctypes.c_uint64),
+        ('n_peers', ctypes.c_int32), ('peer_reserved', ctypes.c_int32),
+        ('peer_rgb', ctypes.c_void_p * 7), ('peer_depth', ctypes.c_void_p * 7),
+        ('peer_mask', ctypes.c_void_p * 7),
     ]
 
 

@@ -992,6 +992,17 @@ render_forward_pipe(const nfi_render_params p, const unsigned char* __restrict__
         p.rgb[ray * 3 + 2] = comp.ab + bg;
         p.depth[ray] = comp.ad;
         p.mask[ray] = comp.am;
+        // the exchange step of the multi-GPU form, fused: the same five floats go to this ray's
+        // place in every peer's full-batch buffers over NVLink (posted stores; the ranks meet at
+        // a barrier after the kernel, parallel.PeerExchange)
+        for (int q = 0; q < p.n_peers; ++q) {
+          float* pr = p.peer_rgb[q] + ray * 3;
+          pr[0] = comp.ar + bg;
+          pr[1] = comp.ag + bg;
+          pr[2] = comp.ab + bg;
+          p.peer_depth[q][ray] = comp.ad;
+          p.peer_mask[q][ray] = comp.am;
+        }
         if (EXTRA == 1 && p.extra != nullptr)
           for (int a = 0; a < 3; ++a) p.extra[ray * 3 + a] = comp.ae[a];
         if (EXTRA == 2 && p.extra != nullptr)

@@ -165,6 +165,7 @@ int launch_fwd_tc_fine(const nfi_render_params& p, const unsigned char* wimg, fl
     return nfi::launch_pipe_forward(p, NP, wimg, scratch, (unsigned)grid, st, g_err,
                                     sizeof(g_err));
   }
+  if (p.n_peers > 0) return fail("peer outputs (n_peers > 0) need the pipelined kernel");
   if constexpr (EX == 2) {
     return fail("semantics output on tensor cores: pipelined kernel only");
   } else {
@@ -414,7 +415,11 @@ int nfi_render_forward(const nfi_render_params* params, void* stream) {
     if (!p.workspace || p.workspace_bytes < nfi_render_workspace_bytes(params))
       return fail("workspace too small (see nfi_render_workspace_bytes)");
   }
+  if (p.n_peers < 0 || p.n_peers > NFI_MAX_PEERS) return fail("n_peers out of range");
+  for (int q = 0; q < p.n_peers; ++q)
+    if (!p.peer_rgb[q] || !p.peer_depth[q] || !p.peer_mask[q]) return fail("peer output pointer is NULL");
   if (want_tc) return launch_fwd_tc(p, np, st);
+  if (p.n_peers > 0) return fail("peer outputs (n_peers > 0) need the pipelined kernel");
   const size_t smem =
       nfi::fwd_smem_floats(np, p.num_samples, p.fine_sampling != 0, wants_normals(params)) *
       sizeof(float);

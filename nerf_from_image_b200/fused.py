@@ -149,7 +149,7 @@ class FusedTriplaneRender(torch.autograd.Function):
     def forward(ctx, planes, w1, b1, w2, b2, palette, beta, alpha, c2w, focal,
                 center, bbox, cfg, height, width, S, noise_t, noise_u,
                 extra_mode, cam_grad, compute_normals=False, out=None,
-                planes_layout='channel_first'):
+                planes_layout='channel_first', peers=None):
         channel_last = planes_layout == 'channel_last'
         _check_shapes(cfg, planes, w1, b1, w2, b2, palette, c2w, focal, center,
                       bbox, height, width, S, noise_t, noise_u, channel_last)
@@ -211,6 +211,14 @@ class FusedTriplaneRender(torch.autograd.Function):
                 p.compute_normals, p.normals = 1, _ptr(normals)
             if DEBUG_BUF is not None:
                 p.normals = _ptr(DEBUG_BUF)
+            if peers:
+                # raw device addresses of this rank's [rgb, depth, mask] slices inside each peer's
+                # buffers (parallel.PeerExchange): the kernel stores its tiles there as well
+                if len(peers) > _lib.MAX_PEERS:
+                    raise _lib.NfiError('at most %d peers' % _lib.MAX_PEERS)
+                p.n_peers = len(peers)
+                for q, (pr, pd, pm) in enumerate(peers):
+                    p.peer_rgb[q], p.peer_depth[q], p.peer_mask[q] = int(pr), int(pd), int(pm)
             ws_bytes = lib.nfi_render_workspace_bytes(ctypes.byref(p))
             ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
             p.workspace, p.workspace_bytes = _ptr(ws), ws_bytes
@@ -336,19 +344,21 @@ class FusedTriplaneRender(torch.autograd.Function):
                     gbbox = res.pop(0)
         return (gplanes, gw1, gb1, gw2, gb2, gpal, gbeta, galpha, gc2w, gfocal,
                 gcenter, gbbox, None, None, None, None, None, None, None, None, None, None,
-                None)
+                None, None)
 
 
 def fused_render(planes, w1, b1, w2, b2, palette, beta, alpha, c2w, focal,
                  center, bbox, cfg, height, width, num_samples, noise_t=None,
                  noise_u=None, extra_mode=_lib.EXTRA_NONE, cam_grad=True,
-                 compute_normals=False, out=None, planes_layout='channel_first'):
+                 compute_normals=False, out=None, planes_layout='channel_first', peers=None):
     """Functional form; returns (rgb, depth, mask, extra|None), with
     ``compute_normals`` (rgb, depth, mask, extra|None, normals).  ``out=(rgb, depth,
     mask)`` makes the kernel write into caller-owned tensors (see parallel.py).
     ``planes_layout``: 'channel_first' = [B,3,32,R,R] as the reference's synthesis network
     leaves them (re-laid-out here), 'channel_last' = [B,3,R,R,32] as synthesis.FusedSynthesis
     emits them (used as they are; a plane gradient comes back in the same layout).
+    ``peers``: list of (rgb, depth, mask) device ADDRESSES of this rank's slices in the other
+    ranks' buffers; the kernel stores its tiles there too (parallel.PeerExchange).
 
     The kernels compute in fp32 like the reference's render (run.py:59-60).  Under
     autocast (BASELINE config 4 trains the synthesis network in bf16) the field tensors
@@ -362,7 +372,7 @@ def fused_render(planes, w1, b1, w2, b2, palette, beta, alpha, c2w, focal,
     rgb, depth, mask, extra, normals = FusedTriplaneRender.apply(
         planes, w1, b1, w2, b2, palette, beta, alpha, c2w, focal, center, bbox,
         cfg, height, width, num_samples, noise_t, noise_u, extra_mode, cam_grad,
-        compute_normals, out, planes_layout)
+        compute_normals, out, planes_layout, peers)
     extra = extra if extra_mode != _lib.EXTRA_NONE else None
     if compute_normals:
         return rgb, depth, mask, extra, normals

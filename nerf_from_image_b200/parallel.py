@@ -156,3 +156,59 @@ def render_sharded(render_fn, batch_inputs, batch, gather=True, group=None, inpl
     if world == 1 or not gather:
         return rgb, depth, mask
     return all_gather_outputs(rgb, depth, mask, batch, group)
+
+
+class PeerExchange:
+    """The all-gather of the output tiles WITHOUT a collective call: every rank's render kernel
+    stores its tiles straight into all ranks' full-batch buffers over NVLink (peer mappings of
+    symmetric memory; ``fused_render(out=..., peers=...)``), and the ranks meet at one device-side
+    barrier.  What ``nn.DataParallel``'s gather does in the reference (run.py:636-644), fused into
+    the epilogue of the render kernel.
+
+    Two buffer sets alternate between calls, so that a rank still reading step k's images cannot be
+    overwritten by a faster peer's step k+1 (it has to pass step k+1's barrier first, and step k+2
+    reuses the set only after that).  Equal shards only (batch % world == 0), world <= 8."""
+
+    def __init__(self, batch, height, width, device, group=None):
+        import torch.distributed._symmetric_memory as symm_mem
+        self.group = group if group is not None else dist.group.WORLD
+        self.world, self.rank = dist.get_world_size(self.group), dist.get_rank(self.group)
+        if batch % self.world:
+            raise ValueError('PeerExchange needs batch %% world == 0 (got %d, %d)' % (batch, self.world))
+        if self.world - 1 > 7:
+            raise ValueError('PeerExchange: at most 8 ranks')
+        self.batch, self.h, self.w = batch, height, width
+        n = batch * height * width
+        self.n = n
+        self.sets = []
+        for _ in range(2):
+            buf = symm_mem.empty(5 * n, dtype=torch.float32, device=device)
+            hdl = symm_mem.rendezvous(buf, self.group)
+            self.sets.append((buf, hdl))
+        self.turn = 0
+
+    def _views(self, buf):
+        n, B, H, W = self.n, self.batch, self.h, self.w
+        return (buf[:3 * n].view(B, H, W, 3), buf[3 * n:4 * n].view(B, H, W), buf[4 * n:].view(B, H, W))
+
+    def begin(self):
+        """-> (full buffers, this rank's slices (``out=``), peer addresses (``peers=``))."""
+        buf, hdl = self.sets[self.turn]
+        full = self._views(buf)
+        a, b = shard_range(self.batch, self.world, self.rank)
+        out = tuple(t[a:b] for t in full)
+        rays0 = a * self.h * self.w
+        peers = []
+        for r in range(self.world):
+            if r == self.rank:
+                continue
+            base = int(hdl.buffer_ptrs[r])
+            peers.append((base + 4 * (3 * rays0), base + 4 * (3 * self.n + rays0),
+                          base + 4 * (4 * self.n + rays0)))
+        return full, out, peers
+
+    def finish(self):
+        """Stream-ordered barrier over the ranks: afterwards every rank's stores have landed."""
+        _, hdl = self.sets[self.turn]
+        hdl.barrier(channel=0)
+        self.turn ^= 1
