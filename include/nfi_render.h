@@ -130,12 +130,22 @@ typedef struct nfi_render_params {
    * rgb / depth / mask tiles (nn.DataParallel, run.py:636-644).  With n_peers > 0 the kernel
    * stores each ray's outputs not only to rgb / depth / mask above but also, through NVLink peer
    * mappings, to the same ray of peer_*[q] for q < n_peers: THIS rank's slice inside peer q's
-   * full-batch buffers (symmetric memory).  No collective call remains, only a barrier. */
+   * full-batch buffers (symmetric memory).  No collective call remains. */
   int32_t n_peers;        /* 0 .. NFI_MAX_PEERS */
   int32_t peer_reserved;
   float *peer_rgb[7];     /* [B,H,W,3] slices in the peers' address spaces */
   float *peer_depth[7];   /* [B,H,W] */
   float *peer_mask[7];    /* [B,H,W] */
+  /* Optional completion handshake inside the kernel (peer_done != NULL): the LAST CTA of the
+   * grid, after every CTA's stores are fenced system-wide, writes peer_epoch to peer_signal[q]
+   * (a word in peer q's memory reserved for this rank) and waits until the words the peers
+   * reserve for us here, peer_signal_self[peer_rank[q]], have reached peer_epoch.  When the
+   * kernel has completed on a rank, all ranks' tiles are in its buffers: no barrier launch. */
+  uint32_t *peer_signal[7];
+  const uint32_t *peer_signal_self;
+  int32_t peer_rank[7];
+  uint32_t peer_epoch;
+  uint32_t *peer_done;    /* zero-initialised device word (CTA counter), reset by the kernel */
 } nfi_render_params;
 
 /* Upstream gradients in, parameter gradients out (all device pointers).

@@ -50,6 +50,9 @@ class RenderParams(ctypes.Structure):
         ('n_peers', ctypes.c_int32), ('peer_reserved', ctypes.c_int32),
         ('peer_rgb', ctypes.c_void_p * 7), ('peer_depth', ctypes.c_void_p * 7),
         ('peer_mask', ctypes.c_void_p * 7),
+        ('peer_signal', ctypes.c_void_p * 7), ('peer_signal_self', ctypes.c_void_p),
+        ('peer_rank', ctypes.c_int32 * 7), ('peer_epoch', ctypes.c_uint32),
+        ('peer_done', ctypes.c_void_p),
     ]
 
 

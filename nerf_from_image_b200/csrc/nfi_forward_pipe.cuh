@@ -1016,6 +1016,32 @@ render_forward_pipe(const nfi_render_params p, const unsigned char* __restrict__
 #undef NFI_T
   tc::tc_fence_before();
   __syncthreads();
+  if (p.n_peers > 0 && p.peer_done != nullptr && tid == 0) {
+    // Completion handshake of the fused exchange.  Every CTA: its threads' peer stores are ordered
+    // before the bar.sync above, the system-scope fence publishes them, then it counts itself.
+    // The last CTA of this rank signals every peer and waits for their signals: a completed
+    // kernel means "all ranks' tiles have landed here".
+    __threadfence_system();
+    const unsigned done = atomicAdd(p.peer_done, 1u);
+    if (done == gridDim.x - 1) {
+      __threadfence();
+      *p.peer_done = 0u;
+      for (int q = 0; q < p.n_peers; ++q)
+        asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p.peer_signal[q]), "r"(p.peer_epoch)
+                     : "memory");
+      const long long t0 = clock64();
+      for (int q = 0; q < p.n_peers; ++q) {
+        const uint32_t* flag = p.peer_signal_self + p.peer_rank[q];
+        uint32_t v;
+        do {
+          asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(flag) : "memory");
+          if ((int)(v - p.peer_epoch) >= 0) break;
+          __nanosleep(200);
+          if (clock64() - t0 > 8000000000LL) __trap();  // a peer never arrived: fail, do not hang
+        } while (true);
+      }
+    }
+  }
   if (tid < 32) tc::tmem_dealloc(tmem_base, 512);
 }
 

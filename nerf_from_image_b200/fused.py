@@ -214,11 +214,19 @@ class FusedTriplaneRender(torch.autograd.Function):
             if peers:
                 # raw device addresses of this rank's [rgb, depth, mask] slices inside each peer's
                 # buffers (parallel.PeerExchange): the kernel stores its tiles there as well
-                if len(peers) > _lib.MAX_PEERS:
+                if len(peers['slices'] if isinstance(peers, dict) else peers) > _lib.MAX_PEERS:
                     raise _lib.NfiError('at most %d peers' % _lib.MAX_PEERS)
-                p.n_peers = len(peers)
-                for q, (pr, pd, pm) in enumerate(peers):
+                slices = peers['slices'] if isinstance(peers, dict) else peers
+                p.n_peers = len(slices)
+                for q, (pr, pd, pm) in enumerate(slices):
                     p.peer_rgb[q], p.peer_depth[q], p.peer_mask[q] = int(pr), int(pd), int(pm)
+                if isinstance(peers, dict) and peers.get('done') is not None:
+                    # completion handshake inside the kernel (parallel.PeerExchange)
+                    for q, (sig, r) in enumerate(zip(peers['signal'], peers['ranks'])):
+                        p.peer_signal[q], p.peer_rank[q] = int(sig), int(r)
+                    p.peer_signal_self = int(peers['self_signal'])
+                    p.peer_epoch = int(peers['epoch']) & 0xFFFFFFFF
+                    p.peer_done = int(peers['done'])
             ws_bytes = lib.nfi_render_workspace_bytes(ctypes.byref(p))
             ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
             p.workspace, p.workspace_bytes = _ptr(ws), ws_bytes

@@ -161,15 +161,19 @@ def render_sharded(render_fn, batch_inputs, batch, gather=True, group=None, inpl
 class PeerExchange:
     """The all-gather of the output tiles WITHOUT a collective call: every rank's render kernel
     stores its tiles straight into all ranks' full-batch buffers over NVLink (peer mappings of
-    symmetric memory; ``fused_render(out=..., peers=...)``), and the ranks meet at one device-side
-    barrier.  What ``nn.DataParallel``'s gather does in the reference (run.py:636-644), fused into
-    the epilogue of the render kernel.
+    symmetric memory; ``fused_render(out=..., peers=...)``) and the kernels themselves shake hands
+    before they finish (the last CTA of a rank signals every peer and waits for their signals:
+    ``nfi_render_params.peer_signal``).  A completed kernel = every rank's tiles are here.  What
+    ``nn.DataParallel``'s gather does in the reference (run.py:636-644), fused into the render.
 
     Two buffer sets alternate between calls, so that a rank still reading step k's images cannot be
-    overwritten by a faster peer's step k+1 (it has to pass step k+1's barrier first, and step k+2
-    reuses the set only after that).  Equal shards only (batch % world == 0), world <= 8."""
+    overwritten by a faster peer's step k+1: that peer's step k+1 kernel cannot complete before
+    this rank's step k+1 kernel has signalled, and step k+2 reuses the set only after that.
+    Equal shards only (batch % world == 0), world <= 8."""
 
-    def __init__(self, batch, height, width, device, group=None):
+    FLAG_WORDS = 64
+
+    def __init__(self, batch, height, width, device, group=None, handshake='kernel'):
         import torch.distributed._symmetric_memory as symm_mem
         self.group = group if group is not None else dist.group.WORLD
         self.world, self.rank = dist.get_world_size(self.group), dist.get_rank(self.group)
@@ -178,37 +182,51 @@ class PeerExchange:
         if self.world - 1 > 7:
             raise ValueError('PeerExchange: at most 8 ranks')
         self.batch, self.h, self.w = batch, height, width
+        self.handshake = handshake          # 'kernel' | 'barrier' (symmetric-memory barrier launch)
         n = batch * height * width
         self.n = n
         self.sets = []
         for _ in range(2):
-            buf = symm_mem.empty(5 * n, dtype=torch.float32, device=device)
+            buf = symm_mem.empty(5 * n + self.FLAG_WORDS, dtype=torch.float32, device=device)
+            buf.zero_()
             hdl = symm_mem.rendezvous(buf, self.group)
-            self.sets.append((buf, hdl))
+            self.sets.append([buf, hdl, 0])     # epoch of the set
+        self.done = torch.zeros(1, dtype=torch.int32, device=device)
+        torch.cuda.synchronize(device)
+        dist.barrier(self.group)               # every rank's flag words are zero before anyone signals
         self.turn = 0
 
     def _views(self, buf):
         n, B, H, W = self.n, self.batch, self.h, self.w
-        return (buf[:3 * n].view(B, H, W, 3), buf[3 * n:4 * n].view(B, H, W), buf[4 * n:].view(B, H, W))
+        return (buf[:3 * n].view(B, H, W, 3), buf[3 * n:4 * n].view(B, H, W), buf[4 * n:5 * n].view(B, H, W))
 
     def begin(self):
-        """-> (full buffers, this rank's slices (``out=``), peer addresses (``peers=``))."""
-        buf, hdl = self.sets[self.turn]
+        """-> (full buffers, this rank's slices (``out=``), the ``peers=`` argument)."""
+        st = self.sets[self.turn]
+        buf, hdl = st[0], st[1]
+        st[2] += 1
         full = self._views(buf)
         a, b = shard_range(self.batch, self.world, self.rank)
         out = tuple(t[a:b] for t in full)
         rays0 = a * self.h * self.w
-        peers = []
+        slices, signal, ranks = [], [], []
         for r in range(self.world):
             if r == self.rank:
                 continue
             base = int(hdl.buffer_ptrs[r])
-            peers.append((base + 4 * (3 * rays0), base + 4 * (3 * self.n + rays0),
-                          base + 4 * (4 * self.n + rays0)))
+            slices.append((base + 4 * (3 * rays0), base + 4 * (3 * self.n + rays0),
+                           base + 4 * (4 * self.n + rays0)))
+            signal.append(base + 4 * (5 * self.n + self.rank))   # our word in peer r's flag area
+            ranks.append(r)
+        peers = {'slices': slices}
+        if self.handshake == 'kernel':
+            peers.update(signal=signal, ranks=ranks, epoch=st[2], done=self.done.data_ptr(),
+                         self_signal=int(hdl.buffer_ptrs[self.rank]) + 4 * 5 * self.n)
         return full, out, peers
 
     def finish(self):
-        """Stream-ordered barrier over the ranks: afterwards every rank's stores have landed."""
-        _, hdl = self.sets[self.turn]
-        hdl.barrier(channel=0)
+        """With the in-kernel handshake nothing is left to do; with ``handshake='barrier'`` a
+        stream-ordered symmetric-memory barrier stands in for it."""
+        if self.handshake != 'kernel':
+            self.sets[self.turn][1].barrier(channel=0)
         self.turn ^= 1
