@@ -351,8 +351,21 @@ class Bench:
         kernel_events = []
         gather_events = []
 
-        peer_ex = (parallel.PeerExchange(gb, H, W, dev) if (world > 1 and a.exchange == 'peer')
-                   else None)
+        # N > 1: the exchange fused into the kernel where symmetric memory is available on this
+        # box ('auto' falls back to the in-place NCCL all-gather, and says so in `exchange`)
+        peer_ex, exchange_note = None, ('nccl' if world > 1 else None)
+        if world > 1 and a.exchange in ('peer', 'auto'):
+            try:
+                peer_ex = parallel.PeerExchange(gb, H, W, dev)
+                ok, why = 1.0, ''
+            except Exception as exc:
+                ok, why = 0.0, repr(exc)[:120]
+            if self.min_over_ranks(ok) < 1.0:
+                if a.exchange == 'peer':
+                    raise SystemExit('--exchange peer: symmetric memory unavailable: ' + why)
+                peer_ex, exchange_note = None, 'nccl (peer exchange unavailable: %s)' % why
+            else:
+                exchange_note = 'peer'
 
         def step(time_kernel=False):
             with torch.no_grad():
@@ -478,7 +491,7 @@ class Bench:
             'gpu_launches': 2 * a.steps,
             'roofline': roofline, 'fwd_bwd': fwd_bwd, 'cpu_baseline': cpu_baseline,
             'torch_eager_gpu': eager, 'parity': parity, 'gathered_check': gathered,
-            'collective_ms': coll_ms, 'exchange': (a.exchange if world > 1 else None),
+            'collective_ms': coll_ms, 'exchange': exchange_note,
             'render_from_channel_first_planes': cf,
             'e2e_planes_from_host': e2e_planes, 'fixture_pretrained_generator': pretrained,
         }
@@ -852,7 +865,7 @@ def main():
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
     ap.add_argument('--config', type=int, default=2, choices=[2, 3, 4, 5])
     ap.add_argument('--scaling', default='weak', choices=['weak', 'strong'])
-    ap.add_argument('--exchange', default='nccl', choices=['nccl', 'peer'],
+    ap.add_argument('--exchange', default='auto', choices=['auto', 'nccl', 'peer'],
                     help='N > 1: in-place NCCL all-gather, or stores into the peers\' buffers from the kernel')
     ap.add_argument('--batch', type=int, default=None)
     ap.add_argument('--no-cpu-baseline', action='store_true')

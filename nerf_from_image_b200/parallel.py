@@ -203,25 +203,30 @@ class PeerExchange:
     def begin(self):
         """-> (full buffers, this rank's slices (``out=``), the ``peers=`` argument)."""
         st = self.sets[self.turn]
-        buf, hdl = st[0], st[1]
+        if len(st) == 3:   # first use of this set: views and peer addresses are fixed from here on
+            buf, hdl = st[0], st[1]
+            full = self._views(buf)
+            a, b = shard_range(self.batch, self.world, self.rank)
+            out = tuple(t[a:b] for t in full)
+            rays0 = a * self.h * self.w
+            slices, signal, ranks = [], [], []
+            for r in range(self.world):
+                if r == self.rank:
+                    continue
+                base = int(hdl.buffer_ptrs[r])
+                slices.append((base + 4 * (3 * rays0), base + 4 * (3 * self.n + rays0),
+                               base + 4 * (4 * self.n + rays0)))
+                signal.append(base + 4 * (5 * self.n + self.rank))   # our word in peer r's flag area
+                ranks.append(r)
+            peers = {'slices': slices}
+            if self.handshake == 'kernel':
+                peers.update(signal=signal, ranks=ranks, done=self.done.data_ptr(),
+                             self_signal=int(hdl.buffer_ptrs[self.rank]) + 4 * 5 * self.n)
+            st.append((full, out, peers))
         st[2] += 1
-        full = self._views(buf)
-        a, b = shard_range(self.batch, self.world, self.rank)
-        out = tuple(t[a:b] for t in full)
-        rays0 = a * self.h * self.w
-        slices, signal, ranks = [], [], []
-        for r in range(self.world):
-            if r == self.rank:
-                continue
-            base = int(hdl.buffer_ptrs[r])
-            slices.append((base + 4 * (3 * rays0), base + 4 * (3 * self.n + rays0),
-                           base + 4 * (4 * self.n + rays0)))
-            signal.append(base + 4 * (5 * self.n + self.rank))   # our word in peer r's flag area
-            ranks.append(r)
-        peers = {'slices': slices}
+        full, out, peers = st[3]
         if self.handshake == 'kernel':
-            peers.update(signal=signal, ranks=ranks, epoch=st[2], done=self.done.data_ptr(),
-                         self_signal=int(hdl.buffer_ptrs[self.rank]) + 4 * 5 * self.n)
+            peers['epoch'] = st[2]
         return full, out, peers
 
     def finish(self):

@@ -28,11 +28,11 @@ for a in "$@"; do
     mgpu2|mgpu4|mgpu8) n=${a#mgpu}; TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port 29511"
              (timeout 400 $TR bench.py --gpus $n --steps 20 --warmup 3 --no-cpu-baseline | tail -1 > gpurun_out/r2_bench_weak_n$n.json) 2> gpurun_out/r2_bench_weak_n$n.err
              (timeout 300 $TR bench.py --gpus $n --scaling strong --quick --no-e2e | tail -1 > gpurun_out/r2_bench_strong_n$n.json) 2> gpurun_out/r2_bench_strong_n$n.err
-             (timeout 300 $TR bench.py --gpus $n --exchange peer --quick --no-e2e | tail -1 > gpurun_out/r2_bench_peer_n$n.json) 2> gpurun_out/r2_bench_peer_n$n.err
-             (timeout 300 $TR bench.py --gpus $n --exchange peer --scaling strong --quick --no-e2e | tail -1 > gpurun_out/r2_bench_peerstrong_n$n.json) 2> gpurun_out/r2_bench_peerstrong_n$n.err
+             (timeout 300 $TR bench.py --gpus $n --exchange nccl --quick --no-e2e | tail -1 > gpurun_out/r2_bench_nccl_n$n.json) 2> gpurun_out/r2_bench_nccl_n$n.err
+             (timeout 300 $TR bench.py --gpus $n --exchange nccl --scaling strong --quick --no-e2e | tail -1 > gpurun_out/r2_bench_ncclstrong_n$n.json) 2> gpurun_out/r2_bench_ncclstrong_n$n.err
              (timeout 300 $TR bench.py --gpus $n --config 3 | tail -1 > gpurun_out/r2_bench_config3_n$n.json) 2> gpurun_out/r2_bench_config3_n$n.err
              (timeout 300 $TR bench.py --gpus $n --config 4 | tail -1 > gpurun_out/r2_bench_config4_n$n.json) 2> gpurun_out/r2_bench_config4_n$n.err
-             for f in weak strong peer peerstrong config3 config4; do echo "== $f n=$n"; cut -c1-700 gpurun_out/r2_bench_${f}_n$n.json; tail -3 gpurun_out/r2_bench_${f}_n$n.err | cut -c1-300; done;;
+             for f in weak strong nccl ncclstrong config3 config4; do echo "== $f n=$n"; cut -c1-700 gpurun_out/r2_bench_${f}_n$n.json; tail -3 gpurun_out/r2_bench_${f}_n$n.err | cut -c1-300; done;;
     cfg1) (timeout 300 python bench.py --config 3 | tail -1 > gpurun_out/r2_bench_config3_n1.json) 2> gpurun_out/r2_bench_config3_n1.err; (timeout 300 python bench.py --config 4 | tail -1 > gpurun_out/r2_bench_config4_n1.json) 2> gpurun_out/r2_bench_config4_n1.err; (timeout 600 python bench.py --config 5 | tail -1 > gpurun_out/r2_bench_config5_n1.json) 2> gpurun_out/r2_bench_config5_n1.err
           for f in config3 config4 config5; do echo "== $f"; cut -c1-1500 gpurun_out/r2_bench_${f}_n1.json; tail -3 gpurun_out/r2_bench_${f}_n1.err | cut -c1-300; done;;
     diag) timeout 600 python tools/grad_diag.py > gpurun_out/r2_grad_diag.txt 2>&1; cat gpurun_out/r2_grad_diag.txt;;
