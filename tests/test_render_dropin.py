@@ -178,3 +178,38 @@ def test_parallel_model_forward(monkeypatch):
     pm(cams['c2w'], cams['focal'], None, cams['bbox'], ws, res_multiplier=0.5, ray_multiplier=2,
        extra_model_inputs=extra_in)
     assert calls[-1]['noise_t'].shape == (2, H // 2, H // 2, 2 * S)
+
+
+def test_front_end_latent_handling_matches_the_generator(monkeypatch):
+    """generator.resolve_ws / resolve_palette (the host logic of both sm_100a front-ends) feed
+    the synthesis network and the palette exactly what Generator.forward feeds them
+    (models/generator.py:423-468), for z, a single broadcast w and a complete w."""
+    from nerf_from_image_b200 import generator as G
+    scene, cams, g, ws, extra_in, calls = setup(monkeypatch)
+    seen = {}
+    stub = g.synthesis_network
+
+    def spy(w, **kw):
+        seen['ws'] = w.clone()
+        return stub.planes
+    monkeypatch.setattr(stub, 'forward', spy)
+    torch.manual_seed(2)
+    z = torch.randn(2, 512)
+    w_full = g.mapping_network(z, None).detach()
+    for c in (z, w_full[:, :1].contiguous(), w_full):
+        out = g(None, c, ['sampler', 'attention_values'], {})
+        w2, batch = G.resolve_ws(g, c)
+        pal, w_syn = G.resolve_palette(g, w2, ['sampler'], {})
+        assert batch == 2
+        assert torch.equal(w_syn, seen['ws'])
+        assert torch.equal(pal, out['attention_values'])
+    bias = torch.randn(2, 10, 3)
+    out = g(None, w_full, ['sampler', 'attention_values'], {'attention_values_bias': bias})
+    pal, _ = G.resolve_palette(g, w_full, ['sampler'], {'attention_values_bias': bias})
+    assert torch.equal(pal, out['attention_values'])
+    assert G.FusedGeneratorFront.supports(['sampler'], {}) is False          # grad mode on
+    with torch.no_grad():
+        assert G.FusedGeneratorFront.supports(['sampler', 'attention_values'], {})
+        assert not G.FusedGeneratorFront.supports(['sampler', 'sdf_eikonal_loss'], {})
+    assert G.HeadsGeneratorFront.supports(['sampler', 'entropy_loss', 'path_length'], {})
+    assert not G.HeadsGeneratorFront.supports(['sampler'], {})
