@@ -545,6 +545,9 @@ class Bench:
             api = ('nerf_from_image_b200.render.render (drop-in of run.py:176-350) on the reference '
                    'Generator with enable_fused_synthesis: mapping-free w input -> texture mapper -> '
                    'FusedSynthesis (tcgen05) -> fused render')
+            fs_only = FusedSynthesis(g.synthesis_network)
+            ws_dev = host['ws'].to(dev)
+            synth_only = lambda: fs_only(ws_dev[:, :14])
         except Exception as exc:
             why = repr(exc)[:80]
             chans = [min(32768 // r, 512) for r in (4, 8, 16, 32, 64, 128, 256)]
@@ -568,6 +571,8 @@ class Bench:
                     host['mask'].copy_(out[2], non_blocking=True)
                 torch.cuda.synchronize()
             api = ('FusedSynthesis + fused_render called directly on seeded parameters (%s)' % why)
+            ws_dev = host['ws'].to(dev)
+            synth_only = lambda: fs(ws_dev[:, :14])
         for _ in range(2):
             step()
         self.barrier()
@@ -577,12 +582,31 @@ class Bench:
             step()
         dt = self.max_over_ranks((time.perf_counter() - t0) / n)
         R._FRONTS.clear()
+        # the plane producer on its own (CUDA events): dense conv FLOPs as executed (transposed convs
+        # on the input grid), x3 for the three bf16 MMAs per product, against the measured bf16 peak
+        with torch.no_grad():
+            ms_syn = self.timed(synth_only, 5, 2)
+        chans = [min(32768 // r, 512) for r in (4, 8, 16, 32, 64, 128, 256)]
+        fl = 0.0
+        for i, r in enumerate((4, 8, 16, 32, 64, 128, 256)):
+            if i:
+                fl += 2.0 * chans[i - 1] * chans[i] * 9 * (r // 2) ** 2
+            fl += 2.0 * chans[i] * chans[i] * 9 * r * r + 2.0 * chans[i] * 96 * r * r
+        pk = peaks()
+        mma_tf = 3 * B * fl / (ms_syn * 1e-3) / 1e12
+        synthesis = {'ms_per_forward': ms_syn, 'images_per_s': world * B / (ms_syn * 1e-3),
+                     'dense_gflop_per_image': fl / 1e9,
+                     'fp32_equivalent_tflops': B * fl / (ms_syn * 1e-3) / 1e12,
+                     'bf16_mma_tflops': mma_tf, 'frac_of_measured_bf16_peak': mma_tf / pk['tflops'],
+                     'what': 'FusedSynthesis alone, %d images, 256^2 x 96 planes, 512-channel '
+                             'StyleGAN2 synthesis (13 modulated 3x3 convs + 7 ToRGB); bf16 hi/lo '
+                             'pairs, three MMAs per product' % B}
         h2d = sum(host[k].numel() * 4 for k in ('ws', 'c2w', 'focal'))
         d2h = sum(host[k].numel() * 4 for k in ('rgb', 'depth', 'mask'))
         torch.cuda.empty_cache()
         return {'value': gb * H * W / dt, 'unit': UNIT, 'h2d_bytes_per_step': h2d,
                 'd2h_bytes_per_step': d2h, 'ms_per_step': dt * 1e3,
-                'mask_mean': host['mask'].mean().item(), 'api': api,
+                'mask_mean': host['mask'].mean().item(), 'api': api, 'synthesis': synthesis,
                 'what': 'generator forward, w -> image: latents + cameras H2D from pinned memory, '
                         'synthesis network and render on the sm_100a kernels (both random draws '
                         'made on the device like the reference), rgb/depth/mask D2H; wall clock '

@@ -1037,7 +1037,7 @@ render_forward_pipe(const nfi_render_params p, const unsigned char* __restrict__
           asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(flag) : "memory");
           if ((int)(v - p.peer_epoch) >= 0) break;
           __nanosleep(200);
-          if (clock64() - t0 > 8000000000LL) __trap();  // a peer never arrived: fail, do not hang
+          if (clock64() - t0 > 60000000000LL) __trap();  // (~30 s) a peer never arrived: fail, do not hang
         } while (true);
       }
     }

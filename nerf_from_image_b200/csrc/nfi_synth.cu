@@ -55,6 +55,11 @@ constexpr int kConvThreads = 320;      // TMA warp, MMA warp, 8 epilogue warps
 constexpr int kMaxPhases = 4, kMaxTaps = 9;
 
 enum { kModeRaw = 0, kModeAct = 1, kModeRgb = 2 };
+// ToRGB: the running image's footprint of one 16x16 output tile is 10x10 low-resolution positions
+// x 96 channels; staged once per tile in shared memory (rows padded to 25 float4: consecutive
+// positions fall into different bank groups)
+constexpr int kSkipDim = 10, kSkipRow4 = 25;
+constexpr int kSkipBytes = kSkipDim * kSkipDim * kSkipRow4 * 16;
 
 struct ActEpilogue {   // shared by conv_tc_kernel (stride-1 layers) and fir_act_kernel (up layers)
   const float* dcoef;  // [B,N]
@@ -213,6 +218,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
   uint64_t* acc_full = empty + kStages; // [2]
   uint64_t* acc_empty = acc_full + 2;   // [2]
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(acc_empty + 2);
+  float4* skip_sm = reinterpret_cast<float4*>(smem + kStages * stage_bytes + 128);  // RGB + skip only
 
   if (tid == 0) {
     if (tc::smem_u32(smem) & 1023u) __trap();
@@ -313,6 +319,24 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
       const TileCoord t = decode_tile(a, tile);
       const uint32_t acc = it & 1;
       const int n0 = t.nt * a.BN;
+      const bool staged = (a.mode == kModeRgb) && (a.skip != nullptr);
+      if (staged) {
+        // while the MMAs of this tile run: the 10x10 low-resolution footprint of the tile, zeros
+        // outside the image (a missing neighbour contributes nothing, stylegan.py:71-75)
+        const int hh = a.H >> 1, hw = a.W >> 1;
+        const int gy0 = t.ty * (kTileH / 2) - 1, gx0 = t.tx * (kTileW / 2) - 1;
+        const int c4n = a.N >> 2;   // float4 per position (24)
+        tc::bar_sync(1, 256);       // the previous tile's readers are done
+        for (int i = tid - 64; i < kSkipDim * kSkipDim * c4n; i += 256) {
+          const int pxl = i / c4n, c4 = i - pxl * c4n;
+          const int gy = gy0 + pxl / kSkipDim, gx = gx0 + pxl % kSkipDim;
+          float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (gy >= 0 && gy < hh && gx >= 0 && gx < hw)
+            v = __ldg(reinterpret_cast<const float4*>(a.skip + (((size_t)t.img * hh + gy) * hw + gx) * a.N) + c4);
+          skip_sm[pxl * kSkipRow4 + c4] = v;
+        }
+        tc::bar_sync(1, 256);
+      }
       tc::mbar_wait(&acc_full[acc], (it >> 1) & 1);
       tc::tc_fence_after();
 #pragma unroll 1
@@ -338,10 +362,15 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
           const int jy = (y & 1) ? iy + 1 : iy - 1, jx = (x & 1) ? ix + 1 : ix - 1;
           const float wy1 = (jy >= 0 && jy < hh) ? 0.25f : 0.f, wx1 = (jx >= 0 && jx < hw) ? 0.25f : 0.f;
           const int cy = min(max(jy, 0), hh - 1), cx = min(max(jx, 0), hw - 1);
-          wsk[0] = 0.75f * 0.75f; psk[0] = ((size_t)t.img * hh + iy) * hw + ix;
-          wsk[1] = 0.75f * wx1;   psk[1] = ((size_t)t.img * hh + iy) * hw + cx;
-          wsk[2] = wy1 * 0.75f;   psk[2] = ((size_t)t.img * hh + cy) * hw + ix;
-          wsk[3] = wy1 * wx1;     psk[3] = ((size_t)t.img * hh + cy) * hw + cx;
+          // positions inside the staged footprint (its origin is one low-res position up / left of
+          // the tile); out-of-image neighbours are staged as zeros, so the weights need no masking
+          const int ly = iy - (t.ty * (kTileH / 2) - 1), lx = ix - (t.tx * (kTileW / 2) - 1);
+          const int my = jy - (t.ty * (kTileH / 2) - 1), mx = jx - (t.tx * (kTileW / 2) - 1);
+          (void)wy1; (void)wx1; (void)cy; (void)cx;
+          wsk[0] = 0.75f * 0.75f; psk[0] = (size_t)(ly * kSkipDim + lx);
+          wsk[1] = 0.75f * 0.25f; psk[1] = (size_t)(ly * kSkipDim + mx);
+          wsk[2] = 0.25f * 0.75f; psk[2] = (size_t)(my * kSkipDim + lx);
+          wsk[3] = 0.25f * 0.25f; psk[3] = (size_t)(my * kSkipDim + mx);
         }
       }
       for (int j = half * chunks; j < (half + 1) * chunks; ++j) {
@@ -363,7 +392,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
             if (a.skip != nullptr) {
 #pragma unroll
               for (int s = 0; s < 4; ++s) {
-                const float4 k = __ldg(reinterpret_cast<const float4*>(a.skip + psk[s] * a.N + nn));
+                const float4 k = skip_sm[psk[s] * kSkipRow4 + (nn >> 2)];
                 acc4.x = fmaf(wsk[s], k.x, acc4.x);
                 acc4.y = fmaf(wsk[s], k.y, acc4.y);
                 acc4.z = fmaf(wsk[s], k.z, acc4.z);
@@ -607,7 +636,8 @@ static int launch_conv(ConvArgs& a, Pair in, Pair wt, int w_taps, cudaStream_t s
              a.C, a.N);
     return 1;
   }
-  const int smem = kStages * (2 * kATile + 2 * a.BN * 128) + 128;
+  const int smem = kStages * (2 * kATile + 2 * a.BN * 128) + 128 +
+                   ((a.mode == kModeRgb && a.skip != nullptr) ? kSkipBytes : 0);
   NFI_SCUDA(cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   const int grid = n_tiles < sm_count() ? n_tiles : sm_count();
   conv_tc_kernel<<<grid, kConvThreads, smem, st>>>(tAh, tAl, tWh, tWl, a, n_tiles);
