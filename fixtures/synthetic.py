@@ -82,6 +82,32 @@ def make_scene(seed, batch, plane_res=256, attention_values=10,
                 white_background=bool(white_background))
 
 
+def add_view_mapper(scene, seed=5):
+    """Turns ``scene`` into a view-direction-conditioned one (--use_viewdir, CARLA:
+    models/generator.py:189-253,376-377): the decoder's second layer gets 1 + 32 outputs (row 0,
+    the distance, is kept) and the scene gains ``view_mapper`` -- EFFECTIVE weights of a
+    ViewDirectionMapper trunk (fc0 .. fc6, four LayerNorms; oracle.render_oracle.view_mapper_trunk)
+    -- and ``w3`` [A,32] / ``b3`` [A] of its output layer (random instead of the reference's zero
+    initialisation, so that the conditioning is visible).  Returns a new dict."""
+    gen = torch.Generator().manual_seed(seed)
+    dev = scene['w2'].device
+    A = scene['palette'].shape[1] if scene['palette'] is not None else 3
+    rn = lambda *shape: torch.randn(*shape, generator=gen)
+    w2 = torch.cat((scene['w2'][:1].cpu(), rn(32, HIDDEN) / math.sqrt(HIDDEN)), dim=0)
+    b2 = torch.cat((scene['b2'][:1].cpu(), 0.1 * rn(32)), dim=0)
+    m = {'fc0_w': rn(64, 3) / math.sqrt(3), 'fc0_b': 0.1 * rn(64)}
+    for i in range(1, 5):
+        m['fc%d_w' % i] = rn(64, 64) / 8
+        m['norm%d_w' % i] = 1 + 0.1 * rn(64)
+        m['norm%d_b' % i] = 0.1 * rn(64)
+    m['fc5_w'], m['fc5_b'] = rn(64, 64) / 8, 0.1 * rn(64)
+    m['fc6_w'], m['fc6_b'] = rn(32, 64) / 8, 0.1 * rn(32)
+    out = dict(scene)
+    out.update(w2=w2.to(dev), b2=b2.to(dev), view_mapper={k: v.to(dev) for k, v in m.items()},
+               w3=(rn(A, 32) / math.sqrt(32)).to(dev), b3=(0.1 * rn(A)).to(dev))
+    return out
+
+
 def make_cameras(seed, batch, ortho=False, radius=3.0, with_bbox=False,
                  with_center=False, device='cpu'):
     """Look-at-origin cameras: dict(c2w [B,4,4], focal [B]|None, center, bbox)."""

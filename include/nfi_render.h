@@ -35,7 +35,7 @@
 extern "C" {
 #endif
 
-#define NFI_ABI_VERSION 4
+#define NFI_ABI_VERSION 5
 
 #if defined(__GNUC__)
 #define NFI_API __attribute__((visibility("default")))
@@ -47,6 +47,7 @@ extern "C" {
 #define NFI_HIDDEN 64         /* hidden_dim             models/generator.py:293 */
 #define NFI_MAX_ATTENTION 15  /* decoder outputs 1+A, padded to <= 16 */
 #define NFI_MAX_PEERS 7       /* other GPUs of one NVSwitch domain */
+#define NFI_VIEW_FEATURES 32  /* ViewDirectionMapper(., num_features=32) models/generator.py:191 */
 
 /* what the 5th output of render() carries (run.py:227-257,337-338) */
 enum nfi_extra_mode {
@@ -146,6 +147,16 @@ typedef struct nfi_render_params {
   int32_t peer_rank[7];
   uint32_t peer_epoch;
   uint32_t *peer_done;    /* zero-initialised device word (CTA counter), reset by the kernel */
+  /* ---- view-direction conditioning (ABI 5; --use_viewdir, CARLA: run.py:216-217,
+   * models/generator.py:189-253,376-377,662-663).  With view_features != NULL the decoder's
+   * second layer emits 1 + 32 values (w2 [33,64], b2 [33]) and every sample's colour logits are
+   *     w3 . leaky_relu(view_features[ray] + decoder_features, 0.2) + b3
+   * (ViewDirectionMapper.mapper_closure); view_features is the mapper's per-RAY trunk output
+   * (fc0 .. fc6 on the unit ray direction, computed by the caller once per ray).  fp32 SIMT
+   * kernels only. */
+  const float *view_features; /* [B,H,W,32] or NULL */
+  const float *w3;            /* [A,32] ([3,32] when A == 0): EFFECTIVE weight of mapper.output */
+  const float *b3;            /* [A] ([3]) */
 } nfi_render_params;
 
 /* Upstream gradients in, parameter gradients out (all device pointers).
@@ -169,6 +180,10 @@ typedef struct nfi_render_grads {
   float *grad_alpha;   /* [1] */
   float *grad_origins; /* [B,H,W,3] dL/d ray origin       (chain to c2w in the binding) */
   float *grad_dirs;    /* [B,H,W,3] dL/d unit ray direction */
+  /* view-direction conditioning (ABI 5); grad_w2 / grad_b2 are then [33,64] / [33] */
+  float *grad_view_features; /* [B,H,W,32] (overwritten per ray, not accumulated) */
+  float *grad_w3;            /* [A,32] */
+  float *grad_b3;            /* [A] */
 } nfi_render_grads;
 
 /* library / build identification */

@@ -16,7 +16,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get('NFI_LIB_PATH') or os.path.join(_HERE, 'csrc', 'libnfi_render.so')
 
 c_float_p = ctypes.POINTER(ctypes.c_float)
-ABI_VERSION = 4  # NFI_ABI_VERSION of include/nfi_render.h
+ABI_VERSION = 5  # NFI_ABI_VERSION of include/nfi_render.h
 MAX_PEERS = 7
 
 EXTRA_NONE, EXTRA_COORDS, EXTRA_SEMANTICS = 0, 1, 2
@@ -53,6 +53,7 @@ class RenderParams(ctypes.Structure):
         ('peer_signal', ctypes.c_void_p * 7), ('peer_signal_self', ctypes.c_void_p),
         ('peer_rank', ctypes.c_int32 * 7), ('peer_epoch', ctypes.c_uint32),
         ('peer_done', ctypes.c_void_p),
+        ('view_features', ctypes.c_void_p), ('w3', ctypes.c_void_p), ('b3', ctypes.c_void_p),
     ]
 
 
@@ -62,7 +63,7 @@ class RenderGrads(ctypes.Structure):
         'g_rgb', 'g_mask', 'g_extra', 'out_rgb', 'out_mask', 'out_extra',
         'grad_planes', 'grad_w1', 'grad_b1', 'grad_w2', 'grad_b2',
         'grad_palette', 'grad_beta', 'grad_alpha', 'grad_origins',
-        'grad_dirs')]
+        'grad_dirs', 'grad_view_features', 'grad_w3', 'grad_b3')]
 
 
 class SampleParams(ctypes.Structure):

@@ -25,6 +25,7 @@
 //            chains them to tform_cam2world / focal with tiny torch ops).
 #pragma once
 #include "nfi_common.cuh"
+#include "nfi_forward.cuh"  // kViewMlpPad
 
 namespace nfi {
 
@@ -42,35 +43,50 @@ __device__ __forceinline__ float warp_sum(float v) {
   return v;
 }
 
-__host__ __device__ inline size_t bwd_smem_floats(int nout_pad, bool wgrad) {
-  size_t n = kC * kHid + kHid + kHid * nout_pad + nout_pad + 48;  // weights, palette
+__host__ __device__ inline size_t bwd_smem_floats(int nout_pad, bool wgrad, bool viewdir = false) {
+  const int nm = viewdir ? kViewMlpPad : nout_pad;
+  size_t n = kC * kHid + kHid + kHid * nm + nm + 48;  // weights, palette
   n += kWarps * 32 * kFRow;                                         // features / dF
   n += kWarps * 32 * 4;                                             // coord grads
-  if (wgrad) n += kWarps * 32 * kDRow + kWarps * 32 * nout_pad;     // staging
-  if (wgrad) n += kC * kHid + kHid + kHid * nout_pad + nout_pad;    // CTA reduction
+  if (wgrad) n += kWarps * 32 * kDRow + kWarps * 32 * nm;           // staging
+  if (wgrad) n += kC * kHid + kHid + kHid * nm + nm;                // CTA reduction
+  if (viewdir) {
+    n += kC * nout_pad + nout_pad + 2 * NFI_VIEW_FEATURES * kThreads;  // W3t, b3, x_ray, dx_ray
+    if (wgrad) n += kC * nout_pad + nout_pad;                          // CTA reduction of dW3, db3
+  }
   return n;
 }
 
-template <int NOUT_PAD, bool WGRAD>
+// VD: view-direction conditioning (nfi_forward.cuh); the head works on NOUT_PAD logits, the
+// decoder's second layer on NM = 36 outputs.
+template <int NOUT_PAD, bool WGRAD, bool VD = false>
 __global__ void __launch_bounds__(kThreads)
 render_backward_simt(const nfi_render_params p, const nfi_render_grads g) {
   constexpr int NA = NOUT_PAD - 1;
+  constexpr int NM = VD ? kViewMlpPad : NOUT_PAD;
   extern __shared__ __align__(16) float smem_f[];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int S = p.num_samples;
   const bool fine = p.fine_sampling != 0;
-  const int nout = 1 + (p.n_attention > 0 ? p.n_attention : 3);
+  const int nhead = 1 + (p.n_attention > 0 ? p.n_attention : 3);
+  const int nout = VD ? 1 + NFI_VIEW_FEATURES : nhead;  // decoder (layer 2) outputs
 
   float* W1t = smem_f;                   // [32][64]
   float* b1s = W1t + kC * kHid;          // [64]
-  float* W2t = b1s + kHid;               // [64][NOUT_PAD]
-  float* b2s = W2t + kHid * NOUT_PAD;    // [NOUT_PAD]
-  float* pal = b2s + NOUT_PAD;           // [48]
+  float* W2t = b1s + kHid;               // [64][NM]
+  float* b2s = W2t + kHid * NM;          // [NM]
+  float* pal = b2s + NM;                 // [48]
   float* Fall = pal + 48;                // [4][32][kFRow]
   float* Gall = Fall + kWarps * 32 * kFRow;  // [4][32][4]
   float* Dall = Gall + kWarps * 32 * 4;      // [4][32][kDRow]   (WGRAD)
-  float* Oall = Dall + (WGRAD ? kWarps * 32 * kDRow : 0);  // [4][32][NOUT_PAD]
-  float* Racc = Oall + (WGRAD ? kWarps * 32 * NOUT_PAD : 0);  // CTA reduction
+  float* Oall = Dall + (WGRAD ? kWarps * 32 * kDRow : 0);  // [4][32][NM]
+  float* Racc = Oall + (WGRAD ? kWarps * 32 * NM : 0);  // CTA reduction
+  constexpr int kRaccFloats = WGRAD ? kC * kHid + kHid + kHid * NM + NM : 0;
+  float* W3t = Racc + kRaccFloats;             // [32][NOUT_PAD]   (VD)
+  float* b3s = W3t + (VD ? kC * NOUT_PAD : 0);  // [NOUT_PAD]
+  float* xs = b3s + (VD ? NOUT_PAD : 0);        // [32][128] mapper features, column = thread
+  float* dxs = xs + (VD ? NFI_VIEW_FEATURES * kThreads : 0);  // [32][128] their gradient
+  float* R3 = dxs + (VD ? NFI_VIEW_FEATURES * kThreads : 0);  // [NOUT_PAD][32] + [NOUT_PAD]  (VD && WGRAD)
 
   const int tiles_x = (p.width + kTileW - 1) / kTileW;
   const int tiles_y = (p.height + kTileH - 1) / kTileH;
@@ -81,19 +97,26 @@ render_backward_simt(const nfi_render_params p, const nfi_render_grads g) {
 
   for (int i = tid; i < kC * kHid; i += kThreads) W1t[i] = p.w1[(i % kHid) * kC + i / kHid];
   for (int i = tid; i < kHid; i += kThreads) b1s[i] = p.b1[i];
-  for (int i = tid; i < kHid * NOUT_PAD; i += kThreads) {
-    const int j = i / NOUT_PAD, o = i % NOUT_PAD;
+  for (int i = tid; i < kHid * NM; i += kThreads) {
+    const int j = i / NM, o = i % NM;
     W2t[i] = (o < nout) ? p.w2[o * kHid + j] : 0.f;
   }
-  for (int i = tid; i < NOUT_PAD; i += kThreads) b2s[i] = (i < nout) ? p.b2[i] : 0.f;
+  for (int i = tid; i < NM; i += kThreads) b2s[i] = (i < nout) ? p.b2[i] : 0.f;
   for (int i = tid; i < 48; i += kThreads)
     pal[i] = (p.n_attention > 0 && i < p.n_attention * 3)
                  ? p.palette[(size_t)b * p.n_attention * 3 + i]
                  : 0.f;
   if (WGRAD)
-    for (int i = tid; i < kC * kHid + kHid + kHid * NOUT_PAD + NOUT_PAD; i += kThreads)
-      Racc[i] = 0.f;
-  __syncthreads();
+    for (int i = tid; i < kRaccFloats; i += kThreads) Racc[i] = 0.f;
+  if (VD) {
+    for (int i = tid; i < kC * NOUT_PAD; i += kThreads) {
+      const int c = i / NOUT_PAD, o = i % NOUT_PAD;
+      W3t[i] = (o >= 1 && o < nhead) ? p.w3[(o - 1) * NFI_VIEW_FEATURES + c] : 0.f;
+    }
+    for (int i = tid; i < NOUT_PAD; i += kThreads) b3s[i] = (i >= 1 && i < nhead) ? p.b3[i - 1] : 0.f;
+    if (WGRAD)
+      for (int i = tid; i < kC * NOUT_PAD + NOUT_PAD; i += kThreads) R3[i] = 0.f;
+  }
 
   int px, py;
   tile_pixel(tile_x, tile_y, warp, lane, px, py);
@@ -101,6 +124,20 @@ render_backward_simt(const nfi_render_params p, const nfi_render_grads g) {
   px = min(px, p.width - 1);
   py = min(py, p.height - 1);
   const size_t ray = ((size_t)b * p.height + py) * p.width + px;
+  if (VD) {
+#pragma unroll
+    for (int c4 = 0; c4 < NFI_VIEW_FEATURES / 4; ++c4) {
+      const float4 v = __ldg(reinterpret_cast<const float4*>(p.view_features +
+                                                             ray * NFI_VIEW_FEATURES) + c4);
+      xs[(4 * c4 + 0) * kThreads + tid] = v.x;
+      xs[(4 * c4 + 1) * kThreads + tid] = v.y;
+      xs[(4 * c4 + 2) * kThreads + tid] = v.z;
+      xs[(4 * c4 + 3) * kThreads + tid] = v.w;
+    }
+#pragma unroll
+    for (int c = 0; c < NFI_VIEW_FEATURES; ++c) dxs[c * kThreads + tid] = 0.f;
+  }
+  __syncthreads();
 
   Ray r;
   setup_ray(p, b, py, px, r);
@@ -118,7 +155,7 @@ render_backward_simt(const nfi_render_params p, const nfi_render_grads g) {
   float* Fw = Fall + warp * 32 * kFRow;
   float* Gw = Gall + warp * 32 * 4;
   float* Dw = Dall + warp * 32 * kDRow;
-  float* Ow = Oall + warp * 32 * NOUT_PAD;
+  float* Ow = Oall + warp * 32 * NM;
   const float* frow = Fw + lane * kFRow;
   const bool explicit_noise = (p.noise_mode == NFI_NOISE_EXPLICIT);
   const int R = p.plane_res;
@@ -154,14 +191,20 @@ render_backward_simt(const nfi_render_params p, const nfi_render_grads g) {
 
   // per-thread accumulators
   float acc_w1[WGRAD ? 64 : 1];  // dW1[j = 2*lane + (i>>5)][k = i&31]
-  float acc_w2[WGRAD ? 2 * NOUT_PAD : 1];
+  float acc_w2[WGRAD ? 2 * NM : 1];
   float acc_b1[2] = {0.f, 0.f};
-  float acc_b2 = 0.f;
+  float acc_b2[(NM + 31) / 32] = {};  // output o = lane + 32 * i
+  float acc_w3[(WGRAD && VD) ? NOUT_PAD : 1];  // dW3t[c = lane][o]
+  float acc_b3 = 0.f;
   if (WGRAD) {
 #pragma unroll
     for (int i = 0; i < 64; ++i) acc_w1[i] = 0.f;
 #pragma unroll
-    for (int i = 0; i < 2 * NOUT_PAD; ++i) acc_w2[i] = 0.f;
+    for (int i = 0; i < 2 * NM; ++i) acc_w2[i] = 0.f;
+    if (VD) {
+#pragma unroll
+      for (int i = 0; i < NOUT_PAD; ++i) acc_w3[i] = 0.f;
+    }
   }
   float accP[NA];  // sum_i w_i probs_i  (-> palette gradient)
 #pragma unroll
@@ -208,9 +251,16 @@ render_backward_simt(const nfi_render_params p, const nfi_render_grads g) {
     const float x0 = wx / p.scene_range, x1 = wy / p.scene_range, x2 = wz / p.scene_range;
     const float keep = (fabsf(x0) > 1.f || fabsf(x1) > 1.f || fabsf(x2) > 1.f) ? 0.f : 1.f;
     gather_features(planes_b, R, x0, x1, x2, Fw, lane);
-    float out[NOUT_PAD];
+    float mo[NM];  // decoder outputs
     float h[kHid];
-    mlp_forward<NOUT_PAD, true>(frow, W1t, b1s, W2t, b2s, out, h);
+    mlp_forward<NM, true>(frow, W1t, b1s, W2t, b2s, mo, h);
+    float out[NOUT_PAD];  // head inputs: distance-or-density, colour logits
+    if constexpr (VD) {
+      view_head<NOUT_PAD>(mo, xs + tid, W3t, b3s, out);
+    } else {
+#pragma unroll
+      for (int o = 0; o < NOUT_PAD; ++o) out[o] = mo[o];
+    }
     float sigma, cr, cg, cb;
     float probs[NOUT_PAD];
     field_head<NOUT_PAD>(out, fc, pal, keep, sigma, cr, cg, cb, probs);
@@ -231,22 +281,22 @@ render_backward_simt(const nfi_render_params p, const nfi_render_grads g) {
     T = T * (one_m_a + 1e-10f);
 
     // ---- field head, reverse
-    float dOut[NOUT_PAD];
+    float dHd[NOUT_PAD];
 #pragma unroll
-    for (int o = 0; o < NOUT_PAD; ++o) dOut[o] = 0.f;
+    for (int o = 0; o < NOUT_PAD; ++o) dHd[o] = 0.f;
     if (fc.use_sdf) {
       const float nd = -out[0];
       const float e = expf(-fabsf(nd) * fc.inv_beta);
       const float sg = (nd > 0.f) ? 1.f : ((nd < 0.f) ? -1.f : 0.f);
       // sigma = inv_alpha * keep * (0.5 + 0.5 sg (1 - e))
       // (analytic derivative also at nd == 0.0 exactly, see nfi_backward_pipe.cuh)
-      dOut[0] = dsig * (-(fc.inv_alpha * keep) * 0.5f * e * fc.inv_beta);
+      dHd[0] = dsig * (-(fc.inv_alpha * keep) * 0.5f * e * fc.inv_beta);
       acc_beta = fmaf(dsig, fc.inv_alpha * keep * (-0.5f * sg * e * fabsf(nd) * fc.inv_beta *
                                                    fc.inv_beta),
                       acc_beta);
       acc_alpha = fmaf(dsig, -sigma * fc.inv_alpha, acc_alpha);
     } else {
-      dOut[0] = dsig * keep * sigmoid_fast(out[0] - 1.f);
+      dHd[0] = dsig * keep * sigmoid_fast(out[0] - 1.f);
     }
     const float wr = w * g_r, wg = w * g_g, wb = w * g_b;
     if (fc.A > 0) {
@@ -264,17 +314,17 @@ render_backward_simt(const nfi_render_params p, const nfi_render_grads g) {
         accP[q] = fmaf(w, probs[q], accP[q]);
       }
 #pragma unroll
-      for (int q = 0; q < NA; ++q) dOut[1 + q] = probs[q] * (dp[q] - dot);
+      for (int q = 0; q < NA; ++q) dHd[1 + q] = probs[q] * (dp[q] - dot);
     } else {
       const float sr = (cr + 1.002f) / 2.004f, sg2 = (cg + 1.002f) / 2.004f,
                   sb = (cb + 1.002f) / 2.004f;
-      dOut[1] = wr * 2.004f * sr * (1.f - sr);
-      dOut[2] = wg * 2.004f * sg2 * (1.f - sg2);
-      dOut[3] = wb * 2.004f * sb * (1.f - sb);
+      dHd[1] = wr * 2.004f * sr * (1.f - sr);
+      dHd[2] = wg * 2.004f * sg2 * (1.f - sg2);
+      dHd[3] = wb * 2.004f * sb * (1.f - sb);
     }
     bool need = false;
 #pragma unroll
-    for (int o = 0; o < NOUT_PAD; ++o) need = need || (dOut[o] != 0.f);
+    for (int o = 0; o < NOUT_PAD; ++o) need = need || (dHd[o] != 0.f);
     float dpx = 0.f, dpy = 0.f, dpz = 0.f;  // dL/d world point
     if (extra == NFI_EXTRA_COORDS) {
       dpx = w * ge[0];
@@ -283,6 +333,57 @@ render_backward_simt(const nfi_render_params p, const nfi_render_grads g) {
     }
     __syncwarp();
     if (__any_sync(kFull, need)) {
+      float dOut[NM];  // dL/d decoder outputs
+      if constexpr (VD) {
+        // ---- mapper closure, reverse: logits = b3 + W3 y, y = leaky_relu(x_ray + features)
+        if (WGRAD) {
+#pragma unroll
+          for (int c = 0; c < NFI_VIEW_FEATURES; ++c) {
+            const float zc = xs[c * kThreads + tid] + mo[1 + c];
+            Dw[lane * kDRow + c] = zc > 0.f ? zc : zc * 0.2f;
+          }
+#pragma unroll
+          for (int o = 0; o < NOUT_PAD; ++o) Dw[lane * kDRow + 32 + o] = dHd[o];
+          __syncwarp();
+          // dW3[o][c] += dlogit[pt][o] * y[pt][c]   (this lane: c = lane)
+          for (int pt = 0; pt < 32; ++pt) {
+            const float yv = Dw[pt * kDRow + lane];
+#pragma unroll
+            for (int o4 = 0; o4 < NOUT_PAD / 4; ++o4) {
+              const float4 d4 = *reinterpret_cast<const float4*>(Dw + pt * kDRow + 32 + 4 * o4);
+              acc_w3[4 * o4 + 0] = fmaf(d4.x, yv, acc_w3[4 * o4 + 0]);
+              acc_w3[4 * o4 + 1] = fmaf(d4.y, yv, acc_w3[4 * o4 + 1]);
+              acc_w3[4 * o4 + 2] = fmaf(d4.z, yv, acc_w3[4 * o4 + 2]);
+              acc_w3[4 * o4 + 3] = fmaf(d4.w, yv, acc_w3[4 * o4 + 3]);
+            }
+            if (lane < NOUT_PAD) acc_b3 += Dw[pt * kDRow + 32 + lane];
+          }
+          __syncwarp();
+        }
+        dOut[0] = dHd[0];
+#pragma unroll
+        for (int o = 1 + NFI_VIEW_FEATURES; o < NM; ++o) dOut[o] = 0.f;
+#pragma unroll
+        for (int c = 0; c < NFI_VIEW_FEATURES; ++c) {
+          const float4* wr3 = reinterpret_cast<const float4*>(W3t + c * NOUT_PAD);
+          float dy = 0.f;
+#pragma unroll
+          for (int o4 = 0; o4 < NOUT_PAD / 4; ++o4) {
+            const float4 wv = wr3[o4];  // column 0 is zero: dHd[0] does not leak in
+            dy = fmaf(wv.x, dHd[4 * o4 + 0], dy);
+            dy = fmaf(wv.y, dHd[4 * o4 + 1], dy);
+            dy = fmaf(wv.z, dHd[4 * o4 + 2], dy);
+            dy = fmaf(wv.w, dHd[4 * o4 + 3], dy);
+          }
+          const float zc = xs[c * kThreads + tid] + mo[1 + c];
+          const float dz = zc > 0.f ? dy : dy * 0.2f;  // F.leaky_relu backward
+          dOut[1 + c] = dz;
+          dxs[c * kThreads + tid] += dz;
+        }
+      } else {
+#pragma unroll
+        for (int o = 0; o < NM; ++o) dOut[o] = dHd[o];
+      }
       // ---- layer 2 reverse: dA_j, then dpre_j = dA_j * sigmoid(pre_j)
       if (WGRAD) {
 #pragma unroll
@@ -295,33 +396,35 @@ render_backward_simt(const nfi_render_params p, const nfi_render_grads g) {
           *reinterpret_cast<float4*>(Dw + lane * kDRow + 4 * j4) = av;
         }
 #pragma unroll
-        for (int o4 = 0; o4 < NOUT_PAD / 4; ++o4)
-          *reinterpret_cast<float4*>(Ow + lane * NOUT_PAD + 4 * o4) =
+        for (int o4 = 0; o4 < NM / 4; ++o4)
+          *reinterpret_cast<float4*>(Ow + lane * NM + 4 * o4) =
               make_float4(dOut[4 * o4], dOut[4 * o4 + 1], dOut[4 * o4 + 2], dOut[4 * o4 + 3]);
         __syncwarp();
         // dW2[o][j] += dOut[pt][o] * a[pt][j]   (this lane: j = 2*lane, 2*lane+1)
         for (int pt = 0; pt < 32; ++pt) {
           const float2 aj = *reinterpret_cast<const float2*>(Dw + pt * kDRow + 2 * lane);
 #pragma unroll
-          for (int o4 = 0; o4 < NOUT_PAD / 4; ++o4) {
-            const float4 d4 = *reinterpret_cast<const float4*>(Ow + pt * NOUT_PAD + 4 * o4);
+          for (int o4 = 0; o4 < NM / 4; ++o4) {
+            const float4 d4 = *reinterpret_cast<const float4*>(Ow + pt * NM + 4 * o4);
             const float dv[4] = {d4.x, d4.y, d4.z, d4.w};
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
               acc_w2[4 * o4 + q] = fmaf(dv[q], aj.x, acc_w2[4 * o4 + q]);
-              acc_w2[NOUT_PAD + 4 * o4 + q] = fmaf(dv[q], aj.y, acc_w2[NOUT_PAD + 4 * o4 + q]);
+              acc_w2[NM + 4 * o4 + q] = fmaf(dv[q], aj.y, acc_w2[NM + 4 * o4 + q]);
             }
           }
-          if (lane < NOUT_PAD) acc_b2 += Ow[pt * NOUT_PAD + lane];
+#pragma unroll
+          for (int i = 0; i < (NM + 31) / 32; ++i)
+            if (lane + 32 * i < NM) acc_b2[i] += Ow[pt * NM + lane + 32 * i];
         }
         __syncwarp();
       }
 #pragma unroll
       for (int j = 0; j < kHid; ++j) {
-        const float4* wrow = reinterpret_cast<const float4*>(W2t + j * NOUT_PAD);
+        const float4* wrow = reinterpret_cast<const float4*>(W2t + j * NM);
         float dA = 0.f;
 #pragma unroll
-        for (int o4 = 0; o4 < NOUT_PAD / 4; ++o4) {
+        for (int o4 = 0; o4 < NM / 4; ++o4) {
           const float4 wv = wrow[o4];
           dA = fmaf(wv.x, dOut[4 * o4 + 0], dA);
           dA = fmaf(wv.y, dOut[4 * o4 + 1], dA);
@@ -381,7 +484,7 @@ render_backward_simt(const nfi_render_params p, const nfi_render_grads g) {
       // buffer in p.normals: [n_total][8] scalars then [n_total][32] dL/d(feature)
       if ((p.mlp_mode & 0x4000) && p.normals != nullptr && ray == (size_t)p.noise_seed && valid) {
         float* q8 = p.normals + (size_t)i * 8;
-        q8[0] = z; q8[1] = sigma; q8[2] = w; q8[3] = T; q8[4] = dsig; q8[5] = dOut[0];
+        q8[0] = z; q8[1] = sigma; q8[2] = w; q8[3] = T; q8[4] = dsig; q8[5] = dHd[0];
         q8[6] = s_i; q8[7] = delta;
         float* d32 = p.normals + (size_t)n_total * 8 + (size_t)i * 32;
         for (int k = 0; k < 32; ++k) d32[k] = Fw[lane * kFRow + k];
@@ -494,23 +597,44 @@ render_backward_simt(const nfi_render_params p, const nfi_render_grads g) {
       if (g.grad_alpha) atomicAdd(g.grad_alpha, sa);
     }
   }
+  if (VD && valid && g.grad_view_features != nullptr) {
+#pragma unroll
+    for (int c4 = 0; c4 < NFI_VIEW_FEATURES / 4; ++c4)
+      *reinterpret_cast<float4*>(g.grad_view_features + ray * NFI_VIEW_FEATURES + 4 * c4) =
+          make_float4(dxs[(4 * c4 + 0) * kThreads + tid], dxs[(4 * c4 + 1) * kThreads + tid],
+                      dxs[(4 * c4 + 2) * kThreads + tid], dxs[(4 * c4 + 3) * kThreads + tid]);
+  }
   if (WGRAD) {
     // CTA-level reduction in shared memory, then one atomic per entry per CTA
     float* R1 = Racc;                       // [64][32]
     float* Rb1 = R1 + kC * kHid;            // [64]
-    float* R2 = Rb1 + kHid;                 // [NOUT_PAD][64]
-    float* Rb2 = R2 + kHid * NOUT_PAD;      // [NOUT_PAD]
+    float* R2 = Rb1 + kHid;                 // [NM][64]
+    float* Rb2 = R2 + kHid * NM;            // [NM]
 #pragma unroll
     for (int i = 0; i < 64; ++i) atomicAdd(&R1[(2 * lane + (i >> 5)) * kC + (i & 31)], acc_w1[i]);
     atomicAdd(&Rb1[2 * lane], acc_b1[0]);
     atomicAdd(&Rb1[2 * lane + 1], acc_b1[1]);
 #pragma unroll
-    for (int o = 0; o < NOUT_PAD; ++o) {
+    for (int o = 0; o < NM; ++o) {
       atomicAdd(&R2[o * kHid + 2 * lane], acc_w2[o]);
-      atomicAdd(&R2[o * kHid + 2 * lane + 1], acc_w2[NOUT_PAD + o]);
+      atomicAdd(&R2[o * kHid + 2 * lane + 1], acc_w2[NM + o]);
     }
-    if (lane < NOUT_PAD) atomicAdd(&Rb2[lane], acc_b2);
+#pragma unroll
+    for (int i = 0; i < (NM + 31) / 32; ++i)
+      if (lane + 32 * i < NM) atomicAdd(&Rb2[lane + 32 * i], acc_b2[i]);
+    if (VD) {
+#pragma unroll
+      for (int o = 0; o < NOUT_PAD; ++o) atomicAdd(&R3[o * kC + lane], acc_w3[o]);
+      if (lane < NOUT_PAD) atomicAdd(&R3[kC * NOUT_PAD + lane], acc_b3);
+    }
     __syncthreads();
+    if (VD) {  // rows o = 1 .. nhead-1 of R3 are the logits a = o - 1
+      if (g.grad_w3)
+        for (int i = tid; i < (nhead - 1) * kC; i += kThreads) atomicAdd(g.grad_w3 + i, R3[kC + i]);
+      if (g.grad_b3)
+        for (int i = tid; i < nhead - 1; i += kThreads)
+          atomicAdd(g.grad_b3 + i, R3[kC * NOUT_PAD + 1 + i]);
+    }
     if (g.grad_w1)
       for (int i = tid; i < kC * kHid; i += kThreads) atomicAdd(g.grad_w1 + i, R1[i]);
     if (g.grad_b1)

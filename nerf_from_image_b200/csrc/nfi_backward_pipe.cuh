@@ -377,35 +377,57 @@ render_backward_pipe(const nfi_render_params p, const nfi_render_grads g,
           const uint32_t in6 = CAM ? __shfl_sync(kFull, cur_in, src) : 0u;
           const float4 d4v = *reinterpret_cast<const float4*>(Dw + src * 36 + 4 * kq);
           float gc0 = 0.f, gc1 = 0.f, gc2 = 0.f;
+          // nw texel clamped to R-2: all four taps of a plane exist at fixed offsets
+          const uint32_t dx = 8u;
+          const uint32_t dy = row_units;
+          uint32_t a00[3];
+          float fxs[3], fys[3];
 #pragma unroll
           for (int pl = 0; pl < 3; ++pl) {
-            const uint32_t o = __shfl_sync(kFull, tp.o[pl], src);
-            const float fx = __shfl_sync(kFull, tp.fx[pl], src);
-            const float fy = __shfl_sync(kFull, tp.fy[pl], src);
-            const uint32_t a00 = o | (uint32_t)kq;   // nw texel clamped to R-2: all four taps exist
-            const uint32_t dx = 8u;
-            const uint32_t dy = row_units;
-            const float gx0 = 1.f - fx, gy0 = 1.f - fy;
-            const float w00 = gx0 * gy0, w01 = fx * gy0, w10 = gx0 * fy, w11 = fx * fy;
-#ifdef NFI_BWD_NO_RED   // timing experiment: everything but the atomics themselves
-            if (false) {
-#else
-            if (gplanes_b != nullptr) {
-#endif
-              float* gp = gplanes_b;
-              red_add_v4(gp + (size_t)a00 * 4, d4v.x * w00, d4v.y * w00, d4v.z * w00, d4v.w * w00);
-              red_add_v4(gp + (size_t)(a00 + dx) * 4, d4v.x * w01, d4v.y * w01, d4v.z * w01,
-                         d4v.w * w01);
-              red_add_v4(gp + (size_t)(a00 + dy) * 4, d4v.x * w10, d4v.y * w10, d4v.z * w10,
-                         d4v.w * w10);
-              red_add_v4(gp + (size_t)(a00 + dy + dx) * 4, d4v.x * w11, d4v.y * w11, d4v.z * w11,
-                         d4v.w * w11);
+            a00[pl] = __shfl_sync(kFull, tp.o[pl], src) | (uint32_t)kq;
+            fxs[pl] = __shfl_sync(kFull, tp.fx[pl], src);
+            fys[pl] = __shfl_sync(kFull, tp.fy[pl], src);
+          }
+          // Pose gradient: the twelve texel re-reads of this point group are issued back to back,
+          // BEFORE the atomics (whose asm carries a memory clobber: a load written after one is
+          // not hoisted above it, which left three dependent L2 round trips per group exposed).
+          float4 v[3][4];
+          if (CAM) {
+#pragma unroll
+            for (int pl = 0; pl < 3; ++pl) {
+              v[pl][0] = ldg4(texel_ptr(planes_b, a00[pl]));
+              v[pl][1] = ldg4(texel_ptr(planes_b, a00[pl] + dx));
+              v[pl][2] = ldg4(texel_ptr(planes_b, a00[pl] + dy));
+              v[pl][3] = ldg4(texel_ptr(planes_b, a00[pl] + dy + dx));
             }
-            if (CAM) {
-              const float4 v00 = ldg4(texel_ptr(planes_b, a00));
-              const float4 v01 = ldg4(texel_ptr(planes_b, a00 + dx));
-              const float4 v10 = ldg4(texel_ptr(planes_b, a00 + dy));
-              const float4 v11 = ldg4(texel_ptr(planes_b, a00 + dy + dx));
+          }
+#ifdef NFI_BWD_NO_RED   // timing experiment: everything but the atomics themselves
+          if (false) {
+#else
+          if (gplanes_b != nullptr) {
+#endif
+#pragma unroll
+            for (int pl = 0; pl < 3; ++pl) {
+              const float gx0 = 1.f - fxs[pl], gy0 = 1.f - fys[pl];
+              const float w00 = gx0 * gy0, w01 = fxs[pl] * gy0, w10 = gx0 * fys[pl],
+                          w11 = fxs[pl] * fys[pl];
+              float* gp = gplanes_b;
+              red_add_v4(gp + (size_t)a00[pl] * 4, d4v.x * w00, d4v.y * w00, d4v.z * w00,
+                         d4v.w * w00);
+              red_add_v4(gp + (size_t)(a00[pl] + dx) * 4, d4v.x * w01, d4v.y * w01, d4v.z * w01,
+                         d4v.w * w01);
+              red_add_v4(gp + (size_t)(a00[pl] + dy) * 4, d4v.x * w10, d4v.y * w10, d4v.z * w10,
+                         d4v.w * w10);
+              red_add_v4(gp + (size_t)(a00[pl] + dy + dx) * 4, d4v.x * w11, d4v.y * w11,
+                         d4v.z * w11, d4v.w * w11);
+            }
+          }
+          if (CAM) {
+#pragma unroll
+            for (int pl = 0; pl < 3; ++pl) {
+              const float fx = fxs[pl], fy = fys[pl];
+              const float gx0 = 1.f - fx, gy0 = 1.f - fy;
+              const float4 v00 = v[pl][0], v01 = v[pl][1], v10 = v[pl][2], v11 = v[pl][3];
               // d/dix = (ne-nw)*gy0 + (se-sw)*gy1 ; d/diy = (sw-nw)*gx0 + (se-ne)*gx1
               float gx = 0.f, gy = 0.f;
 #define NFI_ACC(cmp)                                                              \

@@ -363,6 +363,40 @@ __device__ __forceinline__ void sdf_gradient(float (&h)[kHid], const float* __re
   }
 }
 
+// ViewDirectionMapper.mapper_closure (models/generator.py:242-251): colour logits from the
+// decoder's 32 feature outputs and the ray's mapper features,
+//   hd[1 + a] = b3[a] + sum_c w3[a][c] * leaky_relu(x_ray[c] + out[1 + c], 0.2),  hd[0] = out[0].
+// `xcol` is this thread's column of the [32][kThreads] mapper-feature tile, W3t is [32][NOUT_PAD]
+// with column 0 zero, b3s[0] = 0.
+template <int NOUT_PAD, int NM>
+__device__ __forceinline__ void view_head(const float (&out)[NM], const float* __restrict__ xcol,
+                                          const float* __restrict__ W3t,
+                                          const float* __restrict__ b3s, float (&hd)[NOUT_PAD]) {
+#pragma unroll
+  for (int o4 = 0; o4 < NOUT_PAD / 4; ++o4) {
+    const float4 bv = *reinterpret_cast<const float4*>(b3s + 4 * o4);
+    hd[4 * o4 + 0] = bv.x;
+    hd[4 * o4 + 1] = bv.y;
+    hd[4 * o4 + 2] = bv.z;
+    hd[4 * o4 + 3] = bv.w;
+  }
+#pragma unroll
+  for (int c = 0; c < NFI_VIEW_FEATURES; ++c) {
+    const float z = xcol[c * kThreads] + out[1 + c];
+    const float y = z > 0.f ? z : z * 0.2f;
+    const float4* wr = reinterpret_cast<const float4*>(W3t + c * NOUT_PAD);
+#pragma unroll
+    for (int o4 = 0; o4 < NOUT_PAD / 4; ++o4) {
+      const float4 w = wr[o4];
+      hd[4 * o4 + 0] = fmaf(w.x, y, hd[4 * o4 + 0]);
+      hd[4 * o4 + 1] = fmaf(w.y, y, hd[4 * o4 + 1]);
+      hd[4 * o4 + 2] = fmaf(w.z, y, hd[4 * o4 + 2]);
+      hd[4 * o4 + 3] = fmaf(w.w, y, hd[4 * o4 + 3]);
+    }
+  }
+  hd[0] = out[0];
+}
+
 // Density and colour from the decoder outputs (models/generator.py:625-679).
 struct FieldConst {
   float inv_beta;   // 1 / beta

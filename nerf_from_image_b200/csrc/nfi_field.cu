@@ -44,9 +44,10 @@ sample_field_simt(const nfi_render_params p, const nfi_sample_params io) {
     sm.F = q; q += kWarps * 32 * kFRow;
     sm.G = q;
     sm.colA = sm.colB = nullptr;
+    sm.W3t = sm.b3 = sm.xs = nullptr;
   }
   const int b = blockIdx.y;
-  load_weights_smem<NOUT_PAD>(p, b, sm, tid);
+  load_weights_smem<NOUT_PAD>(p, b, sm, tid, 1 + (p.n_attention > 0 ? p.n_attention : 3));
   __syncthreads();
 
   const long long n = io.n_points;

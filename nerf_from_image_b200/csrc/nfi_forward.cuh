@@ -70,11 +70,18 @@ struct FwdSmem {
   float* G;    // [4][3][32][kFRow]  (normals only)
   float* colA; // [S][128]
   float* colB; // [S][128]
+  float* W3t;  // [32][NOUT_PAD]  (view-direction conditioning only; column o = logit o-1)
+  float* b3;   // [NOUT_PAD]
+  float* xs;   // [32][128] per-ray mapper features, column = thread
 };
 
+constexpr int kViewMlpPad = 36;  // decoder outputs 1 + NFI_VIEW_FEATURES, padded to a float4 multiple
+
 __host__ __device__ inline size_t fwd_smem_floats(int nout_pad, int S, bool fine,
-                                                  bool normals = false) {
-  size_t n = kC * kHid + kHid + kHid * nout_pad + nout_pad + 48 + kWarps * 32 * kFRow;
+                                                  bool normals = false, bool viewdir = false) {
+  const int nm = viewdir ? kViewMlpPad : nout_pad;
+  size_t n = kC * kHid + kHid + kHid * nm + nm + 48 + kWarps * 32 * kFRow;
+  if (viewdir) n += kC * nout_pad + nout_pad + NFI_VIEW_FEATURES * kThreads;
   if (normals) n += kWarps * 3 * 32 * kFRow;  // d features / d coords, per warp
   if (fine) n += 2 * (size_t)S * kThreads;
   return n;
@@ -88,8 +95,7 @@ __host__ __device__ inline size_t fwd_scratch_floats_per_cta(int S, int ne_store
 
 template <int NOUT_PAD>
 __device__ __forceinline__ void load_weights_smem(const nfi_render_params& p, int b,
-                                                  const FwdSmem& sm, int tid) {
-  const int nout = 1 + (p.n_attention > 0 ? p.n_attention : 3);
+                                                  const FwdSmem& sm, int tid, int nout) {
   for (int i = tid; i < kC * kHid; i += kThreads) {
     const int k = i / kHid, j = i % kHid;
     sm.W1t[i] = p.w1[j * kC + k];
@@ -110,9 +116,13 @@ __device__ __forceinline__ void load_weights_smem(const nfi_render_params& p, in
 // (models/generator.py:599-623: normalised analytic gradient of the SDF with respect to the
 // sample position; lib/nerf_utils.py:146-148: weighted with the detached weights), carried
 // as three more "extras" after the EXTRA ones.
-template <int NOUT_PAD, int EXTRA, bool FINE, bool NORM = false>
+// VD: view-direction conditioning (--use_viewdir; models/generator.py:189-253,662-663): the
+// decoder's second layer emits 1 + 32 values and the colour logits are
+// w3 . leaky_relu(view_features[ray] + features, 0.2) + b3.
+template <int NOUT_PAD, int EXTRA, bool FINE, bool NORM = false, bool VD = false>
 __global__ void __launch_bounds__(kThreads)
 render_forward_simt(const nfi_render_params p) {
+  constexpr int NM = VD ? kViewMlpPad : NOUT_PAD;  // decoder (layer 2) outputs, padded
   constexpr int NE0 = (EXTRA == 0) ? 0 : (EXTRA == 1 ? 3 : NOUT_PAD - 1);
   constexpr int NE = NE0 + (NORM ? 3 : 0);
   constexpr int NES0 = (EXTRA == 2) ? NOUT_PAD - 1 : 0;
@@ -126,9 +136,12 @@ render_forward_simt(const nfi_render_params p) {
     float* q = smem_f;
     sm.W1t = q; q += kC * kHid;
     sm.b1 = q; q += kHid;
-    sm.W2t = q; q += kHid * NOUT_PAD;
-    sm.b2 = q; q += NOUT_PAD;
+    sm.W2t = q; q += kHid * NM;
+    sm.b2 = q; q += NM;
     sm.pal = q; q += 48;
+    sm.W3t = q; q += VD ? kC * NOUT_PAD : 0;
+    sm.b3 = q; q += VD ? NOUT_PAD : 0;
+    sm.xs = q; q += VD ? NFI_VIEW_FEATURES * kThreads : 0;
     sm.F = q; q += kWarps * 32 * kFRow;
     sm.G = q; q += NORM ? kWarps * 3 * 32 * kFRow : 0;
     sm.colA = q; q += FINE ? (size_t)S * kThreads : 0;
@@ -141,8 +154,16 @@ render_forward_simt(const nfi_render_params p) {
   const int trem = cta % (tiles_x * tiles_y);
   const int tile_y = trem / tiles_x, tile_x = trem % tiles_x;
 
-  load_weights_smem<NOUT_PAD>(p, b, sm, tid);
-  __syncthreads();
+  const int nhead = 1 + (p.n_attention > 0 ? p.n_attention : 3);
+  load_weights_smem<NM>(p, b, sm, tid, VD ? 1 + NFI_VIEW_FEATURES : nhead);
+  if (VD) {
+    for (int i = tid; i < kC * NOUT_PAD; i += kThreads) {
+      const int c = i / NOUT_PAD, o = i % NOUT_PAD;
+      sm.W3t[i] = (o >= 1 && o < nhead) ? p.w3[(o - 1) * NFI_VIEW_FEATURES + c] : 0.f;
+    }
+    for (int i = tid; i < NOUT_PAD; i += kThreads)
+      sm.b3[i] = (i >= 1 && i < nhead) ? p.b3[i - 1] : 0.f;
+  }
 
   int px, py;
   tile_pixel(tile_x, tile_y, warp, lane, px, py);
@@ -150,6 +171,18 @@ render_forward_simt(const nfi_render_params p) {
   px = min(px, p.width - 1);
   py = min(py, p.height - 1);
   const size_t ray = ((size_t)b * p.height + py) * p.width + px;
+  if (VD) {
+#pragma unroll
+    for (int c4 = 0; c4 < NFI_VIEW_FEATURES / 4; ++c4) {
+      const float4 v = __ldg(reinterpret_cast<const float4*>(p.view_features +
+                                                             ray * NFI_VIEW_FEATURES) + c4);
+      sm.xs[(4 * c4 + 0) * kThreads + tid] = v.x;
+      sm.xs[(4 * c4 + 1) * kThreads + tid] = v.y;
+      sm.xs[(4 * c4 + 2) * kThreads + tid] = v.z;
+      sm.xs[(4 * c4 + 3) * kThreads + tid] = v.w;
+    }
+  }
+  __syncthreads();
 
   Ray r;
   setup_ray(p, b, py, px, r);
@@ -187,14 +220,14 @@ render_forward_simt(const nfi_render_params p) {
     const float x0 = wx / p.scene_range, x1 = wy / p.scene_range, x2 = wz / p.scene_range;
     const float keep =
         (fabsf(x0) > 1.f || fabsf(x1) > 1.f || fabsf(x2) > 1.f) ? 0.f : 1.f;
-    float out[NOUT_PAD];
+    float out[NM];
     float h[kHid];
     if (NORM) {
       float* Gw = sm.G + warp * 3 * 32 * kFRow;
       gather_features_grad(planes_b, p.plane_res, x0, x1, x2, Fw, Gw, lane);
-      mlp_forward<NOUT_PAD, true>(frow, sm.W1t, sm.b1, sm.W2t, sm.b2, out, h);  // h = pre-activations
+      mlp_forward<NM, true>(frow, sm.W1t, sm.b1, sm.W2t, sm.b2, out, h);  // h = pre-activations
       float n0, n1, n2;
-      sdf_gradient<NOUT_PAD>(h, sm.W1t, sm.W2t, Gw, lane, n0, n1, n2);
+      sdf_gradient<NM>(h, sm.W1t, sm.W2t, Gw, lane, n0, n1, n2);
       // common factors of the chain: (R-1)/2 per texel unit, 1/3 plane mean, 1/scene_range
       const float sc = 0.5f * (float)(p.plane_res - 1) / (3.f * p.scene_range);
       n0 *= sc;
@@ -206,11 +239,17 @@ render_forward_simt(const nfi_render_params p) {
       ex[NE0 + 2] = n2 * inv;
     } else {
       gather_features(planes_b, p.plane_res, x0, x1, x2, Fw, lane);
-      mlp_forward<NOUT_PAD, false>(frow, sm.W1t, sm.b1, sm.W2t, sm.b2, out, h);
+      mlp_forward<NM, false>(frow, sm.W1t, sm.b1, sm.W2t, sm.b2, out, h);
     }
     __syncwarp();
     float probs[NOUT_PAD];
-    field_head<NOUT_PAD>(out, fc, sm.pal, keep, sigma, cr, cg, cb, probs);
+    if constexpr (VD) {
+      float hd[NOUT_PAD];
+      view_head<NOUT_PAD>(out, sm.xs + tid, sm.W3t, sm.b3, hd);
+      field_head<NOUT_PAD>(hd, fc, sm.pal, keep, sigma, cr, cg, cb, probs);
+    } else {
+      field_head<NOUT_PAD>(out, fc, sm.pal, keep, sigma, cr, cg, cb, probs);
+    }
     if (EXTRA == 1) {
       ex[0] = wx;
       ex[1] = wy;

@@ -12,6 +12,7 @@
 #include "nfi_forward_tc.cuh"
 #include "nfi_field_launch.h"
 #include "nfi_pipe_launch.h"
+#include "nfi_viewdir_launch.h"
 #include "nfi_render.h"
 #include "nfi_heads.h"
 #include "nfi_heads_launch.h"
@@ -58,6 +59,8 @@ int check_params(const nfi_render_params* p) {
     return fail("planes / decoder weights / tform_cam2world must be given");
   if (p->n_attention > 0 && !p->palette) return fail("palette missing (attention_values > 0)");
   if (p->use_sdf && (!p->beta || !p->alpha)) return fail("use_sdf needs beta and alpha");
+  if (p->view_features && (!p->w3 || !p->b3))
+    return fail("view_features given without w3 / b3 (ViewDirectionMapper.output)");
   if (p->noise_mode == NFI_NOISE_EXPLICIT) {
     if (!p->noise_t) return fail("noise_t missing (randomize=True)");
     if (p->fine_sampling && !p->noise_u) return fail("noise_u missing (fine_sampling)");
@@ -98,6 +101,7 @@ size_t num_tc_ctas(const nfi_render_params* p) {  // persistent grid: at most on
 
 // Can the tensor-core kernel take this configuration?
 bool tc_supported(const nfi_render_params* p) {
+  if (p->view_features) return false;  // view-direction conditioning (CARLA): SIMT kernels
   if (p->compute_normals && !(p->mlp_mode & 0x1000)) return false;  // evaluation-only: SIMT kernel
   const int mode = p->mlp_mode & 0xff;
   const bool pipe_mode = (mode == NFI_MLP_TC_PIPE || mode == NFI_MLP_AUTO || mode == NFI_MLP_TC_WARPSPEC);
@@ -420,6 +424,11 @@ int nfi_render_forward(const nfi_render_params* params, void* stream) {
     if (!p.peer_rgb[q] || !p.peer_depth[q] || !p.peer_mask[q]) return fail("peer output pointer is NULL");
   if (want_tc) return launch_fwd_tc(p, np, st);
   if (p.n_peers > 0) return fail("peer outputs (n_peers > 0) need the pipelined kernel");
+  if (p.view_features) {
+    nfi_render_params pv = p;  // SIMT scratch starts after the weight-image header
+    if (pv.workspace) pv.workspace = (unsigned char*)pv.workspace + kWeightImageBytes;
+    return nfi::launch_forward_viewdir(pv, np, wants_normals(params), st, g_err, sizeof(g_err));
+  }
   const size_t smem =
       nfi::fwd_smem_floats(np, p.num_samples, p.fine_sampling != 0, wants_normals(params)) *
       sizeof(float);
@@ -485,6 +494,10 @@ int nfi_render_backward(const nfi_render_params* params, const nfi_render_grads*
   // setting, run.py:628-629), no semantics output, S within the pipelined kernels' envelope,
   // and a workspace for the two weight images.  Everything else: render_backward_simt.
   const int mode = p.mlp_mode & 0xff;
+  if (p.view_features)
+    return nfi::launch_backward_viewdir(p, g, nout_pad_of(params), st, g_err, sizeof(g_err));
+  if (g.grad_view_features || g.grad_w3 || g.grad_b3)
+    return fail("grad_view_features / grad_w3 / grad_b3 need params->view_features");
   const bool wgrad = g.grad_w1 || g.grad_b1 || g.grad_w2 || g.grad_b2;
   const bool tc_ok = !wgrad && mode != NFI_MLP_FP32_SIMT && p.extra_mode != NFI_EXTRA_SEMANTICS &&
                      p.num_samples <= 128 && p.num_samples % 4 == 0 && p.workspace != nullptr &&
@@ -607,6 +620,9 @@ int nfi_render_forward_host(const nfi_render_params* hp, int32_t device) {
   // streams: while chunk c is re-laid-out and rendered, chunk c+1's planes and
   // noise are already crossing PCIe, and chunk c-1's rgb/depth/mask go back.
   if (hp == nullptr) return fail("params is NULL");
+  if (hp->view_features)
+    return fail("view-direction conditioning is not offered through the host entry point "
+                "(use nfi_render_forward)");
   NFI_CUDA(cudaSetDevice(device));
   cudaStream_t st = nullptr, cp = nullptr;
   // Everything acquired below is released on the single exit path at the bottom (streams,

@@ -78,7 +78,7 @@ def planes_from_channel_last(planes_cl):
 
 def _make_params(cfg, planes_cl, w1, b1, w2, b2, palette, beta, alpha, c2w,
                  focal, center, bbox, height, width, S, noise_t, noise_u,
-                 extra_mode):
+                 extra_mode, view_feat=None, w3=None, b3=None):
     p = _lib.RenderParams()
     B, _, R, _, _ = planes_cl.shape
     p.batch, p.height, p.width, p.num_samples = B, height, width, S
@@ -97,14 +97,23 @@ def _make_params(cfg, planes_cl, w1, b1, w2, b2, palette, beta, alpha, c2w,
     p.palette, p.beta, p.alpha = _ptr(palette), _ptr(beta), _ptr(alpha)
     p.c2w, p.focal, p.center, p.bbox = _ptr(c2w), _ptr(focal), _ptr(center), _ptr(bbox)
     p.noise_t, p.noise_u = _ptr(noise_t), _ptr(noise_u)
+    p.view_features, p.w3, p.b3 = _ptr(view_feat), _ptr(w3), _ptr(b3)
     return p
 
 
 def _check_shapes(cfg, planes, w1, b1, w2, b2, palette, c2w, focal, center,
-                  bbox, height, width, S, noise_t, noise_u, channel_last=False):
+                  bbox, height, width, S, noise_t, noise_u, channel_last=False,
+                  view_feat=None, w3=None, b3=None):
     B = planes.shape[0]
     A = cfg.attention_values
     nout = 1 + (A if A > 0 else 3)
+    if view_feat is not None:
+        # --use_viewdir: the decoder emits 1 + 32 values, the colour logits come from the
+        # mapper's output layer (generator.py:376-377,395-396)
+        assert tuple(view_feat.shape) == (B, height, width, 32), view_feat.shape
+        assert w3 is not None and tuple(w3.shape) == (nout - 1, 32), (None if w3 is None else w3.shape)
+        assert b3 is not None and tuple(b3.shape) == (nout - 1,)
+        nout = 33
     if channel_last:
         assert (planes.dim() == 5 and planes.shape[1] == 3 and planes.shape[4] == 32
                 and planes.shape[2] == planes.shape[3]), planes.shape
@@ -124,14 +133,15 @@ def _check_shapes(cfg, planes, w1, b1, w2, b2, palette, c2w, focal, center,
         assert tuple(noise_t.shape) == (B, height, width, S), noise_t.shape
         if cfg.fine_sampling:
             assert noise_u is not None and tuple(noise_u.shape) == (B * height * width, S)
-    for t in (planes, w1, b1, w2, b2, palette, c2w, focal, center, bbox, noise_t, noise_u):
+    for t in (planes, w1, b1, w2, b2, palette, c2w, focal, center, bbox, noise_t, noise_u,
+              view_feat, w3, b3):
         if t is not None and not t.is_cuda:
             raise _lib.NfiError('the fused renderer only runs on CUDA tensors '
                                 '(there is no CPU path)')
 
 
 _FIELD_KEYS = ('w1', 'b1', 'w2', 'b2', 'palette', 'beta', 'alpha', 'c2w', 'focal', 'center',
-               'bbox', 'noise_t', 'noise_u')
+               'bbox', 'noise_t', 'noise_u', 'view_feat', 'w3', 'b3')
 
 
 class FusedTriplaneRender(torch.autograd.Function):
@@ -142,17 +152,19 @@ class FusedTriplaneRender(torch.autograd.Function):
     focal [B]|None; center [B,2]|None; bbox [B,2,2]|None.  ``noise_t`` /
     ``noise_u`` None selects the reference's ``randomize=False`` behaviour.
     ``extra_mode``: 0 none, 1 coords, 2 semantics.  ``cam_grad`` False is the
-    reference's ``force_no_cam_grad``.
+    reference's ``force_no_cam_grad``.  ``view_feat`` [B,H,W,32] / ``w3`` [A,32] / ``b3`` [A]:
+    the ViewDirectionMapper's per-ray trunk output and its output layer (--use_viewdir,
+    generator.py:189-253); w2 / b2 then have 33 rows.
     """
 
     @staticmethod
     def forward(ctx, planes, w1, b1, w2, b2, palette, beta, alpha, c2w, focal,
                 center, bbox, cfg, height, width, S, noise_t, noise_u,
                 extra_mode, cam_grad, compute_normals=False, out=None,
-                planes_layout='channel_first', peers=None):
+                planes_layout='channel_first', peers=None, view_feat=None, w3=None, b3=None):
         channel_last = planes_layout == 'channel_last'
         _check_shapes(cfg, planes, w1, b1, w2, b2, palette, c2w, focal, center,
-                      bbox, height, width, S, noise_t, noise_u, channel_last)
+                      bbox, height, width, S, noise_t, noise_u, channel_last, view_feat, w3, b3)
         lib = _lib.load()
         dev = planes.device
         with torch.cuda.device(dev):
@@ -169,7 +181,10 @@ class FusedTriplaneRender(torch.autograd.Function):
                      focal=_f32c(focal.detach(), 'focal_length') if focal is not None else None,
                      center=_f32c(center.detach(), 'center') if center is not None else None,
                      bbox=_f32c(bbox.detach(), 'bbox') if bbox is not None else None,
-                     noise_t=_f32c(noise_t, 'noise_t'), noise_u=_f32c(noise_u, 'noise_u'))
+                     noise_t=_f32c(noise_t, 'noise_t'), noise_u=_f32c(noise_u, 'noise_u'),
+                     view_feat=_f32c(view_feat.detach(), 'view_feat') if view_feat is not None else None,
+                     w3=_f32c(w3.detach(), 'w3') if view_feat is not None else None,
+                     b3=_f32c(b3.detach(), 'b3') if view_feat is not None else None)
             B = planes.shape[0]
             A = cfg.attention_values
             needs_grad = any(ctx.needs_input_grad)
@@ -204,7 +219,8 @@ class FusedTriplaneRender(torch.autograd.Function):
             p = _make_params(cfg, planes_cl, t['w1'], t['b1'], t['w2'], t['b2'],
                              t['palette'], t['beta'], t['alpha'], t['c2w'],
                              t['focal'], t['center'], t['bbox'], height, width,
-                             S, t['noise_t'], t['noise_u'], extra_mode)
+                             S, t['noise_t'], t['noise_u'], extra_mode,
+                             t['view_feat'], t['w3'], t['b3'])
             p.rgb, p.depth, p.mask, p.extra = _ptr(rgb), _ptr(depth), _ptr(mask), _ptr(extra)
             p.z_fine = _ptr(z_fine)
             if normals is not None:
@@ -275,6 +291,7 @@ class FusedTriplaneRender(torch.autograd.Function):
         need = ctx.needs_input_grad
         (n_planes, n_w1, n_b1, n_w2, n_b2, n_pal, n_beta, n_alpha, n_c2w,
          n_focal, n_center, n_bbox) = need[:12]
+        n_vf, n_w3, n_b3 = need[24:27]
         rgb, mask, extra = saved['out_rgb'], saved['out_mask'], saved.get('out_extra')
         A = cfg.attention_values
         with torch.cuda.device(dev):
@@ -300,6 +317,11 @@ class FusedTriplaneRender(torch.autograd.Function):
             cam = ctx.cam_grad and (n_c2w or n_focal or n_center or n_bbox)
             go = torch.zeros(rgb.shape, device=dev) if cam else None
             gd = torch.zeros(rgb.shape, device=dev) if cam else None
+            vd = t['view_feat'] is not None
+            gvf = z(t['view_feat']) if (vd and n_vf) else None
+            gw3 = z(t['w3']) if (vd and n_w3) else None
+            gb3 = z(t['b3']) if (vd and n_b3) else None
+            g.grad_view_features, g.grad_w3, g.grad_b3 = _ptr(gvf), _ptr(gw3), _ptr(gb3)
             (g.grad_planes, g.grad_w1, g.grad_b1, g.grad_w2, g.grad_b2,
              g.grad_palette, g.grad_beta, g.grad_alpha, g.grad_origins,
              g.grad_dirs) = (_ptr(gp_cl), _ptr(gw1), _ptr(gb1), _ptr(gw2),
@@ -308,7 +330,8 @@ class FusedTriplaneRender(torch.autograd.Function):
             p = _make_params(cfg, planes_cl, t['w1'], t['b1'], t['w2'], t['b2'],
                              t['palette'], t['beta'], t['alpha'], t['c2w'],
                              t['focal'], t['center'], t['bbox'], height, width,
-                             S, t['noise_t'], t['noise_u'], ctx.extra_mode)
+                             S, t['noise_t'], t['noise_u'], ctx.extra_mode,
+                             t['view_feat'], t['w3'], t['b3'])
             p.rgb, p.depth, p.mask = _ptr(rgb), _ptr(mask), _ptr(mask)  # unused
             p.extra = _ptr(extra)
             p.z_fine = _ptr(z_fine)
@@ -352,13 +375,14 @@ class FusedTriplaneRender(torch.autograd.Function):
                     gbbox = res.pop(0)
         return (gplanes, gw1, gb1, gw2, gb2, gpal, gbeta, galpha, gc2w, gfocal,
                 gcenter, gbbox, None, None, None, None, None, None, None, None, None, None,
-                None, None)
+                None, None, gvf, gw3, gb3)
 
 
 def fused_render(planes, w1, b1, w2, b2, palette, beta, alpha, c2w, focal,
                  center, bbox, cfg, height, width, num_samples, noise_t=None,
                  noise_u=None, extra_mode=_lib.EXTRA_NONE, cam_grad=True,
-                 compute_normals=False, out=None, planes_layout='channel_first', peers=None):
+                 compute_normals=False, out=None, planes_layout='channel_first', peers=None,
+                 view=None):
     """Functional form; returns (rgb, depth, mask, extra|None), with
     ``compute_normals`` (rgb, depth, mask, extra|None, normals).  ``out=(rgb, depth,
     mask)`` makes the kernel write into caller-owned tensors (see parallel.py).
@@ -367,6 +391,8 @@ def fused_render(planes, w1, b1, w2, b2, palette, beta, alpha, c2w, focal,
     emits them (used as they are; a plane gradient comes back in the same layout).
     ``peers``: list of (rgb, depth, mask) device ADDRESSES of this rank's slices in the other
     ranks' buffers; the kernel stores its tiles there too (parallel.PeerExchange).
+    ``view``: (view_features [B,H,W,32], w3 [A,32], b3 [A]) switches on the view-direction
+    conditioning of the CARLA models (--use_viewdir; fp32 SIMT kernels).
 
     The kernels compute in fp32 like the reference's render (run.py:59-60).  Under
     autocast (BASELINE config 4 trains the synthesis network in bf16) the field tensors
@@ -377,10 +403,11 @@ def fused_render(planes, w1, b1, w2, b2, palette, beta, alpha, c2w, focal,
     planes, w1, b1, w2, b2, palette, beta, alpha = map(f32, (planes, w1, b1, w2, b2, palette,
                                                               beta, alpha))
     c2w, focal, center, bbox = map(f32, (c2w, focal, center, bbox))
+    view_feat, w3, b3 = map(f32, view) if view is not None else (None, None, None)
     rgb, depth, mask, extra, normals = FusedTriplaneRender.apply(
         planes, w1, b1, w2, b2, palette, beta, alpha, c2w, focal, center, bbox,
         cfg, height, width, num_samples, noise_t, noise_u, extra_mode, cam_grad,
-        compute_normals, out, planes_layout, peers)
+        compute_normals, out, planes_layout, peers, view_feat, w3, b3)
     extra = extra if extra_mode != _lib.EXTRA_NONE else None
     if compute_normals:
         return rgb, depth, mask, extra, normals

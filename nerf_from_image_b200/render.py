@@ -30,6 +30,7 @@ from torch import nn
 
 from . import _lib
 from .fused import RenderConfig, fused_render
+from .rays import unit_rays
 
 args = None
 dataset_config = None
@@ -107,6 +108,23 @@ def _join_planes(xy, xz, yz):
     return torch.stack((xy, xz, yz), dim=1)
 
 
+def extract_view(target_model, sampler):
+    """--use_viewdir (generator.py:189-253,468-469,662-663): the per-ray features ``x``
+    [B,H,W,1,32] the ViewDirectionMapper trunk produced from the view directions (captured by
+    the mapper closure the sampler closes over) and the effective weights of its output layer.
+    Returns (view_features [B,H,W,32], w3, b3)."""
+    if isinstance(sampler, dict):
+        return sampler['view_features'], sampler['w3'], sampler['b3']
+    mapper_closure = _closure_vars(sampler).get('viewdir_mapper_closure')
+    if mapper_closure is None:
+        raise _lib.NfiError("args.use_viewdir is set but target_model's sampler carries no "
+                            'viewdir_mapper_closure (generator.py:468-469): was the model built '
+                            'with use_viewdir=True?')
+    x = _closure_vars(mapper_closure)['x']
+    out = target_model.viewdir_mapper.output
+    return x.squeeze(-2), out.weight * out.weight_gain, out.bias * out.bias_gain
+
+
 def extract_field(target_model, sampler):
     """Pulls (planes, palette, w1, b1, w2, b2, beta, alpha) out of the
     reference Generator and the sampler closure it returned.
@@ -160,10 +178,6 @@ def render(target_model,
     if args is None or dataset_config is None:
         raise RuntimeError('call nerf_from_image_b200.render.configure(args, '
                            'dataset_config) first')
-    if args.use_viewdir:
-        raise NotImplementedError(
-            '--use_viewdir (CARLA only, generator.py:189-253) is outside the '
-            'fused path (SURVEY.md section 8f N4)')
     if 'bbox' in extra_model_outputs and compute_coords:
         # models/generator.py:640-657: the closure adds a 100 x box-frame debug density to
         # sigma when coords are requested together with 'bbox'; the fused kernels render
@@ -184,20 +198,29 @@ def render(target_model,
     if randomize:
         noise_t = torch.rand(B, height, width, S, device=dev)
 
+    viewdirs = None
+    if args.use_viewdir:
+        # run.py:196,210-217: the model is conditioned on the unit ray directions (detached under
+        # force_no_cam_grad); its ViewDirectionMapper trunk runs once per ray in the model's own
+        # forward, the per-sample part (mapper closure) inside the fused kernels
+        _, dirs = unit_rays(height, width, tform_cam2world, focal_length, center, bbox)
+        viewdirs = (dirs.detach() if force_no_cam_grad else dirs).unsqueeze(-2)
+
     requests = ['sampler'] + list(extra_model_outputs)
     front = _FRONTS.get(id(target_model))
     hfront = _HEAD_FRONTS.get(id(target_model))
-    if front is not None and front.supports(requests, extra_model_inputs):
+    if viewdirs is None and front is not None and front.supports(requests, extra_model_inputs):
         # plane producer on sm_100a too (generator.FusedGeneratorFront; no_grad calls only)
         model_outputs = front(None, model_input, requests, extra_model_inputs)
-    elif hfront is not None and hfront.supports(requests, extra_model_inputs):
+    elif viewdirs is None and hfront is not None and hfront.supports(requests, extra_model_inputs):
         # regulariser heads on the fused point evaluator (generator.HeadsGeneratorFront)
         model_outputs = hfront(None, model_input, requests, extra_model_inputs)
     else:
-        model_outputs = target_model(None, model_input, requests, extra_model_inputs)
+        model_outputs = target_model(viewdirs, model_input, requests, extra_model_inputs)
     sampler = model_outputs.pop('triplane', None) or model_outputs['sampler']
     model_outputs.pop('sampler', None)
     planes, palette, w1, b1, w2, b2, beta, alpha = extract_field(target_model, sampler)
+    view = extract_view(target_model, sampler) if args.use_viewdir else None
     layout = sampler.get('planes_layout', 'channel_first') if isinstance(sampler, dict) \
         else 'channel_first'
 
@@ -219,7 +242,7 @@ def render(target_model,
         planes, w1, b1, w2, b2, palette, beta, alpha, tform_cam2world,
         focal_length, center, bbox, cfg, height, width, S, noise_t, noise_u,
         extra_mode, cam_grad=not force_no_cam_grad,
-        compute_normals=bool(compute_normals), planes_layout=layout)
+        compute_normals=bool(compute_normals), planes_layout=layout, view=view)
     rgb, depth, mask, extra = out[:4]
     normals = out[4] if compute_normals else None
     return rgb, depth, mask, normals, extra, model_outputs

@@ -84,7 +84,8 @@ class _PlaneStub(torch.nn.Module):
 
 
 def build_reference_generator(scene, use_sdf=True):
-    """Reference Generator carrying ``scene``'s decoder weights, beta/alpha.
+    """Reference Generator carrying ``scene``'s decoder weights, beta/alpha (and, for a scene from
+    ``fixtures.synthetic.add_view_mapper``, its ViewDirectionMapper: ``use_viewdir=True``).
 
     ``scene`` is a dict from ``fixtures.synthetic.make_scene``:
     effective decoder weights are divided by the EqualizedLinear gains so the
@@ -92,11 +93,24 @@ def build_reference_generator(scene, use_sdf=True):
     """
     _, generator = _import_reference()
     A = scene['palette'].shape[1] if scene['palette'] is not None else 0
+    vd = 'view_mapper' in scene
     g = generator.Generator(512, scene['scene_range'], attention_values=A,
-                            use_sdf=use_sdf, disable_stylegan_noise=True)
+                            use_sdf=use_sdf, disable_stylegan_noise=True, use_viewdir=vd)
     g.synthesis_network = _PlaneStub()
     l1, l2 = g.decoder.net[0], g.decoder.net[2]
     with torch.no_grad():
+        if vd:
+            vm, m = g.viewdir_mapper, scene['view_mapper']
+            for i in range(7):
+                fc = getattr(vm, 'fc%d' % i)
+                fc.weight.copy_(m['fc%d_w' % i] / fc.weight_gain)
+                if fc.bias is not None:
+                    fc.bias.copy_(m['fc%d_b' % i] / fc.bias_gain)
+            for i in range(1, 5):
+                getattr(vm, 'norm%d' % i).weight.copy_(m['norm%d_w' % i])
+                getattr(vm, 'norm%d' % i).bias.copy_(m['norm%d_b' % i])
+            vm.output.weight.copy_(scene['w3'] / vm.output.weight_gain)
+            vm.output.bias.copy_(scene['b3'] / vm.output.bias_gain)
         l1.weight.copy_(scene['w1'] / l1.weight_gain)
         l1.bias.copy_(scene['b1'] / l1.bias_gain)
         l2.weight.copy_(scene['w2'] / l2.weight_gain)
@@ -123,7 +137,7 @@ def reference_render(scene, cams, height, width, num_samples, seed=None,
     A = scene['palette'].shape[1] if scene['palette'] is not None else 0
     render = lift_render(scene['scene_range'], scene['white_background'],
                          use_sdf=use_sdf, attention_values=A,
-                         fine_sampling=fine_sampling)
+                         fine_sampling=fine_sampling, use_viewdir='view_mapper' in scene)
     g = generator if generator is not None else build_reference_generator(
         scene, use_sdf)
     planes = scene['planes'] if planes is None else planes

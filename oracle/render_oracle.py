@@ -21,6 +21,8 @@ Reference functions restated here (all paths relative to /root/reference):
                         models/stylegan.py:148-180  EqualizedLinear (gains are
                         folded into the "effective" weights by the caller)
   field                 models/generator.py:587-681 sampler closure
+  view_mapper_trunk     models/generator.py:223-240 ViewDirectionMapper.forward (per-ray part)
+  view_head             models/generator.py:242-251 mapper_closure (per-sample part, --use_viewdir)
   composite_weights     lib/nerf_utils.py:164-180 render_volume_density_weights_only
   smooth_weights        run.py:266-272
   inverse_cdf_samples   lib/nerf_utils.py:183-222 sample_pdf
@@ -162,11 +164,39 @@ def triplane_decoder(planes: torch.Tensor, coords: torch.Tensor,
     return F.linear(h, w2, b2)
 
 
+def view_mapper_trunk(viewdir, m):
+    """ViewDirectionMapper.forward up to the closure (models/generator.py:223-240): the per-RAY
+    features x [..., 32] from unit view directions [..., 3].  ``m`` holds EFFECTIVE weights:
+    fc0_w/fc0_b, fc1_w .. fc4_w (no bias), norm1_w/norm1_b .. norm4_*, fc5_w/fc5_b, fc6_w/fc6_b."""
+    lrelu = lambda t: F.leaky_relu(t, 0.2)
+    ln = lambda t, i: F.layer_norm(t, (t.shape[-1],), m['norm%d_w' % i], m['norm%d_b' % i])
+    scale = math.sqrt(2) / 2
+    x = lrelu(F.linear(viewdir, m['fc0_w'], m['fc0_b']))
+    for a, b in ((1, 2), (3, 4)):
+        shortcut = x
+        x = lrelu(ln(F.linear(x, m['fc%d_w' % a]), a))
+        x = lrelu(ln(F.linear(x, m['fc%d_w' % b]), b))
+        x = (x + shortcut) * scale
+    x = lrelu(F.linear(x, m['fc5_w'], m['fc5_b']))
+    return F.linear(x, m['fc6_w'], m['fc6_b'])
+
+
+def view_head(feat, view_features, w3, b3):
+    """mapper_closure (models/generator.py:242-251): ``feat`` [B, rays*S, 32] decoder features,
+    ``view_features`` [B, rays, 32] -> colour logits [B, rays*S, A]."""
+    B, n, c = feat.shape
+    rays = view_features.shape[1]
+    y = F.leaky_relu(view_features.unsqueeze(2) + feat.view(B, rays, n // rays, c), 0.2)
+    return F.linear(y.view(B, n, c), w3, b3)
+
+
 def field(points, planes, w1, b1, w2, b2, palette, beta, alpha, scene_range,
-          use_sdf=True, want_normals=False):
+          use_sdf=True, want_normals=False, view=None):
     """sigma [B,N], rgb [B,N,3], probs [B,N,A]|None, normals [B,N,3]|None.
 
-    models/generator.py:587-681.  ``points`` is [B,N,3] in world units.
+    models/generator.py:587-681.  ``points`` is [B,N,3] in world units.  ``view`` =
+    (view_features [B,rays,32], w3, b3) switches on the view-direction conditioning
+    (:662-663): N = rays * samples, ray-major.
     """
     if want_normals:
         points = points.detach().requires_grad_()
@@ -182,6 +212,8 @@ def field(points, planes, w1, b1, w2, b2, palette, beta, alpha, scene_range,
         normals = F.normalize(grad, dim=-1)
         dist = dist.detach()
         feat = feat.detach()
+    if view is not None:
+        feat = view_head(feat, *view)
     if use_sdf:
         nd = -dist
         cdf = 0.5 + 0.5 * torch.sign(nd) * (1 - torch.exp(-nd.abs() / beta))
@@ -325,7 +357,7 @@ def render_oracle(planes, w1, b1, w2, b2, palette, beta, alpha,
                   white_background=False, use_sdf=True, fine_sampling=True,
                   compute_normals=False, compute_semantics=False,
                   compute_coords=False, force_no_cam_grad=False,
-                  global_near_far_fallback=True):
+                  global_near_far_fallback=True, view_features=None, w3=None, b3=None):
     """run.py:176-350 with the planes / palette given instead of produced by
     ``target_model`` and with the two random draws passed in:
 
@@ -333,6 +365,10 @@ def render_oracle(planes, w1, b1, w2, b2, palette, beta, alpha,
                         lib/nerf_utils.py:112); None -> ``randomize=False``
     noise_u  [B*H*W,S]  inverse-CDF uniforms (``torch.rand`` at :201); None ->
                         the deterministic ``linspace(0,1,S)`` of :194-199
+
+    ``view_features`` [B,H,W,32] (+ ``w3`` [A,32], ``b3`` [A]; then w2 is [33,64]) is the
+    ViewDirectionMapper trunk output of the rays (``--use_viewdir``, run.py:216-217: the
+    reference feeds the unit directions, detached under ``force_no_cam_grad``, to the model).
 
     Returns a dict with rgb [B,H,W,3], depth, mask [B,H,W], normals, semantics
     (``coords`` overwrite ``semantics`` as at run.py:337-338), plus z_fine.
@@ -351,11 +387,15 @@ def render_oracle(planes, w1, b1, w2, b2, palette, beta, alpha,
         depths = depths.detach()
         dirs = dirs.detach()
 
+    view = None
+    if view_features is not None:
+        view = (view_features.reshape(B, height * width, -1), w3, b3)
+
     def run_field(pts):
         shp = pts.shape[:-1]
         s, c, p, n = field(pts.reshape(B, -1, 3), planes, w1, b1, w2, b2,
                            palette, beta, alpha, scene_range, use_sdf,
-                           compute_normals)
+                           compute_normals, view)
         s = s.view(*shp)
         c = c.view(*shp, 3)
         n = n.view(*shp, 3) if n is not None else None
@@ -399,6 +439,22 @@ def render_oracle(planes, w1, b1, w2, b2, palette, beta, alpha,
     return {'rgb': rgb_map, 'depth': depth_map, 'mask': mask,
             'normals': normal_map, 'semantics': extra_map, 'z_fine': z_fine,
             'near': near, 'far': far}
+
+
+def effective_view_mapper_weights(mapper):
+    """(trunk dict for ``view_mapper_trunk``, w3, b3) of a reference ViewDirectionMapper with the
+    EqualizedLinear gains folded in (models/generator.py:189-221, stylegan.py:175-177)."""
+    m = {}
+    for i in range(7):
+        fc = getattr(mapper, 'fc%d' % i)
+        m['fc%d_w' % i] = fc.weight * fc.weight_gain
+        if fc.bias is not None:
+            m['fc%d_b' % i] = fc.bias * fc.bias_gain
+    for i in range(1, 5):
+        norm = getattr(mapper, 'norm%d' % i)
+        m['norm%d_w' % i], m['norm%d_b' % i] = norm.weight, norm.bias
+    out = mapper.output
+    return m, out.weight * out.weight_gain, out.bias * out.bias_gain
 
 
 def effective_decoder_weights(decoder):

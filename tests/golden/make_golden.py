@@ -33,6 +33,9 @@ GOLDEN = {
     'p3d_coords': ('p3d_plain', dict(randomize=True, compute_coords=True)),
     'p3d_direct_rgb': ('p3d_plain', dict(randomize=True, attention_values=0)),
     'p3d_density': ('p3d_plain', dict(randomize=True, use_sdf=False)),
+    # --use_viewdir (the CARLA models): view-direction-conditioned colour, generator.py:189-253
+    'chairs_viewdir': ('chairs_white_center', dict(randomize=True, viewdir=True)),
+    'p3d_viewdir_direct_rgb': ('p3d_bbox', dict(randomize=True, viewdir=True, attention_values=0)),
 }
 B, R, H, W, S = 2, 16, 12, 20, 8
 
@@ -48,6 +51,10 @@ def main():
         kw = dict(kw)
         A = kw.pop('attention_values', 10)
         scene, cams = Hh.make_case(case, seed=11, batch=B, plane_res=R, attention_values=A)
+        viewdir = kw.pop('viewdir', False)
+        if viewdir:
+            from fixtures import synthetic
+            scene = synthetic.add_view_mapper(scene)
         planes = scene['planes'].clone().requires_grad_()
         palette = scene['palette'].clone().requires_grad_() if A > 0 else None
         cams_l = dict(cams)
@@ -65,18 +72,26 @@ def main():
             leaves.append(palette); names.append('palette')
         if kw.get('use_sdf', True):
             leaves += [gen.beta, gen.alpha]; names += ['beta', 'alpha']
-        grads = torch.autograd.grad(loss, leaves)
         gains = {'w1': dec[0].weight_gain, 'b1': dec[0].bias_gain,
                  'w2': dec[2].weight_gain, 'b2': dec[2].bias_gain}
+        if viewdir:
+            vm = gen.viewdir_mapper
+            leaves += [vm.output.weight, vm.output.bias, vm.fc0.weight, vm.fc4.weight, vm.norm3.bias]
+            names += ['w3', 'b3', 'vm_fc0_w', 'vm_fc4_w', 'vm_norm3_b']
+            gains.update(w3=vm.output.weight_gain, b3=vm.output.bias_gain,
+                         vm_fc0_w=vm.fc0.weight_gain, vm_fc4_w=vm.fc4.weight_gain)
+        grads = torch.autograd.grad(loss, leaves)
         arrays = dict(rgb=rgb, depth=depth, mask=mask)
         if extra is not None:
             arrays['extra'] = extra
         for n, g in zip(names, grads):
             # the fixture stores gradients w.r.t. the EFFECTIVE weights
             arrays['grad_' + n] = g / gains[n] if n in gains else g
-        for k in ('planes', 'w1', 'b1', 'w2', 'b2', 'palette', 'beta', 'alpha'):
-            if scene[k] is not None:
+        for k in ('planes', 'w1', 'b1', 'w2', 'b2', 'palette', 'beta', 'alpha', 'w3', 'b3'):
+            if scene.get(k) is not None:
                 arrays['in_' + k] = scene[k]
+        for k, v in scene.get('view_mapper', {}).items():
+            arrays['in_vm_' + k] = v
         for k, v in cams.items():
             if v is not None:
                 arrays['cam_' + k] = v

@@ -15,7 +15,8 @@ from tests import helpers as Hh
 
 GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden')
 FILES = sorted(glob.glob(os.path.join(GOLDEN_DIR, '*.npz')))
-GRAD_NAMES = ['planes', 'w1', 'b1', 'w2', 'b2', 'c2w', 'palette', 'beta', 'alpha']
+GRAD_NAMES = ['planes', 'w1', 'b1', 'w2', 'b2', 'c2w', 'palette', 'beta', 'alpha', 'w3', 'b3',
+              'vm_fc0_w', 'vm_fc4_w', 'vm_norm3_b']  # vm_*: ViewDirectionMapper trunk (--use_viewdir)
 
 
 def load(path, device='cpu'):
@@ -23,6 +24,9 @@ def load(path, device='cpu'):
     t = lambda k: torch.from_numpy(z[k]).to(device) if k in z.files else None
     meta = {k[5:]: z[k].item() for k in z.files if k.startswith('meta_')}
     scene = {k: t('in_' + k) for k in ('planes', 'w1', 'b1', 'w2', 'b2', 'palette', 'beta', 'alpha')}
+    if 'in_w3' in z.files:
+        scene.update(w3=t('in_w3'), b3=t('in_b3'),
+                     view_mapper={k[6:]: t(k) for k in z.files if k.startswith('in_vm_')})
     scene['scene_range'] = float(meta['scene_range'])
     scene['white_background'] = bool(meta['white_background'])
     cams = {k: t('cam_' + k) for k in ('c2w', 'focal', 'center', 'bbox')}
@@ -40,9 +44,18 @@ def loss_of(rgb, mask):
 def with_leaves(scene, cams):
     sc = {k: (v.clone().requires_grad_() if (torch.is_tensor(v) and k in GRAD_NAMES) else v)
           for k, v in scene.items()}
+    if 'view_mapper' in scene:
+        sc['view_mapper'] = {k: (v.clone().requires_grad_() if 'vm_' + k in GRAD_NAMES else v)
+                             for k, v in scene['view_mapper'].items()}
     cm = dict(cams)
     cm['c2w'] = cams['c2w'].clone().requires_grad_()
     return sc, cm
+
+
+def leaf_of(sc, cm, n):
+    if n == 'c2w':
+        return cm['c2w']
+    return sc['view_mapper'][n[3:]] if n.startswith('vm_') else sc[n]
 
 
 def test_fixture_set_is_complete():
@@ -62,7 +75,7 @@ def test_oracle_reproduces_reference_golden(path):
     if 'extra' in exp:
         assert (out['semantics'] - exp['extra']).abs().max().item() < 2e-5
     names = [n for n in GRAD_NAMES if ('grad_' + n) in exp]
-    leaves = [sc[n] if n != 'c2w' else cm['c2w'] for n in names]
+    leaves = [leaf_of(sc, cm, n) for n in names]
     grads = torch.autograd.grad(loss_of(out['rgb'], out['mask']), leaves)
     for n, g in zip(names, grads):
         assert Hh.rel_l2(g, exp['grad_' + n]) < 1e-4, n
@@ -84,7 +97,7 @@ def test_cuda_reproduces_reference_golden(cuda_lib, path):
     if 'extra' in exp:
         assert Hh.rel_l2(extra, exp['extra']) < 2e-4
     names = [n for n in GRAD_NAMES if ('grad_' + n) in exp]
-    leaves = [sc[n] if n != 'c2w' else cm['c2w'] for n in names]
+    leaves = [leaf_of(sc, cm, n) for n in names]
     grads = torch.autograd.grad(loss_of(rgb, mask), leaves)
     for n, g in zip(names, grads):
         assert Hh.rel_l2(g, exp['grad_' + n]) < 2e-3, n

@@ -39,6 +39,36 @@ def test_render_variants_match_reference(kw):
         assert (out[4] - o['semantics']).abs().max().item() < 2e-5
 
 
+@pytest.mark.parametrize('case,A,kw', [('p3d_plain', 10, {}), ('chairs_white_center', 0, {}),
+                                       ('cub_ortho', 10, dict(compute_semantics=True)),
+                                       ('p3d_bbox', 10, dict(force_no_cam_grad=True)),
+                                       ('p3d_plain', 10, dict(compute_normals=True))])
+def test_view_direction_conditioning_matches_reference(case, A, kw):
+    """--use_viewdir (run.py:216-221, models/generator.py:189-253,662-663): the reference
+    Generator built with use_viewdir=True and given the oracle scene's ViewDirectionMapper
+    weights, called by the reference's own render(), against the oracle's restatement of the
+    mapper trunk (per ray) and closure (per sample)."""
+    from fixtures import synthetic
+    scene, cams = Hh.make_case(case, seed=2, batch=2, plane_res=24, attention_values=A)
+    scene = synthetic.add_view_mapper(scene)
+    out, nt, nu = RL.reference_render(scene, cams, 12, 20, 12, seed=4, **kw)
+    o = Hh.run_oracle(scene, cams, 12, 20, 12, nt, nu, **kw)
+    for ref, k in zip(out[:3], ('rgb', 'depth', 'mask')):
+        assert (ref - o[k]).abs().max().item() < 2e-5, k
+    if out[3] is not None:
+        assert (out[3] - o['normals']).abs().max().item() < 1e-4
+    if out[4] is not None:
+        assert (out[4] - o['semantics']).abs().max().item() < 2e-5
+    # the trunk alone, against the module (bit-identical: same ops in the same order)
+    g = RL.build_reference_generator(scene)
+    m, w3, b3 = O.effective_view_mapper_weights(g.viewdir_mapper)
+    d = torch.nn.functional.normalize(torch.randn(3, 5, 1, 3), dim=-1)
+    closure = g.viewdir_mapper(d)
+    x_ref = dict(zip(closure.__code__.co_freevars,
+                     (c.cell_contents for c in closure.__closure__)))['x']
+    assert torch.equal(O.view_mapper_trunk(d, m), x_ref)
+
+
 def test_stage_functions_match_reference():
     nerf_utils, _ = RL._import_reference()
     scene, cams = Hh.make_case('p3d_bbox', seed=6, batch=2)

@@ -29,10 +29,12 @@ def oracle_core(calls):
     """Stand-in for fused.fused_render with the same signature, on the CPU oracle."""
     def core(planes, w1, b1, w2, b2, palette, beta, alpha, c2w, focal, center, bbox, cfg,
              height, width, num_samples, noise_t=None, noise_u=None, extra_mode=0,
-             cam_grad=True, compute_normals=False, out=None, planes_layout='channel_first'):
+             cam_grad=True, compute_normals=False, out=None, planes_layout='channel_first',
+             view=None):
         assert planes_layout == 'channel_first'   # the reference Generator's own planes
         calls.append(dict(planes=planes, cfg=cfg, extra_mode=extra_mode, cam_grad=cam_grad,
-                          noise_t=noise_t, noise_u=noise_u))
+                          noise_t=noise_t, noise_u=noise_u, view=view))
+        vkw = dict(view_features=view[0], w3=view[1], b3=view[2]) if view is not None else {}
         o = O.render_oracle(planes, w1, b1, w2, b2, palette, beta, alpha, c2w, focal, center,
                             bbox, height, width, num_samples, noise_t, noise_u,
                             scene_range=cfg.scene_range, white_background=cfg.white_background,
@@ -40,20 +42,23 @@ def oracle_core(calls):
                             compute_normals=compute_normals,
                             compute_semantics=extra_mode == _lib.EXTRA_SEMANTICS,
                             compute_coords=extra_mode == _lib.EXTRA_COORDS,
-                            force_no_cam_grad=not cam_grad)
+                            force_no_cam_grad=not cam_grad, **vkw)
         extra = o['semantics'] if extra_mode != _lib.EXTRA_NONE else None
         res = (o['rgb'], o['depth'], o['mask'], extra)
         return res + ((o['normals'],) if compute_normals else ())
     return core
 
 
-def setup(monkeypatch, case='p3d_bbox', A=10, use_sdf=True, fine=True):
+def setup(monkeypatch, case='p3d_bbox', A=10, use_sdf=True, fine=True, viewdir=False):
     scene, cams = Hh.make_case(case, seed=21, batch=2, plane_res=16, attention_values=A)
+    if viewdir:
+        from fixtures import synthetic
+        scene = synthetic.add_view_mapper(scene)
     g = RL.build_reference_generator(scene, use_sdf=use_sdf)
     g.synthesis_network.planes = scene['planes'].reshape(2, 96, 16, 16)
     calls = []
     monkeypatch.setattr(R, 'fused_render', oracle_core(calls))
-    R.configure(types.SimpleNamespace(use_viewdir=False, use_sdf=use_sdf, attention_values=A,
+    R.configure(types.SimpleNamespace(use_viewdir=viewdir, use_sdf=use_sdf, attention_values=A,
                                       fine_sampling=fine),
                 {'scene_range': scene['scene_range'],
                  'white_background': scene['white_background']})
@@ -71,9 +76,14 @@ def setup(monkeypatch, case='p3d_bbox', A=10, use_sdf=True, fine=True):
     ('p3d_plain', dict(compute_coords=True, compute_semantics=True)),  # coords win, run.py:337
     ('p3d_plain', dict(compute_normals=True)),
     ('p3d_plain', dict(force_no_cam_grad=True)),
+    # --use_viewdir (CARLA; run.py:216-221): the model is called with the unit view directions
+    ('chairs_white_center', dict(viewdir=True)),
+    ('p3d_bbox', dict(viewdir=True, compute_semantics=True)),
+    ('cub_ortho', dict(viewdir=True, force_no_cam_grad=True)),
 ])
 def test_render_returns_what_the_reference_returns(monkeypatch, case, kw):
-    scene, cams, g, ws, extra_in, calls = setup(monkeypatch, case)
+    kw = dict(kw)
+    scene, cams, g, ws, extra_in, calls = setup(monkeypatch, case, viewdir=kw.pop('viewdir', False))
     ref_kw = dict(kw)
     randomize = ref_kw.pop('randomize', True)
     ref, _, _ = RL.reference_render(scene, cams, H, W, S, seed=33, randomize=randomize,
@@ -96,6 +106,30 @@ def test_render_returns_what_the_reference_returns(monkeypatch, case, kw):
     (call,) = calls
     assert call['cam_grad'] == (not kw.get('force_no_cam_grad', False))
     assert (call['noise_t'] is None) == (not randomize)
+    if 'view_mapper' in scene:
+        vf, w3, b3 = call['view']
+        assert vf.shape == (2, H, W, 32)
+        assert torch.allclose(w3, scene['w3'], rtol=1e-6, atol=0) and torch.allclose(b3, scene['b3'], rtol=1e-6, atol=0)
+        # the view directions reach the mapper attached to the cameras unless force_no_cam_grad
+        assert vf.requires_grad  # (the mapper's parameters; the cameras unless force_no_cam_grad)
+
+
+def test_viewdir_gradients_reach_the_mapper_and_the_cameras(monkeypatch):
+    """--use_viewdir: d rgb / d(ViewDirectionMapper parameters) and the camera gradient THROUGH the
+    view directions agree with the reference's autograd (the per-ray trunk stays the reference
+    module under autograd; the kernel returns d/d view_features, d/d w3, d/d b3)."""
+    scene, cams, g, ws, extra_in, calls = setup(monkeypatch, 'p3d_plain', viewdir=True)
+    cam = dict(cams, c2w=cams['c2w'].clone().requires_grad_())
+    vm = g.viewdir_mapper
+    leaves = [cam['c2w'], vm.fc0.weight, vm.fc3.weight, vm.norm2.bias, vm.output.weight, vm.output.bias]
+    ref, _, _ = RL.reference_render(scene, cam, H, W, S, seed=4, generator=g)
+    want = torch.autograd.grad(ref[0].square().sum() + ref[2].sum(), leaves)
+    torch.manual_seed(4)
+    got = R.render(g, H, W, cam['c2w'], cam['focal'], cam['center'], cam['bbox'], ws, S,
+                   extra_model_inputs=extra_in)
+    have = torch.autograd.grad(got[0].square().sum() + got[2].sum(), leaves)
+    for a, b in zip(have, want):
+        assert Hh.rel_l2(a, b) < 1e-4
 
 
 def test_planes_are_lifted_without_a_copy(monkeypatch):
@@ -130,8 +164,8 @@ def test_variants_and_model_outputs(monkeypatch):
 def test_error_behaviour(monkeypatch):
     scene, cams, g, ws, extra_in, calls = setup(monkeypatch)
     a = (g, H, W, cams['c2w'], cams['focal'], None, None, ws, S)
-    R.args.use_viewdir = True
-    with pytest.raises(NotImplementedError):
+    R.args.use_viewdir = True                             # model built without use_viewdir
+    with pytest.raises(_lib.NfiError):
         R.render(*a, extra_model_inputs=extra_in)
     R.args.use_viewdir = False
     R.args.attention_values = 0

@@ -31,7 +31,7 @@ def _rel(a, b):
     return ((a - b).norm() / b.norm().clamp_min(1e-12)).item()
 
 
-def _setup(dataset='p3d_car', A=10, B=2, seed=1234):
+def _setup(dataset='p3d_car', A=10, B=2, seed=1234, use_viewdir=False):
     from nerf_from_image_b200 import render as R
     from fixtures import synthetic
     torch.backends.cuda.matmul.allow_tf32 = False   # run.py:59-60
@@ -40,21 +40,24 @@ def _setup(dataset='p3d_car', A=10, B=2, seed=1234):
     cfg = synthetic.DATASET_CONFIGS[dataset]
     torch.manual_seed(seed)                        # the reference's own seed, run.py:413
     g = generator.Generator(512, cfg['scene_range'], attention_values=A, use_sdf=True,
-                            disable_stylegan_noise=True).cuda().eval()
+                            disable_stylegan_noise=True, use_viewdir=use_viewdir).cuda().eval()
     g.requires_grad_(False)                        # inversion setting, run.py:628-629
     with torch.no_grad():                          # the random-init SDF head is ~ N(1.13, 0.27):
         g.decoder.net[2].bias[0] = -1.15           # shift it so it crosses zero (mask ~ 0.5-0.6)
+        if use_viewdir:                            # the mapper's output layer starts at zero
+            g.viewdir_mapper.output.weight.normal_()   # (generator.py:217-218): make it matter
+            g.viewdir_mapper.output.bias.normal_(0, 0.1)
     cams = synthetic.make_cameras(seed, B, ortho=cfg['ortho'], radius=cfg['radius'],
                                   with_bbox=not cfg['ortho'], device='cuda')
     z = torch.randn(B, 512, device='cuda')
     with torch.no_grad():
         ws = g.mapping_network(z, None)
-    args = types.SimpleNamespace(use_viewdir=False, use_sdf=True, attention_values=A,
+    args = types.SimpleNamespace(use_viewdir=use_viewdir, use_sdf=True, attention_values=A,
                                  fine_sampling=True)
     dcfg = {'scene_range': cfg['scene_range'], 'white_background': cfg['white_background']}
     R.configure(args, dcfg)
     ref_render = RL.lift_render(cfg['scene_range'], cfg['white_background'], use_sdf=True,
-                                attention_values=A, fine_sampling=True)
+                                attention_values=A, fine_sampling=True, use_viewdir=use_viewdir)
     return R, g, cams, ws, ref_render
 
 
@@ -78,6 +81,35 @@ def test_render_equals_the_reference_on_cuda(cuda_lib, dataset, kw):
             assert got[i].shape == ref[i].shape and got[i].device == ref[i].device, name
             assert _rel(got[i], ref[i]) < 1e-3, (name, _rel(got[i], ref[i]))
     assert torch.equal(state_ref, state_got), 'RNG consumption differs from the reference'
+
+
+@pytest.mark.parametrize('kw', [{}, dict(compute_semantics=True), dict(force_no_cam_grad=True)])
+def test_render_with_viewdir_equals_the_reference_on_cuda(cuda_lib, kw):
+    """--use_viewdir (the CARLA models, run.py:216-221): the reference Generator built with
+    use_viewdir=True, called with the unit view directions, its ViewDirectionMapper's per-sample
+    closure evaluated inside the fused kernels."""
+    R, g, cams, ws, ref_render = _setup('p3d_car', use_viewdir=True)
+    a = (g, H, W, cams['c2w'], cams['focal'], cams['center'], cams['bbox'], ws, S)
+    with torch.no_grad():
+        torch.manual_seed(77)
+        ref = ref_render(*a, **kw)
+        state_ref = torch.cuda.get_rng_state()
+        torch.manual_seed(77)
+        got = R.render(*a, **kw)
+        state_got = torch.cuda.get_rng_state()
+    for i, name in enumerate(('rgb', 'depth', 'mask', 'normals', 'extra')):
+        assert (got[i] is None) == (ref[i] is None), name
+        if ref[i] is not None:
+            assert _rel(got[i], ref[i]) < 1e-3, (name, _rel(got[i], ref[i]))
+    assert torch.equal(state_ref, state_got), 'RNG consumption differs from the reference'
+    # and the pose gradient, which now also flows through the view directions
+    grads = []
+    for fn in (ref_render, R.render):
+        c2w = cams['c2w'].clone().requires_grad_()
+        torch.manual_seed(5)
+        out = fn(g, H, W, c2w, cams['focal'], None, cams['bbox'], ws, S)
+        grads.append(torch.autograd.grad(out[0].square().mean() + out[2].mean(), [c2w])[0])
+    assert _rel(grads[1], grads[0]) < 5e-3
 
 
 def test_inversion_gradients_flow_to_the_latents_like_the_reference(cuda_lib):
