@@ -359,10 +359,14 @@ __device__ __forceinline__ float4 ldg_nc_volatile_next(const float4* p) {  // th
                : "l"(p));
   return r;
 }
+// WITH_Y: also the features rounded to bf16 into columns 0..31 of a [128 rows][64 bf16]
+// SWIZZLE_128B tile (the MN-major B operand of the weight-gradient chain, nfi_wgrad_pipe.cuh).
+template <bool WITH_Y = false>
 __device__ __forceinline__ void gather_to_tiles_lean(const unsigned char* __restrict__ planes_b,
                                                      int R, const ByteTaps& tp,
                                                      unsigned char* a_hi, unsigned char* a_lo,
-                                                     int row0, int lane) {
+                                                     int row0, int lane,
+                                                     unsigned char* y_tile = nullptr) {
   const int q = lane >> 3, k = lane & 7;
   const uint32_t row_units = (uint32_t)R * 8u;
 #pragma unroll 1
@@ -403,6 +407,12 @@ __device__ __forceinline__ void gather_to_tiles_lean(const unsigned char* __rest
     const uint32_t offs = tc::sw128_offset(row0 + src, k);
     *reinterpret_cast<float4*>(a_hi + offs) = fh;
     *reinterpret_cast<float4*>(a_lo + offs) = fl;
+    if constexpr (WITH_Y) {
+      uint2 yb;
+      asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(yb.x) : "f"(f.y), "f"(f.x));
+      asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(yb.y) : "f"(f.w), "f"(f.z));
+      *reinterpret_cast<uint2*>(y_tile + tc::sw128_offset(row0 + src, k >> 1) + (k & 1) * 8) = yb;
+    }
   }
 }
 

@@ -8,6 +8,7 @@
 #include "nfi_backward_pipe.cuh"
 #include "nfi_forward_pipe.cuh"
 #include "nfi_pipe_launch.h"
+#include "nfi_wgrad_pipe.cuh"
 
 namespace nfi {
 namespace {
@@ -80,7 +81,20 @@ int bwd_np(const nfi_render_params& p, const nfi_render_grads& g, const unsigned
              : run_bwd<NP, 0, false>(p, g, wimg, grid, st, err, err_len);
 }
 
+template <int NP>
+int run_wgrad(const nfi_render_params& p, const nfi_render_grads& g, const unsigned char* wimg,
+              unsigned grid, cudaStream_t st, char* err, size_t err_len) {
+  auto k = render_wgrad_pipe<NP>;
+  NFI_PCUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, WgCfg::kSmBytes));
+  k<<<grid, WgCfg::kThreadsTotal, WgCfg::kSmBytes, st>>>(
+      p, g, wimg, reinterpret_cast<float*>(const_cast<unsigned char*>(wimg) + 65536));
+  NFI_PCUDA(cudaGetLastError());
+  return 0;
+}
+
 }  // namespace
+
+size_t pipe_wgrad_workspace_bytes(unsigned grid) { return 65536 + (size_t)grid * kWgAccBytesPerCta; }
 
 size_t pipe_scratch_bytes_per_cta(int num_samples, int nes) {
   return pipe_scratch_floats(num_samples, nes) * sizeof(float);
@@ -115,6 +129,22 @@ int launch_pipe_backward(const nfi_render_params& p, const nfi_render_grads& g, 
   if (nout_pad == 4) return bwd_np<4>(p, g, wimg, grid, st, err, err_len);
   if (nout_pad == 12) return bwd_np<12>(p, g, wimg, grid, st, err, err_len);
   return bwd_np<16>(p, g, wimg, grid, st, err, err_len);
+}
+
+// decoder-weight gradients on tcgen05 (nfi_wgrad_pipe.cuh): both weight images + render_wgrad_pipe
+int launch_pipe_wgrad(const nfi_render_params& p, const nfi_render_grads& g, int nout_pad,
+                      unsigned char* wimg, unsigned grid, cudaStream_t st, char* err,
+                      size_t err_len) {
+  const int nout = 1 + (p.n_attention > 0 ? p.n_attention : 3);
+  if (launch_pipe_weight_image(p, wimg, st)) {
+    snprintf(err, err_len, "weight image launch failed");
+    return 2;
+  }
+  prep_weight_image_bwd<<<1, 256, 0, st>>>(p.w1, p.w2, nout, wimg + 32768);
+  NFI_PCUDA(cudaGetLastError());
+  if (nout_pad == 4) return run_wgrad<4>(p, g, wimg, grid, st, err, err_len);
+  if (nout_pad == 12) return run_wgrad<12>(p, g, wimg, grid, st, err, err_len);
+  return run_wgrad<16>(p, g, wimg, grid, st, err, err_len);
 }
 
 }  // namespace nfi

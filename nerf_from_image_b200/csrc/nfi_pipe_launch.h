@@ -16,6 +16,14 @@ int launch_pipe_forward(const nfi_render_params& p, int nout_pad, const unsigned
 int launch_pipe_backward(const nfi_render_params& p, const nfi_render_grads& g, int nout_pad,
                          unsigned char* wimg, unsigned grid, cudaStream_t st, char* err,
                          size_t err_len);
+// decoder-weight gradients (grad_w1 / b1 / w2 / b2 of `g`, accumulated) on tcgen05: both weight
+// images + render_wgrad_pipe; the other gradients of `g` are NOT produced (launch_pipe_backward)
+// (workspace at `wimg`: the two weight images, then one accumulator row buffer per CTA:
+// pipe_wgrad_workspace_bytes(grid) in all)
+size_t pipe_wgrad_workspace_bytes(unsigned grid);
+int launch_pipe_wgrad(const nfi_render_params& p, const nfi_render_grads& g, int nout_pad,
+                      unsigned char* wimg, unsigned grid, cudaStream_t st, char* err,
+                      size_t err_len);
 // the pipelined kernels' weight image (log2 e folded into layer 1 and the colour rows of
 // layer 2, padded logits at -1e30)
 int launch_pipe_weight_image(const nfi_render_params& p, unsigned char* wimg, cudaStream_t st);

@@ -499,20 +499,42 @@ int nfi_render_backward(const nfi_render_params* params, const nfi_render_grads*
   if (g.grad_view_features || g.grad_w3 || g.grad_b3)
     return fail("grad_view_features / grad_w3 / grad_b3 need params->view_features");
   const bool wgrad = g.grad_w1 || g.grad_b1 || g.grad_w2 || g.grad_b2;
-  const bool tc_ok = !wgrad && mode != NFI_MLP_FP32_SIMT && p.extra_mode != NFI_EXTRA_SEMANTICS &&
-                     p.num_samples <= 128 && p.num_samples % 4 == 0 && p.workspace != nullptr &&
-                     p.workspace_bytes >= kBackwardWorkspaceBytes &&
-                     (!p.fine_sampling || p.z_fine != nullptr) && g.out_rgb && g.out_mask &&
-                     (!g.g_extra || g.out_extra) &&
-                     ((g.grad_origins == nullptr) == (g.grad_dirs == nullptr));
+  const bool tc_env = mode != NFI_MLP_FP32_SIMT && p.extra_mode != NFI_EXTRA_SEMANTICS &&
+                      p.num_samples <= 128 && p.num_samples % 4 == 0 && p.workspace != nullptr &&
+                      p.workspace_bytes >= kBackwardWorkspaceBytes &&
+                      (!p.fine_sampling || p.z_fine != nullptr) && g.out_rgb && g.out_mask &&
+                      (!g.g_extra || g.out_extra) &&
+                      ((g.grad_origins == nullptr) == (g.grad_dirs == nullptr));
+  // decoder-weight gradients (the GAN generator step, run.py:1044) on tcgen05 too: a second
+  // kernel (render_wgrad_pipe) beside render_backward_pipe, which then sees a frozen decoder.
+  // An upstream gradient of the coords output stays on the SIMT kernel, and so do small
+  // renders under NFI_MLP_AUTO (below 2^20 points the fp32 kernel takes a few hundred
+  // microseconds and has none of the 1e-3 bf16 operand rounding of the tensor-core chain).
+  const long long n_points = (long long)p.batch * p.height * p.width * p.num_samples *
+                             (p.fine_sampling ? 2 : 1);
+  const bool tc_ok = tc_env && (!wgrad || (!g.g_extra && (mode != NFI_MLP_AUTO ||
+                                                           n_points >= (1ll << 20)) &&
+                                           p.workspace_bytes >= nfi::pipe_wgrad_workspace_bytes(
+                                                                    (unsigned)kMaxPersistentCtas)));
   if (tc_ok) {
     int dev = 0, sms = 0;
     NFI_CUDA(cudaGetDevice(&dev));
     NFI_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
     size_t grid = num_ctas(&p);
     if (grid > (size_t)sms) grid = sms;
-    return nfi::launch_pipe_backward(p, g, nout_pad_of(params), (unsigned char*)p.workspace,
-                                     (unsigned)grid, st, g_err, sizeof(g_err));
+    nfi_render_grads g1 = g;
+    g1.grad_w1 = g1.grad_b1 = g1.grad_w2 = g1.grad_b2 = nullptr;
+    const bool others = g1.grad_planes || g1.grad_palette || g1.grad_beta || g1.grad_alpha ||
+                        g1.grad_origins;
+    if (others || !wgrad) {
+      if (int rc = nfi::launch_pipe_backward(p, g1, nout_pad_of(params), (unsigned char*)p.workspace,
+                                             (unsigned)grid, st, g_err, sizeof(g_err)))
+        return rc;
+    }
+    if (wgrad)
+      return nfi::launch_pipe_wgrad(p, g, nout_pad_of(params), (unsigned char*)p.workspace,
+                                    (unsigned)grid, st, g_err, sizeof(g_err));
+    return 0;
   }
   return nfi::launch_backward(*params, *grads, st, g_err, sizeof(g_err));
 }

@@ -1,0 +1,644 @@
+// Decoder-weight gradients on tcgen05 (the GAN generator step,
+// run.py:1044: loss.backward() with the decoder trainable).
+//
+//   dW1[j][c] = sum_points dpre[p][j] F[p][c]      db1[j] = sum_points dpre[p][j]
+//   dW2[o][j] = sum_points dOut[p][o] H[p][j]      db2[o] = sum_points dOut[p][o]
+//
+// are contractions over the POINTS, i.e. over what the other GEMMs of the path keep as the M
+// dimension (TMEM lane = point).  tcgen05 reads MN-major operands from shared memory (for 16-bit
+// types with the ordinary 128-byte swizzle; TF32 would need the 32-byte-atomicity layout, which
+// the K-major feature tiles of MMA1 cannot double as), so a step's operands are laid down
+// point-major in bf16 and ONE accumulating MMA chain per 128-point step (kind::f16, M128 N64,
+// eight K16 instructions) forms all three products at once:
+//
+//   A = X^T,  X [128 points][128] = [ dpre (64) | H (64) ]         (2 MN atoms of 64 bf16)
+//   B = Y^T,  Y [128 points][64]  = [ F (32) | dOut (16) | 1 0.. ]  (1 MN atom, one per A stage)
+//   D [128][64] += X^T Y :  rows 0..63  x cols 0..31  = dW1        rows 0..63 x col 48 = db1
+//                           rows 64..127 x cols 32..47 = dW2^T     (the other blocks are unused)
+//
+// accumulated in fp32 in 64 TMEM columns (chains of kWgFlush steps, banked in fp32) and added to
+// the global gradients once per CTA; db2 is summed in fp32 registers by the shading threads.
+// Accuracy: every operand is ONE bf16 (round-to-nearest, 2^-9).  These sums are dominated by a
+// few very large terms (samples at the surface of rays with a large upstream gradient), so the
+// roundings do not average out with the number of points: measured against the fp32 kernel
+// dW1 9e-4 .. 1.2e-3, db1 1e-4 .. 7e-4, dW2 2e-4 .. 4e-4 relative L2 at every size
+// (profiles/r2_wgrad_tc_accuracy.txt; hi/lo pairs on one side only do not help: dpre pairs make
+// db1 exact and leave dW1 where it is).  Pairs on both sides need twice the operand tiles,
+// which the 227 KB beside MMA1's fp32 stages do not hold.  The fp32 SIMT
+// kernel (3e-5) stays selectable (NFI_MLP_FP32_SIMT) and serves small renders by itself.
+//
+// The kernel re-runs the recompute chain of render_backward_pipe in its 3xTF32 form (gather ->
+// MMA1 -> softplus -> MMA2 -> reverse compositing -> MMA3 -> softplus') but neither MMA4 nor
+// the scatter: plane / palette / pose gradients come from render_backward_pipe, launched beside
+// it (the decoder is then a constant of that kernel), which leaves the shared memory (X tile,
+// Y tiles) and TMEM columns this one needs.  Roles as nfi_backward_pipe.cuh; TMEM: two slots of
+// 224 columns
+//   [0,64) D1 -> H_lo   [64,128) H_hi   [128,144) D2 -> dOut_hi   [144,160) dOut_lo   [160,224) D3
+// and the accumulator at [448,512).
+#pragma once
+#include "nfi_backward_pipe.cuh"
+
+namespace nfi {
+
+constexpr int kWgSlots = 2;
+constexpr int kWgSlotCols = 224;
+constexpr int kWgAccCol = 448;
+constexpr int kWgStages = 3;
+// The tensor core ADDS into a TMEM accumulator with truncation, a bias of about half an ulp of
+// the RUNNING sum per instruction: over the ~28,000 accumulating MMAs of a CTA at config 2 it
+// reached 1e-2 of columns whose terms cancel.  The chain is therefore cut every kWgFlush steps
+// (128 MMAs: 4e-6): the accumulator is added, in fp32 round-to-nearest, to a per-CTA row buffer
+// in global memory (L2-resident, single writer per element) and the next chain starts from zero.
+constexpr int kWgFlush = 16;
+constexpr size_t kWgAccBytesPerCta = 128 * 64 * sizeof(float);
+
+struct WgCfg {
+  static constexpr int P = 2;
+  static constexpr int kThreadsTotal = 384 + 128 * P;
+  static constexpr int kSmWb = 25600;                                 // W2^T hi / lo (16 KB)
+  static constexpr int kSmA = kSmWb + 16384;                          // 41 * 1024
+  static constexpr int kSmY = kSmA + kWgStages * kPipeStageBytes;     // 137 * 1024: 3 x 16 KB
+  static constexpr int kSmX = kSmY + kWgStages * 16384;               // 185 * 1024: 32 KB
+  static constexpr int kSmPal = kSmX + 32768;
+  static constexpr int kSmFrac = kSmPal + 48 * 4;
+  static constexpr int kSmBars = kSmFrac + 128 * 4;
+  // full[3], a_free[3], per slot: d1_full, h_ready, d2_full, dout_ready, d3_full, slot_free;
+  // x_ready, x_free; weights x2
+  static constexpr int kNumBars = 2 * kWgStages + 6 * kWgSlots + 2 + 2;
+  static constexpr int kSmTmemPtr = kSmBars + kNumBars * 8;
+  static constexpr int kSmBytes = kSmTmemPtr + 16;
+  // 640 x 96 = 61440 = 256 x 96 + 128 x (128 + 136 + 24)
+  static constexpr int kActRegs = 128;
+  static constexpr int kShadeRegs = 136;
+  static constexpr int kAuxRegs = 24;
+};
+static_assert(WgCfg::kSmBytes <= 227 * 1024, "shared memory budget");
+static_assert((WgCfg::kSmA & 1023) == 0 && (WgCfg::kSmX & 1023) == 0 && (WgCfg::kSmY & 1023) == 0,
+              "SWIZZLE_128B tiles are 1024-byte aligned");
+
+namespace tc {
+// two floats -> packed bf16 pair (round-to-nearest-even), `lo` in the low half (lower address)
+__device__ __forceinline__ uint32_t bf16x2_rn(float lo, float hi) {
+  uint32_t y;
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(y) : "f"(hi), "f"(lo));
+  return y;
+}
+// Shared-memory matrix descriptor, MN-major, SWIZZLE_128B, 16-bit elements: an atom is 64
+// elements of the M/N dimension (128 contiguous bytes) x 8 K rows (128 B apart, 16-byte chunks
+// XOR-swizzled with the row); `lbo` = bytes between atoms along M/N, `sbo` = bytes between
+// 8-row K groups (a K16 instruction reads two of them).
+__device__ __forceinline__ uint64_t umma_desc_mn_sw128(uint32_t smem_addr, uint32_t lbo,
+                                                       uint32_t sbo) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
+  d |= (uint64_t)((lbo >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)((sbo >> 4) & 0x3FFF) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+// Instruction descriptor, kind::f16 with bf16 operands, fp32 accumulate, A and B MN-major:
+//   [4,6) c_format=1 (F32)  [7,10) a_format=1 (BF16)  [10,13) b_format=1  [15] / [16] MN-major
+//   [17,23) N>>3            [24,29) M>>4
+__host__ __device__ constexpr uint32_t umma_idesc_bf16_mn(int M, int N) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) |
+         ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+template <bool ACC>
+__device__ __forceinline__ void umma_f16_ss(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc,
+                                            uint32_t idesc) {
+  if (ACC)
+    asm volatile(
+        "{\n.reg .pred p;\nsetp.eq.u32 p, 0, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}\n" ::"r"(d_tmem),
+        "l"(a_desc), "l"(b_desc), "r"(idesc)
+        : "memory");
+  else
+    asm volatile(
+        "{\n.reg .pred p;\nsetp.ne.u32 p, 0, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}\n" ::"r"(d_tmem),
+        "l"(a_desc), "l"(b_desc), "r"(idesc)
+        : "memory");
+}
+}  // namespace tc
+
+template <int NOUT_PAD>
+__global__ void __launch_bounds__(WgCfg::kThreadsTotal, 1)
+render_wgrad_pipe(const nfi_render_params p, const nfi_render_grads g,
+                  const unsigned char* __restrict__ wimg, float* __restrict__ acc_ws) {
+  using Cfg = WgCfg;
+  constexpr int P = Cfg::P;
+  constexpr int NA = NOUT_PAD - 1;
+  constexpr int NS = kWgStages;
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  unsigned char* base = smem_raw;
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int hw_wg = __shfl_sync(kFull, tid >> 7, 0);
+  // logical role: 0 activation, 1 shading, 2 MMA issuers, 3.. producer sets
+  const int wg = (hw_wg < P) ? hw_wg + 3 : (P + 2 - hw_wg);
+  const int gt = tid & 127;
+  const int wig = __shfl_sync(kFull, gt >> 5, 0);
+  const int S = p.num_samples;
+  const int n_total = (p.fine_sampling ? 2 : 1) * S;  // steps per tile
+
+  uint64_t* bars = reinterpret_cast<uint64_t*>(base + Cfg::kSmBars);
+  uint64_t* full = bars;                      // [3] stage gathered (4 warps)
+  uint64_t* a_free = full + NS;               // [3] stage read by the dW MMAs (commit)
+  uint64_t* d1_full = a_free + NS;            // [2] commit
+  uint64_t* h_ready = d1_full + kWgSlots;     // [2] 4 warps
+  uint64_t* d2_full = h_ready + kWgSlots;     // [2] commit
+  uint64_t* dout_ready = d2_full + kWgSlots;  // [2] 4 warps (dOut in TMEM and in the Y tile)
+  uint64_t* d3_full = dout_ready + kWgSlots;  // [2] commit
+  uint64_t* slot_free = d3_full + kWgSlots;   // [2] 4 warps (D3 / H read)
+  uint64_t* x_ready = slot_free + kWgSlots;   // X tile written (4 warps)
+  uint64_t* x_free = x_ready + 1;             // X tile read by the dW MMAs (commit)
+  uint64_t* wbar = x_free + 1;                // [2] weight images landed
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(base + Cfg::kSmTmemPtr);
+  const float* b1s = reinterpret_cast<const float*>(base + kWiB1);
+  const float* b2s = reinterpret_cast<const float*>(base + kWiB2);
+  float* pal = reinterpret_cast<float*>(base + Cfg::kSmPal);
+  float* frac = reinterpret_cast<float*>(base + Cfg::kSmFrac);
+  if (tid < 128) frac[tid] = (float)tid / (float)S;
+  // the constant part of the Y tiles: column 48 = 1 (-> db1), columns 49..63 = 0 (chunks 6, 7)
+  for (int i = tid; i < NS * 128; i += Cfg::kThreadsTotal) {
+    unsigned char* yt = base + Cfg::kSmY + (i >> 7) * 16384;
+    *reinterpret_cast<uint4*>(yt + tc::sw128_offset(i & 127, 6)) = make_uint4(0x3F80u, 0u, 0u, 0u);
+    *reinterpret_cast<uint4*>(yt + tc::sw128_offset(i & 127, 7)) = make_uint4(0u, 0u, 0u, 0u);
+  }
+  tc::fence_async_smem();
+
+  if (tid == 0) {
+    if (tc::smem_u32(base) & 1023u) __trap();
+    for (int i = 0; i < NS; ++i) {
+      tc::mbar_init(&full[i], 4);
+      tc::mbar_init(&a_free[i], 1);
+    }
+    for (int i = 0; i < kWgSlots; ++i) {
+      tc::mbar_init(&d1_full[i], 1);
+      tc::mbar_init(&h_ready[i], kWarps);
+      tc::mbar_init(&d2_full[i], 1);
+      tc::mbar_init(&dout_ready[i], kWarps);
+      tc::mbar_init(&d3_full[i], 1);
+      tc::mbar_init(&slot_free[i], kWarps);
+    }
+    tc::mbar_init(x_ready, kWarps);
+    tc::mbar_init(x_free, 1);
+    tc::mbar_init(&wbar[0], 1);
+    tc::mbar_init(&wbar[1], 1);
+    tc::fence_mbar_init();
+  }
+  if (tid < 32) tc::tmem_alloc(tmem_ptr, 512);
+  tc::tc_fence_before();
+  __syncthreads();
+  tc::tc_fence_after();
+  const uint32_t tmem_base = __shfl_sync(kFull, *tmem_ptr, 0);
+  if (tid == 0) {
+    tc::mbar_expect_tx(&wbar[0], kWiBytes);
+    tc::tma_bulk_g2s(base, wimg, kWiBytes, &wbar[0]);
+    tc::mbar_expect_tx(&wbar[1], 16384);
+    tc::tma_bulk_g2s(base + Cfg::kSmWb, wimg + 32768, 16384, &wbar[1]);  // W2^T hi | lo
+  }
+  tc::mbar_wait(&wbar[0], 0);
+  tc::mbar_wait(&wbar[1], 0);
+
+  const uint32_t base_s = tc::smem_u32(base);
+  const int tiles_x = (p.width + kTileW - 1) / kTileW;
+  const int tiles_y = (p.height + kTileH - 1) / kTileH;
+  const int n_tiles = tiles_x * tiles_y * p.batch;
+  const int my_tiles =
+      ((int)blockIdx.x < n_tiles) ? (n_tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+  const uint32_t total_steps = (uint32_t)my_tiles * (uint32_t)n_total;
+  const int R = p.plane_res;
+  const float inv_range = 1.f / p.scene_range;
+  const uint32_t plane_bytes = (uint32_t)R * (uint32_t)R * 128u;
+  const uint32_t lane_addr = (uint32_t)(32 * wig) << 16;
+
+  if (wg >= 3) {
+    // ================================ PRODUCERS (gather only) ================================
+    const int set = wg - 3;
+    uint32_t n0 = 0;  // ring position of the tile's first step
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, n0 += (uint32_t)n_total) {
+      const TileCoord tcd = tile_coord(tile, tiles_x, tiles_y);
+      const int b = tcd.b;
+      int px, py;
+      tile_pixel(tcd.tile_x, tcd.tile_y, wig, lane, px, py);
+      px = min(px, p.width - 1);
+      py = min(py, p.height - 1);
+      const size_t ray = ((size_t)b * p.height + py) * p.width + px;
+      Ray r;
+      setup_ray(p, b, py, px, r);
+      const unsigned char* planes_b =
+          reinterpret_cast<const unsigned char*>(p.planes) + (size_t)b * 3 * plane_bytes;
+      MergeWalk mw;
+      mw.init(p, r, ray, frac);
+      int walked = 0;
+      for (int i = set; i < n_total; i += P) {
+        float z = 0.f;
+        while (walked <= i) {
+          z = mw.pop();
+          ++walked;
+        }
+        const float x0 = (r.ox + r.dx * z) * inv_range, x1 = (r.oy + r.dy * z) * inv_range,
+                    x2 = (r.oz + r.dz * z) * inv_range;
+        ByteTaps tp;
+        byte_taps(x0, x1, R, 0u, tp.o[0], tp.fx[0], tp.fy[0]);
+        byte_taps(x0, x2, R, plane_bytes >> 4, tp.o[1], tp.fx[1], tp.fy[1]);
+        byte_taps(x1, x2, R, plane_bytes >> 3, tp.o[2], tp.fx[2], tp.fy[2]);
+        const uint32_t m = n0 + (uint32_t)i;
+        const uint32_t st = m % NS, u = m / NS;
+        unsigned char* const stage = base + Cfg::kSmA + st * kPipeStageBytes;
+        NFI_STEP_WAIT(&a_free[st], (u & 1) ^ 1);
+        gather_to_tiles_lean<true>(planes_b, R, tp, stage, stage + 16384, 32 * wig, lane,
+                                   base + Cfg::kSmY + st * 16384);
+        tc::fence_async_smem();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&full[st]);
+      }
+    }
+  } else if (wg == 2) {
+    // ================================ MMA ISSUERS ================================
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(Cfg::kAuxRegs));
+    if (wig == 0) {
+      const uint64_t dsc_w1_hi = tc::umma_desc_sw128(base_s + kWiW1Hi);
+      const uint64_t dsc_w1_lo = tc::umma_desc_sw128(base_s + kWiW1Lo);
+      const uint64_t dsc_a0 = tc::umma_desc_sw128(base_s + Cfg::kSmA);
+      uint32_t st = 0, u = 0, sl = 0, v = 0;
+      for (uint32_t m = 0; m < total_steps; ++m) {
+        NFI_STEP_WAIT(&full[st], u & 1);
+        NFI_STEP_WAIT(&slot_free[sl], (v & 1) ^ 1);
+        if (elect_one()) {
+          tc::tc_fence_after();
+          const uint64_t dsc_a = dsc_a0 + (uint64_t)st * (kPipeStageBytes >> 4);
+          tc::issue_layer1_d(tmem_base + sl * kWgSlotCols, dsc_a, dsc_a + (16384 >> 4), dsc_w1_hi,
+                             dsc_w1_lo);
+          tc::umma_commit(&d1_full[sl]);
+        }
+        __syncwarp();
+        if (++st == NS) { st = 0; ++u; }
+        if (++sl == kWgSlots) { sl = 0; ++v; }
+      }
+    } else if (wig == 1) {
+      const uint64_t dsc_w2_hi = tc::umma_desc_sw128(base_s + kWiW2Hi);
+      const uint64_t dsc_w2_lo = tc::umma_desc_sw128(base_s + kWiW2Lo);
+      uint32_t sl = 0, v = 0;
+      for (uint32_t m = 0; m < total_steps; ++m) {
+        NFI_STEP_WAIT(&h_ready[sl], v & 1);
+        if (elect_one()) {
+          tc::tc_fence_after();
+          const uint32_t d = tmem_base + sl * kWgSlotCols;
+          issue_layer2_tt(d + 128, d, d + 64, dsc_w2_hi, dsc_w2_lo);
+          tc::umma_commit(&d2_full[sl]);
+        }
+        __syncwarp();
+        if (++sl == kWgSlots) { sl = 0; ++v; }
+      }
+    } else if (wig == 2) {
+      const uint64_t b_hi = tc::umma_desc_sw128(base_s + Cfg::kSmWb + kWbW2tHi);
+      const uint64_t b_lo = tc::umma_desc_sw128(base_s + Cfg::kSmWb + kWbW2tLo);
+      uint32_t sl = 0, v = 0;
+      for (uint32_t m = 0; m < total_steps; ++m) {
+        NFI_STEP_WAIT(&dout_ready[sl], v & 1);
+        if (elect_one()) {
+          tc::tc_fence_after();
+          const uint32_t d = tmem_base + sl * kWgSlotCols;
+          issue_mma3(d + 160, d + 128, d + 144, b_hi, b_lo);
+          tc::umma_commit(&d3_full[sl]);
+        }
+        __syncwarp();
+        if (++sl == kWgSlots) { sl = 0; ++v; }
+      }
+    } else {
+      // the weight-gradient chain: 8 k-steps of 16 points, [dpre | H]^T x [F | dOut | 1]
+      constexpr uint32_t idesc = tc::umma_idesc_bf16_mn(128, 64);
+      const uint64_t dsc_x = tc::umma_desc_mn_sw128(base_s + Cfg::kSmX, 16384, 1024);
+      const uint32_t dacc = tmem_base + kWgAccCol;
+      uint32_t st = 0, u = 0, sl = 0, v = 0;
+      for (uint32_t m = 0; m < total_steps; ++m) {
+        NFI_STEP_WAIT(&full[st], u & 1);
+        NFI_STEP_WAIT(&dout_ready[sl], v & 1);
+        NFI_STEP_WAIT(x_ready, m & 1);
+        if (elect_one()) {
+          tc::tc_fence_after();
+          const uint64_t dsc_y =
+              tc::umma_desc_mn_sw128(base_s + Cfg::kSmY + st * 16384, 16384, 1024);
+          if (m % kWgFlush == 0) tc::umma_f16_ss<false>(dacc, dsc_x, dsc_y, idesc);  // new chain
+          else tc::umma_f16_ss<true>(dacc, dsc_x, dsc_y, idesc);
+#pragma unroll
+          for (int ks = 1; ks < 8; ++ks)  // 16 points = two 1024-byte row groups
+            tc::umma_f16_ss<true>(dacc, dsc_x + 128 * ks, dsc_y + 128 * ks, idesc);
+          tc::umma_commit(&a_free[st]);
+          tc::umma_commit(x_free);
+        }
+        __syncwarp();
+        if (++st == NS) { st = 0; ++u; }
+        if (++sl == kWgSlots) { sl = 0; ++v; }
+      }
+    }
+  } else if (wg == 0) {
+    // ================================ ACTIVATION (forward and reverse) ================================
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(Cfg::kActRegs));
+    unsigned char* const xrow = base + Cfg::kSmX;
+    // Accumulator row of this thread (TMEM lane gt): rows 0..63 hold dpre_j x [F (cols 0..31) |
+    // . | 1 (col 48)], rows 64..127 hold H_j x dOut (cols 32..47).  `first`: the row buffer is
+    // written, not added to; `final`: the total goes to the global gradients instead.
+    float* const myrow = acc_ws + ((size_t)blockIdx.x * 128 + gt) * 64;
+    const int nout_w = 1 + (p.n_attention > 0 ? p.n_attention : 3);
+    auto flush = [&](bool first, bool final) {
+      const uint32_t dacc = tmem_base + kWgAccCol + lane_addr;
+#pragma unroll 1
+      for (int c = 0; c < 4; ++c) {
+        float v16[16];
+        tc::tmem_ld16(dacc + 16 * c, v16);
+        const bool mine = (gt < kHid) ? (c != 2) : (c == 2);
+        if (!mine) continue;
+        float4* row4 = reinterpret_cast<float4*>(myrow + 16 * c);
+        if (!first) {
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const float4 o = row4[q];
+            v16[4 * q] += o.x;
+            v16[4 * q + 1] += o.y;
+            v16[4 * q + 2] += o.z;
+            v16[4 * q + 3] += o.w;
+          }
+        }
+        if (!final) {
+#pragma unroll
+          for (int q = 0; q < 4; ++q)
+            row4[q] = make_float4(v16[4 * q], v16[4 * q + 1], v16[4 * q + 2], v16[4 * q + 3]);
+        } else if (gt < kHid) {
+          if (c < 2 && g.grad_w1) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) atomicAdd(g.grad_w1 + gt * kC + 16 * c + i, v16[i]);
+          }
+          if (c == 3 && g.grad_b1) atomicAdd(g.grad_b1 + gt, v16[0]);
+        } else if (g.grad_w2) {
+#pragma unroll
+          for (int i = 0; i < 16; ++i)
+            if (i < nout_w) atomicAdd(g.grad_w2 + i * kHid + (gt - kHid), v16[i]);
+        }
+      }
+    };
+    auto act_fwd = [&](uint32_t m) {
+      const uint32_t sl = m % kWgSlots, v = m / kWgSlots;
+      const uint32_t d1 = tmem_base + sl * kWgSlotCols + lane_addr;
+      NFI_STEP_WAIT(&d1_full[sl], v & 1);
+      tc::tc_fence_after();
+#pragma unroll 1
+      for (int c = 0; c < 4; ++c) {
+        float lo[16], hi[16];
+        tc::tmem_ld16(d1 + 16 * c, lo);
+        softplus_split16(lo, hi, b1s + 16 * c);
+        tc::tmem_st16(d1 + 16 * c, lo);
+        tc::tmem_st16(d1 + 64 + 16 * c, hi);
+      }
+      tc::tmem_wait_st();
+      tc::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&h_ready[sl]);
+    };
+    // dpre = dH * sigmoid(pre),  sigmoid(pre) = 1 - exp(-softplus(pre)); dpre and H go to the
+    // X tile in bf16 (row = point = this thread, two MN-major atoms of 64 columns)
+    auto act_bwd = [&](uint32_t m) {
+      const uint32_t sl = m % kWgSlots, v = m / kWgSlots;
+      const uint32_t d = tmem_base + sl * kWgSlotCols + lane_addr;
+      NFI_STEP_WAIT(&d3_full[sl], v & 1);
+      NFI_STEP_WAIT(x_free, (m & 1) ^ 1);  // the previous step's dW MMAs have read the X tile
+      tc::tc_fence_after();
+      // the chain of steps [m - kWgFlush, m) is complete and the next one cannot start before
+      // this step's x_ready: the accumulator is quiescent -> bank it
+      if (m > 0 && m % kWgFlush == 0) flush(m == kWgFlush, false);
+#pragma unroll 1
+      for (int c = 0; c < 4; ++c) {
+        uint32_t r3[16], rh[16], rl[16];
+        tc::tmem_ld16_nowait(d + 160 + 16 * c, r3);
+        tc::tmem_ld16_nowait(d + 64 + 16 * c, rh);
+        tc::tmem_ld16_nowait(d + 16 * c, rl);
+        tc::tmem_wait_ld();
+        float dp[16], hh[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          const float h = __uint_as_float(rh[i]) + __uint_as_float(rl[i]);
+          const float sg = 1.f - tc::ex2_approx(-h * kLog2e);
+          dp[i] = __uint_as_float(r3[i]) * sg;
+          hh[i] = h;
+        }
+        // columns 16c .. 16c+15 of dpre (atom 0) and of H (atom 1): two 16-byte chunks each
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+          const uint32_t off = tc::sw128_offset(gt, 2 * c + q);
+          *reinterpret_cast<uint4*>(xrow + off) =
+              make_uint4(tc::bf16x2_rn(dp[8 * q + 0], dp[8 * q + 1]), tc::bf16x2_rn(dp[8 * q + 2], dp[8 * q + 3]),
+                         tc::bf16x2_rn(dp[8 * q + 4], dp[8 * q + 5]), tc::bf16x2_rn(dp[8 * q + 6], dp[8 * q + 7]));
+          *reinterpret_cast<uint4*>(xrow + 16384 + off) =
+              make_uint4(tc::bf16x2_rn(hh[8 * q + 0], hh[8 * q + 1]), tc::bf16x2_rn(hh[8 * q + 2], hh[8 * q + 3]),
+                         tc::bf16x2_rn(hh[8 * q + 4], hh[8 * q + 5]), tc::bf16x2_rn(hh[8 * q + 6], hh[8 * q + 7]));
+        }
+      }
+      tc::tc_fence_before();
+      tc::fence_async_smem();
+      __syncwarp();
+      if (lane == 0) {
+        mbar_arrive(x_ready);
+        mbar_arrive(&slot_free[sl]);
+      }
+    };
+    if (total_steps > 0) act_fwd(0);
+    for (uint32_t m = 0; m < total_steps; ++m) {
+      if (m + 1 < total_steps) act_fwd(m + 1);
+      act_bwd(m);
+    }
+    // ---- the last chain + the banked ones -> global gradients (one atomic per entry per CTA)
+    if (total_steps > 0) {
+      NFI_STEP_WAIT(x_free, (total_steps - 1) & 1);
+      tc::tc_fence_after();
+      flush(total_steps <= (uint32_t)kWgFlush, true);
+      tc::tc_fence_before();
+    }
+  } else {
+    // ================================ SHADING (forward and reverse) ================================
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(Cfg::kShadeRegs));
+    FieldConst fc;
+    fc.A = p.n_attention;
+    fc.use_sdf = p.use_sdf;
+    const float beta = p.use_sdf ? p.beta[0] : 1.f;
+    fc.inv_beta = p.use_sdf ? 1.f / beta : 0.f;
+    fc.inv_alpha = p.use_sdf ? 1.f / p.alpha[0] : 0.f;
+    float acc_b2[NOUT_PAD];
+#pragma unroll
+    for (int o = 0; o < NOUT_PAD; ++o) acc_b2[o] = 0.f;
+    uint32_t m = 0;
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+      const TileCoord tcd = tile_coord(tile, tiles_x, tiles_y);
+      const int b = tcd.b;
+      int px, py;
+      tile_pixel(tcd.tile_x, tcd.tile_y, wig, lane, px, py);
+      const bool valid = (px < p.width) && (py < p.height);
+      px = min(px, p.width - 1);
+      py = min(py, p.height - 1);
+      const size_t ray = ((size_t)b * p.height + py) * p.width + px;
+      Ray r;
+      setup_ray(p, b, py, px, r);
+      tc::bar_sync(1, kThreads);
+      if (gt < 48)
+        pal[gt] = (p.n_attention > 0 && gt < p.n_attention * 3)
+                      ? p.palette[(size_t)b * p.n_attention * 3 + gt]
+                      : 0.f;
+      tc::bar_sync(1, kThreads);
+
+      // upstream gradients of this ray (zero for padding lanes)
+      const float vz = valid ? 1.f : 0.f;
+      const float g_r = vz * g.g_rgb[ray * 3 + 0], g_g = vz * g.g_rgb[ray * 3 + 1],
+                  g_b = vz * g.g_rgb[ray * 3 + 2];
+      float g_m = (g.g_mask ? vz * g.g_mask[ray] : 0.f);
+      const float out_m = g.out_mask[ray];
+      float o_r = g.out_rgb[ray * 3 + 0], o_g = g.out_rgb[ray * 3 + 1],
+            o_b = g.out_rgb[ray * 3 + 2];
+      if (p.white_background) {
+        g_m -= (g_r + g_g + g_b);
+        const float bg = 1.f - out_m;
+        o_r -= bg;
+        o_g -= bg;
+        o_b -= bg;
+      }
+      const float total = (g_r * o_r + g_g * o_g + g_b * o_b) + g_m * out_m;
+
+      MergeWalk mw;
+      mw.init(p, r, ray, frac);
+      float z = mw.pop();
+      float T = 1.f, prefix = 0.f;
+      for (int i = 0; i < n_total; ++i, ++m) {
+        const bool has_next = (i + 1 < n_total);
+        const float zn = has_next ? mw.pop() : z;
+        const float delta = has_next ? (zn - z) * r.dn : 0.f;
+        const uint32_t sl = m % kWgSlots, v = m / kWgSlots;
+        const uint32_t d = tmem_base + sl * kWgSlotCols + lane_addr;
+        const float wx = r.ox + r.dx * z, wy = r.oy + r.dy * z, wz = r.oz + r.dz * z;
+        const float x0 = wx * inv_range, x1 = wy * inv_range, x2 = wz * inv_range;
+        const float keep = (fabsf(x0) > 1.f || fabsf(x1) > 1.f || fabsf(x2) > 1.f) ? 0.f : 1.f;
+        NFI_STEP_WAIT(&d2_full[sl], v & 1);
+        tc::tc_fence_after();
+        float o16[16];
+        tc::tmem_ld16(d + 128, o16);
+        float out[NOUT_PAD];
+#pragma unroll
+        for (int o = 0; o < NOUT_PAD; ++o) out[o] = o16[o] + b2s[o];
+        // density (models/generator.py:629-636) and its derivative wrt out[0]
+        float sigma, dsig_dout0;
+        if (fc.use_sdf) {
+          const float nd = -out[0];
+          const float e_sdf = tc::ex2_approx(-fabsf(nd) * (fc.inv_beta * kLog2e));
+          const float sg = (nd > 0.f) ? 1.f : ((nd < 0.f) ? -1.f : 0.f);
+          sigma = fc.inv_alpha * ((0.5f + 0.5f * sg * (1.f - e_sdf)) * keep);
+          // analytic derivative also AT the zero crossing (see nfi_backward_pipe.cuh)
+          dsig_dout0 = -(fc.inv_alpha * keep) * 0.5f * e_sdf * fc.inv_beta;
+        } else {
+          const float x = out[0] - 1.f;
+          sigma = (x > 20.f ? x : log1pf(expf(x))) * keep;
+          dsig_dout0 = keep * sigmoid_fast(x);
+        }
+        float probs[NA];
+        float cr, cg, cb;
+        if (fc.A > 0) {
+          float mx = out[1];
+#pragma unroll
+          for (int a = 1; a < NA; ++a) mx = fmaxf(mx, out[1 + a]);
+          float s = 0.f;
+#pragma unroll
+          for (int a = 0; a < NA; ++a) {
+            probs[a] = tc::ex2_approx(out[1 + a] - mx);
+            s += probs[a];
+          }
+          const float inv = __fdividef(1.f, s);
+          cr = cg = cb = 0.f;
+#pragma unroll
+          for (int a = 0; a < NA; ++a) {
+            probs[a] *= inv;
+            cr = fmaf(probs[a], pal[3 * a + 0], cr);
+            cg = fmaf(probs[a], pal[3 * a + 1], cg);
+            cb = fmaf(probs[a], pal[3 * a + 2], cb);
+          }
+        } else {
+          cr = sigmoid_fast(out[1]) * 2.004f - 1.002f;
+          cg = sigmoid_fast(out[2]) * 2.004f - 1.002f;
+          cb = sigmoid_fast(out[3]) * 2.004f - 1.002f;
+#pragma unroll
+          for (int a = 0; a < NA; ++a) probs[a] = 0.f;
+        }
+        // ---- compositing, forward and reverse (nfi_backward.cuh header)
+        const float e_sd = __expf(-sigma * delta);
+        const float a = 1.f - e_sd;
+        const float w = a * T;
+        const float s_i = (g_r * cr + g_g * cg + g_b * cb) + g_m;
+        prefix = fmaf(w, s_i, prefix);
+        const float one_m_a = 1.f - a;
+        const float dsig = delta * one_m_a * (T * s_i - (total - prefix) / (one_m_a + 1e-10f));
+        T = T * (one_m_a + 1e-10f);
+        // ---- field head, reverse
+        float dOut[16];
+#pragma unroll
+        for (int o = 0; o < 16; ++o) dOut[o] = 0.f;
+        dOut[0] = dsig * dsig_dout0;
+        const float wr = w * g_r, wg2 = w * g_g, wb = w * g_b;
+        if (fc.A > 0) {
+          float dp[NA];
+          float dot = 0.f;
+#pragma unroll
+          for (int q = 0; q < NA; ++q) {
+            const float vv = wr * pal[3 * q + 0] + wg2 * pal[3 * q + 1] + wb * pal[3 * q + 2];
+            dp[q] = vv;
+            dot = fmaf(probs[q], vv, dot);
+          }
+#pragma unroll
+          for (int q = 0; q < NA; ++q) dOut[1 + q] = probs[q] * (dp[q] - dot);
+        } else {
+          const float sr = (cr + 1.002f) / 2.004f, sg2 = (cg + 1.002f) / 2.004f,
+                      sb = (cb + 1.002f) / 2.004f;
+          dOut[1] = wr * 2.004f * sr * (1.f - sr);
+          dOut[2] = wg2 * 2.004f * sg2 * (1.f - sg2);
+          dOut[3] = wb * 2.004f * sb * (1.f - sb);
+        }
+#pragma unroll
+        for (int o = 0; o < NOUT_PAD; ++o) acc_b2[o] += dOut[o];
+        // ---- hand dOut to the tensor core: hi/lo into TMEM (MMA3), bf16 into columns 32..47 of
+        //      the step's Y tile (its previous user, step m - 3, is done: the producers waited
+        //      for that before gathering this step into the stage)
+        {
+          float hi[16], lo[16];
+#pragma unroll
+          for (int o = 0; o < 16; ++o) {
+            hi[o] = tc::tf32_hi(dOut[o]);
+            lo[o] = dOut[o] - hi[o];
+          }
+          tc::tmem_st16(d + 128, hi);
+          tc::tmem_st16(d + 144, lo);
+          unsigned char* const yt = base + Cfg::kSmY + (m % NS) * 16384;
+#pragma unroll
+          for (int q = 0; q < 2; ++q)
+            *reinterpret_cast<uint4*>(yt + tc::sw128_offset(gt, 4 + q)) = make_uint4(
+                tc::bf16x2_rn(dOut[8 * q + 0], dOut[8 * q + 1]), tc::bf16x2_rn(dOut[8 * q + 2], dOut[8 * q + 3]),
+                tc::bf16x2_rn(dOut[8 * q + 4], dOut[8 * q + 5]), tc::bf16x2_rn(dOut[8 * q + 6], dOut[8 * q + 7]));
+          tc::tmem_wait_st();
+          tc::tc_fence_before();
+          tc::fence_async_smem();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&dout_ready[sl]);
+        }
+        z = zn;
+      }
+    }
+    if (g.grad_b2 != nullptr) {
+      const int nout = 1 + (p.n_attention > 0 ? p.n_attention : 3);
+#pragma unroll
+      for (int o = 0; o < NOUT_PAD; ++o) {
+        const float sb = warp_sum(acc_b2[o]);
+        if (lane == 0 && o < nout) atomicAdd(g.grad_b2 + o, sb);
+      }
+    }
+  }
+  tc::tc_fence_before();
+  __syncthreads();
+  if (tid < 32) tc::tmem_dealloc(tmem_base, 512);
+}
+
+}  // namespace nfi

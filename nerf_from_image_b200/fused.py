@@ -338,9 +338,11 @@ class FusedTriplaneRender(torch.autograd.Function):
             if DEBUG_RAY is not None and DEBUG_BUF is not None:
                 p.normals, p.noise_seed = _ptr(DEBUG_BUF), int(DEBUG_RAY)
                 p.mlp_mode = cfg.mlp_mode | 0x4000
-            # the tensor-core backward keeps its two weight images here (64 KiB)
-            ws = torch.empty(65536, dtype=torch.uint8, device=dev)
-            p.workspace, p.workspace_bytes = _ptr(ws), 65536
+            # the tensor-core backward keeps its two weight images here (64 KiB), the
+            # weight-gradient kernel one accumulator row buffer per CTA behind them
+            ws_bytes = _lib.BACKWARD_WORKSPACE_BYTES if (n_w1 or n_b1 or n_w2 or n_b2) else 65536
+            ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+            p.workspace, p.workspace_bytes = _ptr(ws), ws_bytes
             _lib.check(lib.nfi_render_backward(ctypes.byref(p), ctypes.byref(g), stream))
             gplanes = None
             if n_planes:  # gradient in the layout the planes came in

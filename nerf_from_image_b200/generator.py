@@ -89,7 +89,8 @@ class FusedGeneratorFront:
             raise _lib.NfiError('FusedGeneratorFront: outside its envelope (no_grad, outputs '
                                 'within %r)' % (SUPPORTED_OUTPUTS,))
         if g.use_viewdir and viewdir is not None:
-            raise NotImplementedError('--use_viewdir is outside the fused path')
+            raise NotImplementedError('view-direction-conditioned models (--use_viewdir) keep the '
+                                      'reference front-end: render() routes them there')
         ws, batch = resolve_ws(g, c)
         attention_values, w_synthesis = resolve_palette(g, ws, request_model_outputs, model_inputs)
         # ---- planes (generator.py:471-477), channel-last
@@ -132,7 +133,8 @@ class HeadsGeneratorFront:
         from .heads import regulariser_heads
         g = self.g
         if g.use_viewdir and viewdir is not None:
-            raise NotImplementedError('--use_viewdir is outside the fused path')
+            raise NotImplementedError('view-direction-conditioned models (--use_viewdir) keep the '
+                                      'reference front-end: render() routes them there')
         ws, batch = resolve_ws(g, c)
         if 'path_length' in request_model_outputs:
             assert torch.is_grad_enabled()

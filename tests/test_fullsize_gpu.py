@@ -33,17 +33,18 @@ def _leaves(scene, cams, names, cam_names):
     return sc, cm
 
 
-@pytest.mark.parametrize('case,mode', [('p3d_plain', 4), ('p3d_plain', 1), ('cub_ortho', 4),
-                                       ('p3d_bbox', 4)])
-def test_backward_at_benchmark_geometry(cuda_lib, case, mode):
+@pytest.mark.parametrize('case,mode,wgrad', [('p3d_plain', 4, False), ('p3d_plain', 1, True),
+                                             ('cub_ortho', 4, False), ('p3d_bbox', 4, False),
+                                             ('p3d_plain', 4, True), ('cub_ortho', 4, True)])
+def test_backward_at_benchmark_geometry(cuda_lib, case, mode, wgrad):
     torch.backends.cuda.matmul.allow_tf32 = False
     torch.backends.cudnn.allow_tf32 = False
     B, H, W, S = 1, 128, 128, 64
     scene, cams = Hh.make_case(case, batch=B, plane_res=256, device='cuda')
     nt, nu = synthetic.make_noise(51, B, H, W, S, device='cuda')
-    # mode 4 (tcgen05, frozen decoder = the inversion setting) / mode 1 (SIMT, GAN G-step:
-    # decoder weights too)
-    names = ['planes', 'palette', 'beta', 'alpha'] + (['w1', 'b1', 'w2', 'b2'] if mode == 1 else [])
+    # mode 4 (tcgen05; frozen decoder = the inversion setting, or with wgrad the GAN G-step:
+    # render_backward_pipe + render_wgrad_pipe) / mode 1 (SIMT, decoder weights too)
+    names = ['planes', 'palette', 'beta', 'alpha'] + (['w1', 'b1', 'w2', 'b2'] if wgrad else [])
     cam_names = [k for k in ('c2w', 'focal', 'bbox', 'center') if cams[k] is not None]
     wr, wm = _weights((B, H, W, 3), (B, H, W), 'cuda')
 
@@ -70,6 +71,11 @@ def test_backward_at_benchmark_geometry(cuda_lib, case, mode):
     for n, a, b in zip(names + cam_names, got, gref):
         err = Hh.rel_l2(a.double(), b)
         tol = 2e-4 if mode == 1 else (5e-3 if n == 'beta' else 1e-3)
+        if mode != 1 and n in ('w1', 'b1', 'w2'):
+            # render_wgrad_pipe: ONE bf16 per operand of the weight-gradient GEMM (measured
+            # 9e-4 .. 1.2e-3 / 1e-4 .. 7e-4 / 2e-4 .. 4e-4, nfi_wgrad_pipe.cuh header; the fp32
+            # SIMT kernel, mode 1 above, is at 3e-5)
+            tol = 3e-3
         assert err < tol, (n, err)
 
 
