@@ -359,14 +359,15 @@ __device__ __forceinline__ float4 ldg_nc_volatile_next(const float4* p) {  // th
                : "l"(p));
   return r;
 }
-// WITH_Y: also the features rounded to bf16 into columns 0..31 of a [128 rows][64 bf16]
-// SWIZZLE_128B tile (the MN-major B operand of the weight-gradient chain, nfi_wgrad_pipe.cuh).
-template <bool WITH_Y = false>
+// BF16: the features as a bf16 hi/lo PAIR in two [128 rows][32 bf16] SWIZZLE_64B tiles (64-byte
+// rows) instead of the TF32 pair in two SWIZZLE_128B tiles: half the bytes, and a layout that is
+// both the K-major A operand of a kind::f16 layer-1 MMA and -- rows = K -- an MN-major B operand
+// (nfi_wgrad_pipe.cuh).
+template <bool BF16 = false>
 __device__ __forceinline__ void gather_to_tiles_lean(const unsigned char* __restrict__ planes_b,
                                                      int R, const ByteTaps& tp,
                                                      unsigned char* a_hi, unsigned char* a_lo,
-                                                     int row0, int lane,
-                                                     unsigned char* y_tile = nullptr) {
+                                                     int row0, int lane) {
   const int q = lane >> 3, k = lane & 7;
   const uint32_t row_units = (uint32_t)R * 8u;
 #pragma unroll 1
@@ -401,17 +402,24 @@ __device__ __forceinline__ void gather_to_tiles_lean(const unsigned char* __rest
     }
     const float third = 0.33333334f;
     const float4 f = make_float4(lo.x * third, lo.y * third, hi.x * third, hi.y * third);
-    const float4 fh = make_float4(tc::tf32_hi(f.x), tc::tf32_hi(f.y), tc::tf32_hi(f.z),
-                                  tc::tf32_hi(f.w));
-    const float4 fl = make_float4(f.x - fh.x, f.y - fh.y, f.z - fh.z, f.w - fh.w);
-    const uint32_t offs = tc::sw128_offset(row0 + src, k);
-    *reinterpret_cast<float4*>(a_hi + offs) = fh;
-    *reinterpret_cast<float4*>(a_lo + offs) = fl;
-    if constexpr (WITH_Y) {
-      uint2 yb;
-      asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(yb.x) : "f"(f.y), "f"(f.x));
-      asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(yb.y) : "f"(f.w), "f"(f.z));
-      *reinterpret_cast<uint2*>(y_tile + tc::sw128_offset(row0 + src, k >> 1) + (k & 1) * 8) = yb;
+    if constexpr (BF16) {
+      uint2 h, l;
+      asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(h.x) : "f"(f.y), "f"(f.x));
+      asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(h.y) : "f"(f.w), "f"(f.z));
+      const float rx = f.x - __uint_as_float(h.x << 16), ry = f.y - __uint_as_float(h.x & 0xFFFF0000u);
+      const float rz = f.z - __uint_as_float(h.y << 16), rw = f.w - __uint_as_float(h.y & 0xFFFF0000u);
+      asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(l.x) : "f"(ry), "f"(rx));
+      asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(l.y) : "f"(rw), "f"(rz));
+      const uint32_t offs = tc::sw64_offset(row0 + src, k >> 1) + (k & 1) * 8;
+      *reinterpret_cast<uint2*>(a_hi + offs) = h;
+      *reinterpret_cast<uint2*>(a_lo + offs) = l;
+    } else {
+      const float4 fh = make_float4(tc::tf32_hi(f.x), tc::tf32_hi(f.y), tc::tf32_hi(f.z),
+                                    tc::tf32_hi(f.w));
+      const float4 fl = make_float4(f.x - fh.x, f.y - fh.y, f.z - fh.z, f.w - fh.w);
+      const uint32_t offs = tc::sw128_offset(row0 + src, k);
+      *reinterpret_cast<float4*>(a_hi + offs) = fh;
+      *reinterpret_cast<float4*>(a_lo + offs) = fl;
     }
   }
 }

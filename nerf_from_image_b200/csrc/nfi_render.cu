@@ -507,13 +507,8 @@ int nfi_render_backward(const nfi_render_params* params, const nfi_render_grads*
                       ((g.grad_origins == nullptr) == (g.grad_dirs == nullptr));
   // decoder-weight gradients (the GAN generator step, run.py:1044) on tcgen05 too: a second
   // kernel (render_wgrad_pipe) beside render_backward_pipe, which then sees a frozen decoder.
-  // An upstream gradient of the coords output stays on the SIMT kernel, and so do small
-  // renders under NFI_MLP_AUTO (below 2^20 points the fp32 kernel takes a few hundred
-  // microseconds and has none of the 1e-3 bf16 operand rounding of the tensor-core chain).
-  const long long n_points = (long long)p.batch * p.height * p.width * p.num_samples *
-                             (p.fine_sampling ? 2 : 1);
-  const bool tc_ok = tc_env && (!wgrad || (!g.g_extra && (mode != NFI_MLP_AUTO ||
-                                                           n_points >= (1ll << 20)) &&
+  // An upstream gradient of the coords output stays on the SIMT kernel.
+  const bool tc_ok = tc_env && (!wgrad || (!g.g_extra &&
                                            p.workspace_bytes >= nfi::pipe_wgrad_workspace_bytes(
                                                                     (unsigned)kMaxPersistentCtas)));
   if (tc_ok) {

@@ -217,6 +217,15 @@ __device__ __forceinline__ uint32_t sw128_offset(int row, int chunk) {
   return (uint32_t)((row >> 3) * 1024 + (row & 7) * 128 + ((chunk ^ (row & 7)) << 4));
 }
 
+// byte offset of (row, 16-byte chunk) inside a [rows x 64 B] SWIZZLE_64B tile (chunk 0..3) and a
+// [rows x 32 B] SWIZZLE_32B tile (chunk 0..1): address bits [4,6) / [4,5) XOR bits [7,9) / [7,8)
+__device__ __forceinline__ uint32_t sw64_offset(int row, int chunk) {
+  return (uint32_t)(row * 64 + ((chunk ^ ((row >> 1) & 3)) << 4));
+}
+__device__ __forceinline__ uint32_t sw32_offset(int row, int chunk) {
+  return (uint32_t)(row * 32 + ((chunk ^ ((row >> 2) & 1)) << 4));
+}
+
 __device__ __forceinline__ float tf32_hi(float x) {
   return __uint_as_float(__float_as_uint(x) & 0xFFFFE000u);
 }

@@ -5,37 +5,33 @@
 //   dW2[o][j] = sum_points dOut[p][o] H[p][j]      db2[o] = sum_points dOut[p][o]
 //
 // are contractions over the POINTS, i.e. over what the other GEMMs of the path keep as the M
-// dimension (TMEM lane = point).  tcgen05 reads MN-major operands from shared memory (for 16-bit
-// types with the ordinary 128-byte swizzle; TF32 would need the 32-byte-atomicity layout, which
-// the K-major feature tiles of MMA1 cannot double as), so a step's operands are laid down
-// point-major in bf16 and ONE accumulating MMA chain per 128-point step (kind::f16, M128 N64,
-// eight K16 instructions) forms all three products at once:
+// dimension (TMEM lane = point).  tcgen05 reads MN-major ("transposed") operands from shared
+// memory -- for 16-bit types with every swizzle; TF32 would need the 32-byte-atomicity layout,
+// which a K-major feature tile cannot double as -- so every operand of a step is laid down
+// point-major as a bf16 hi/lo PAIR (2^-17: these sums are dominated by a few very large terms,
+// single bf16 operands left 1e-3 at every size; with pairs 3e-5 against the fp32 kernel,
+// profiles/r2_wgrad_tc_accuracy.txt) and five accumulating kind::f16 MMAs per 16 points form
 //
-//   A = X^T,  X [128 points][128] = [ dpre (64) | H (64) ]         (2 MN atoms of 64 bf16)
-//   B = Y^T,  Y [128 points][64]  = [ F (32) | dOut (16) | 1 0.. ]  (1 MN atom, one per A stage)
-//   D [128][64] += X^T Y :  rows 0..63  x cols 0..31  = dW1        rows 0..63 x col 48 = db1
-//                           rows 64..127 x cols 32..47 = dW2^T     (the other blocks are unused)
+//   XA = [ dpre_hi (64) | dpre_lo (64) ]   XB = [ H_hi (64) | H_lo (64) ]      (A operands, M = 128)
+//   [448,480) += XA^T F_hi,  += XA^T F_lo      rows j and 64 + j together: dW1[j][.]
+//   [480,496) += XB^T dOut_hi, += XB^T dOut_lo   rows j and 64 + j together: dW2[.][j]
+//   [496,504) += XA^T 1                          db1[j]
 //
-// accumulated in fp32 in 64 TMEM columns (chains of kWgFlush steps, banked in fp32) and added to
-// the global gradients once per CTA; db2 is summed in fp32 registers by the shading threads.
-// Accuracy: every operand is ONE bf16 (round-to-nearest, 2^-9).  These sums are dominated by a
-// few very large terms (samples at the surface of rays with a large upstream gradient), so the
-// roundings do not average out with the number of points: measured against the fp32 kernel
-// dW1 9e-4 .. 1.2e-3, db1 1e-4 .. 7e-4, dW2 2e-4 .. 4e-4 relative L2 at every size
-// (profiles/r2_wgrad_tc_accuracy.txt; hi/lo pairs on one side only do not help: dpre pairs make
-// db1 exact and leave dW1 where it is).  Pairs on both sides need twice the operand tiles,
-// which the 227 KB beside MMA1's fp32 stages do not hold.  The fp32 SIMT
-// kernel (3e-5) stays selectable (NFI_MLP_FP32_SIMT) and serves small renders by itself.
+// in 56 TMEM columns, cut into chains of kWgFlush steps that are banked in fp32 (below) and added
+// to the global gradients once per CTA.  db2 is summed in fp32 registers by the shading threads.
 //
-// The kernel re-runs the recompute chain of render_backward_pipe in its 3xTF32 form (gather ->
-// MMA1 -> softplus -> MMA2 -> reverse compositing -> MMA3 -> softplus') but neither MMA4 nor
-// the scatter: plane / palette / pose gradients come from render_backward_pipe, launched beside
-// it (the decoder is then a constant of that kernel), which leaves the shared memory (X tile,
-// Y tiles) and TMEM columns this one needs.  Roles as nfi_backward_pipe.cuh; TMEM: two slots of
-// 224 columns
+// To make room for the pair tiles, layer 1 of the recompute chain runs on bf16 pairs too (as the
+// synthesis convolutions do): the gather writes the features as two [128][32 bf16] SWIZZLE_64B
+// tiles (16 KB per stage instead of 32) that are BOTH the K-major A operand of MMA1 and, rows = K,
+// the MN-major B operand of the dW1 products.  The rest of the chain is render_backward_pipe's
+// (MMA2 / MMA3 in 3xTF32, softplus and its reverse, reverse compositing); MMA4 and the scatter are
+// gone: plane / palette / pose gradients come from render_backward_pipe, launched beside this
+// kernel with the decoder as a constant.  TMEM: two slots of 224 columns
 //   [0,64) D1 -> H_lo   [64,128) H_hi   [128,144) D2 -> dOut_hi   [144,160) dOut_lo   [160,224) D3
-// and the accumulator at [448,512).
+// and the accumulators at [448,504).
 #pragma once
+#include <cuda_bf16.h>
+
 #include "nfi_backward_pipe.cuh"
 
 namespace nfi {
@@ -55,11 +51,14 @@ constexpr size_t kWgAccBytesPerCta = 128 * 64 * sizeof(float);
 struct WgCfg {
   static constexpr int P = 2;
   static constexpr int kThreadsTotal = 384 + 128 * P;
+  static constexpr int kStageBytes = 16384;                           // F_hi | F_lo, 8 KB each
   static constexpr int kSmWb = 25600;                                 // W2^T hi / lo (16 KB)
-  static constexpr int kSmA = kSmWb + 16384;                          // 41 * 1024
-  static constexpr int kSmY = kSmA + kWgStages * kPipeStageBytes;     // 137 * 1024: 3 x 16 KB
-  static constexpr int kSmX = kSmY + kWgStages * 16384;               // 185 * 1024: 32 KB
-  static constexpr int kSmPal = kSmX + 32768;
+  static constexpr int kSmW1 = kSmWb + 16384;                         // 41 * 1024: W1 bf16 hi | lo
+  static constexpr int kSmA = kSmW1 + 8192;                           // 49 * 1024
+  static constexpr int kSmX = kSmA + kWgStages * kStageBytes;         // 97 * 1024: 4 x 16 KB
+  static constexpr int kSmE = kSmX + 65536;                           // 161 * 1024: dOut hi | lo
+  static constexpr int kSmOnes = kSmE + 8192;                         // 169 * 1024: 1 KB of 1.0
+  static constexpr int kSmPal = kSmOnes + 1024;
   static constexpr int kSmFrac = kSmPal + 48 * 4;
   static constexpr int kSmBars = kSmFrac + 128 * 4;
   // full[3], a_free[3], per slot: d1_full, h_ready, d2_full, dout_ready, d3_full, slot_free;
@@ -73,8 +72,9 @@ struct WgCfg {
   static constexpr int kAuxRegs = 24;
 };
 static_assert(WgCfg::kSmBytes <= 227 * 1024, "shared memory budget");
-static_assert((WgCfg::kSmA & 1023) == 0 && (WgCfg::kSmX & 1023) == 0 && (WgCfg::kSmY & 1023) == 0,
-              "SWIZZLE_128B tiles are 1024-byte aligned");
+static_assert((WgCfg::kSmA & 1023) == 0 && (WgCfg::kSmX & 1023) == 0 && (WgCfg::kSmE & 1023) == 0 &&
+                  (WgCfg::kSmW1 & 1023) == 0 && (WgCfg::kSmOnes & 1023) == 0,
+              "swizzled tiles are 1024-byte aligned");
 
 namespace tc {
 // two floats -> packed bf16 pair (round-to-nearest-even), `lo` in the low half (lower address)
@@ -83,25 +83,26 @@ __device__ __forceinline__ uint32_t bf16x2_rn(float lo, float hi) {
   asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(y) : "f"(hi), "f"(lo));
   return y;
 }
-// Shared-memory matrix descriptor, MN-major, SWIZZLE_128B, 16-bit elements: an atom is 64
-// elements of the M/N dimension (128 contiguous bytes) x 8 K rows (128 B apart, 16-byte chunks
-// XOR-swizzled with the row); `lbo` = bytes between atoms along M/N, `sbo` = bytes between
-// 8-row K groups (a K16 instruction reads two of them).
-__device__ __forceinline__ uint64_t umma_desc_mn_sw128(uint32_t smem_addr, uint32_t lbo,
-                                                       uint32_t sbo) {
+// Shared-memory matrix descriptors for 16-bit operands.  `layout`: 2 = SWIZZLE_128B (128-byte
+// rows), 4 = SWIZZLE_64B (64-byte rows), 6 = SWIZZLE_32B (32-byte rows).  K-major: rows = M / N,
+// `sbo` = bytes between 8-row groups.  MN-major: rows = K, a row holds 64 / 32 / 16 elements of
+// M / N; `lbo` = bytes between such atoms along M / N, `sbo` = bytes between 8-row K groups (a
+// K16 instruction reads two of them).
+__device__ __forceinline__ uint64_t umma_desc(uint32_t smem_addr, uint32_t layout, uint32_t lbo,
+                                              uint32_t sbo) {
   uint64_t d = 0;
   d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
   d |= (uint64_t)((lbo >> 4) & 0x3FFF) << 16;
   d |= (uint64_t)((sbo >> 4) & 0x3FFF) << 32;
   d |= (uint64_t)1 << 46;
-  d |= (uint64_t)2 << 61;
+  d |= (uint64_t)layout << 61;
   return d;
 }
-// Instruction descriptor, kind::f16 with bf16 operands, fp32 accumulate, A and B MN-major:
-//   [4,6) c_format=1 (F32)  [7,10) a_format=1 (BF16)  [10,13) b_format=1  [15] / [16] MN-major
-//   [17,23) N>>3            [24,29) M>>4
-__host__ __device__ constexpr uint32_t umma_idesc_bf16_mn(int M, int N) {
-  return (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) |
+// Instruction descriptor, kind::f16 with bf16 operands, fp32 accumulate:
+//   [4,6) c_format=1 (F32)  [7,10) a_format=1 (BF16)  [10,13) b_format=1
+//   [15] A MN-major  [16] B MN-major  [17,23) N>>3  [24,29) M>>4
+__host__ __device__ constexpr uint32_t umma_idesc_bf16(int M, int N, bool a_mn, bool b_mn) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((a_mn ? 1u : 0u) << 15) | ((b_mn ? 1u : 0u) << 16) |
          ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 template <bool ACC>
@@ -147,11 +148,11 @@ render_wgrad_pipe(const nfi_render_params p, const nfi_render_grads g,
   uint64_t* d1_full = a_free + NS;            // [2] commit
   uint64_t* h_ready = d1_full + kWgSlots;     // [2] 4 warps
   uint64_t* d2_full = h_ready + kWgSlots;     // [2] commit
-  uint64_t* dout_ready = d2_full + kWgSlots;  // [2] 4 warps (dOut in TMEM and in the Y tile)
+  uint64_t* dout_ready = d2_full + kWgSlots;  // [2] 4 warps (dOut in TMEM and in the E tiles)
   uint64_t* d3_full = dout_ready + kWgSlots;  // [2] commit
   uint64_t* slot_free = d3_full + kWgSlots;   // [2] 4 warps (D3 / H read)
   uint64_t* x_ready = slot_free + kWgSlots;   // X tile written (4 warps)
-  uint64_t* x_free = x_ready + 1;             // X tile read by the dW MMAs (commit)
+  uint64_t* x_free = x_ready + 1;             // X and E tiles read by the dW MMAs (commit)
   uint64_t* wbar = x_free + 1;                // [2] weight images landed
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(base + Cfg::kSmTmemPtr);
   const float* b1s = reinterpret_cast<const float*>(base + kWiB1);
@@ -159,14 +160,21 @@ render_wgrad_pipe(const nfi_render_params p, const nfi_render_grads g,
   float* pal = reinterpret_cast<float*>(base + Cfg::kSmPal);
   float* frac = reinterpret_cast<float*>(base + Cfg::kSmFrac);
   if (tid < 128) frac[tid] = (float)tid / (float)S;
-  // the constant part of the Y tiles: column 48 = 1 (-> db1), columns 49..63 = 0 (chunks 6, 7)
-  for (int i = tid; i < NS * 128; i += Cfg::kThreadsTotal) {
-    unsigned char* yt = base + Cfg::kSmY + (i >> 7) * 16384;
-    *reinterpret_cast<uint4*>(yt + tc::sw128_offset(i & 127, 6)) = make_uint4(0x3F80u, 0u, 0u, 0u);
-    *reinterpret_cast<uint4*>(yt + tc::sw128_offset(i & 127, 7)) = make_uint4(0u, 0u, 0u, 0u);
+  // constants in shared memory: 1 KB of bf16 ones (the B operand of db1) and layer 1's weights
+  // (x log2 e, as the forward weight image has them) as a bf16 hi / lo pair, [64 rows = hidden
+  // unit][32 k] K-major SWIZZLE_64B
+  for (int i = tid; i < 256; i += Cfg::kThreadsTotal)
+    reinterpret_cast<uint32_t*>(base + Cfg::kSmOnes)[i] = 0x3F803F80u;
+  for (int i = tid; i < kHid * kC; i += Cfg::kThreadsTotal) {
+    const int j = i / kC, c = i % kC;
+    const float w = p.w1[i] * kLog2e;
+    const __nv_bfloat16 hi = __float2bfloat16_rn(w);
+    const __nv_bfloat16 lo = __float2bfloat16_rn(w - __bfloat162float(hi));
+    const uint32_t off = tc::sw64_offset(j, c >> 3) + (c & 7) * 2;
+    *reinterpret_cast<__nv_bfloat16*>(base + Cfg::kSmW1 + off) = hi;
+    *reinterpret_cast<__nv_bfloat16*>(base + Cfg::kSmW1 + 4096 + off) = lo;
   }
   tc::fence_async_smem();
-
   if (tid == 0) {
     if (tc::smem_u32(base) & 1023u) __trap();
     for (int i = 0; i < NS; ++i) {
@@ -246,10 +254,9 @@ render_wgrad_pipe(const nfi_render_params p, const nfi_render_grads g,
         byte_taps(x1, x2, R, plane_bytes >> 3, tp.o[2], tp.fx[2], tp.fy[2]);
         const uint32_t m = n0 + (uint32_t)i;
         const uint32_t st = m % NS, u = m / NS;
-        unsigned char* const stage = base + Cfg::kSmA + st * kPipeStageBytes;
+        unsigned char* const stage = base + Cfg::kSmA + st * Cfg::kStageBytes;
         NFI_STEP_WAIT(&a_free[st], (u & 1) ^ 1);
-        gather_to_tiles_lean<true>(planes_b, R, tp, stage, stage + 16384, 32 * wig, lane,
-                                   base + Cfg::kSmY + st * 16384);
+        gather_to_tiles_lean<true>(planes_b, R, tp, stage, stage + 8192, 32 * wig, lane);
         tc::fence_async_smem();
         __syncwarp();
         if (lane == 0) mbar_arrive(&full[st]);
@@ -259,18 +266,26 @@ render_wgrad_pipe(const nfi_render_params p, const nfi_render_grads g,
     // ================================ MMA ISSUERS ================================
     asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(Cfg::kAuxRegs));
     if (wig == 0) {
-      const uint64_t dsc_w1_hi = tc::umma_desc_sw128(base_s + kWiW1Hi);
-      const uint64_t dsc_w1_lo = tc::umma_desc_sw128(base_s + kWiW1Lo);
-      const uint64_t dsc_a0 = tc::umma_desc_sw128(base_s + Cfg::kSmA);
+      // layer 1 on bf16 pairs: D1 = F_lo W1_hi + F_hi W1_lo + F_hi W1_hi, K = 32 = two K16 steps
+      constexpr uint32_t idesc1 = tc::umma_idesc_bf16(128, 64, false, false);
+      const uint64_t dsc_w1_hi = tc::umma_desc(base_s + Cfg::kSmW1, 4, 16, 512);
+      const uint64_t dsc_w1_lo = tc::umma_desc(base_s + Cfg::kSmW1 + 4096, 4, 16, 512);
       uint32_t st = 0, u = 0, sl = 0, v = 0;
       for (uint32_t m = 0; m < total_steps; ++m) {
         NFI_STEP_WAIT(&full[st], u & 1);
         NFI_STEP_WAIT(&slot_free[sl], (v & 1) ^ 1);
         if (elect_one()) {
           tc::tc_fence_after();
-          const uint64_t dsc_a = dsc_a0 + (uint64_t)st * (kPipeStageBytes >> 4);
-          tc::issue_layer1_d(tmem_base + sl * kWgSlotCols, dsc_a, dsc_a + (16384 >> 4), dsc_w1_hi,
-                             dsc_w1_lo);
+          const uint32_t stage_s = base_s + Cfg::kSmA + st * Cfg::kStageBytes;
+          const uint64_t a_hi = tc::umma_desc(stage_s, 4, 16, 512);
+          const uint64_t a_lo = tc::umma_desc(stage_s + 8192, 4, 16, 512);
+          const uint32_t d1 = tmem_base + sl * kWgSlotCols;
+          tc::umma_f16_ss<false>(d1, a_lo, dsc_w1_hi, idesc1);
+          tc::umma_f16_ss<true>(d1, a_lo + 2, dsc_w1_hi + 2, idesc1);
+          tc::umma_f16_ss<true>(d1, a_hi, dsc_w1_lo, idesc1);
+          tc::umma_f16_ss<true>(d1, a_hi + 2, dsc_w1_lo + 2, idesc1);
+          tc::umma_f16_ss<true>(d1, a_hi, dsc_w1_hi, idesc1);
+          tc::umma_f16_ss<true>(d1, a_hi + 2, dsc_w1_hi + 2, idesc1);
           tc::umma_commit(&d1_full[sl]);
         }
         __syncwarp();
@@ -308,10 +323,16 @@ render_wgrad_pipe(const nfi_render_params p, const nfi_render_grads g,
         if (++sl == kWgSlots) { sl = 0; ++v; }
       }
     } else {
-      // the weight-gradient chain: 8 k-steps of 16 points, [dpre | H]^T x [F | dOut | 1]
-      constexpr uint32_t idesc = tc::umma_idesc_bf16_mn(128, 64);
-      const uint64_t dsc_x = tc::umma_desc_mn_sw128(base_s + Cfg::kSmX, 16384, 1024);
-      const uint32_t dacc = tmem_base + kWgAccCol;
+      // the weight-gradient chain: 8 k-steps of 16 points, five MMAs each
+      constexpr uint32_t id_w1 = tc::umma_idesc_bf16(128, 32, true, true);
+      constexpr uint32_t id_w2 = tc::umma_idesc_bf16(128, 16, true, true);
+      constexpr uint32_t id_b1 = tc::umma_idesc_bf16(128, 8, true, false);
+      const uint64_t dsc_xa = tc::umma_desc(base_s + Cfg::kSmX, 2, 16384, 1024);
+      const uint64_t dsc_xb = tc::umma_desc(base_s + Cfg::kSmX + 32768, 2, 16384, 1024);
+      const uint64_t dsc_ehi = tc::umma_desc(base_s + Cfg::kSmE, 6, 16, 256);
+      const uint64_t dsc_elo = tc::umma_desc(base_s + Cfg::kSmE + 4096, 6, 16, 256);
+      const uint64_t dsc_one = tc::umma_desc(base_s + Cfg::kSmOnes, 6, 16, 256);  // K-major [8][16]
+      const uint32_t d_w1 = tmem_base + kWgAccCol, d_w2 = d_w1 + 32, d_b1 = d_w1 + 48;
       uint32_t st = 0, u = 0, sl = 0, v = 0;
       for (uint32_t m = 0; m < total_steps; ++m) {
         NFI_STEP_WAIT(&full[st], u & 1);
@@ -319,13 +340,25 @@ render_wgrad_pipe(const nfi_render_params p, const nfi_render_grads g,
         NFI_STEP_WAIT(x_ready, m & 1);
         if (elect_one()) {
           tc::tc_fence_after();
-          const uint64_t dsc_y =
-              tc::umma_desc_mn_sw128(base_s + Cfg::kSmY + st * 16384, 16384, 1024);
-          if (m % kWgFlush == 0) tc::umma_f16_ss<false>(dacc, dsc_x, dsc_y, idesc);  // new chain
-          else tc::umma_f16_ss<true>(dacc, dsc_x, dsc_y, idesc);
+          const uint32_t stage_s = base_s + Cfg::kSmA + st * Cfg::kStageBytes;
+          const uint64_t dsc_fhi = tc::umma_desc(stage_s, 4, 16, 512);        // MN-major: rows = K
+          const uint64_t dsc_flo = tc::umma_desc(stage_s + 8192, 4, 16, 512);
+          const bool fresh = (m % kWgFlush == 0);  // new chain: the first MMA into each accumulator overwrites
 #pragma unroll
-          for (int ks = 1; ks < 8; ++ks)  // 16 points = two 1024-byte row groups
-            tc::umma_f16_ss<true>(dacc, dsc_x + 128 * ks, dsc_y + 128 * ks, idesc);
+          for (int ks = 0; ks < 8; ++ks) {  // 16 points: 2048 B of X, 1024 B of F, 512 B of dOut
+            const uint64_t xa = dsc_xa + 128 * ks, xb = dsc_xb + 128 * ks;
+            if (ks == 0 && fresh) {
+              tc::umma_f16_ss<false>(d_w1, xa, dsc_fhi, id_w1);
+              tc::umma_f16_ss<false>(d_w2, xb, dsc_ehi, id_w2);
+              tc::umma_f16_ss<false>(d_b1, xa, dsc_one, id_b1);
+            } else {
+              tc::umma_f16_ss<true>(d_w1, xa, dsc_fhi + 64 * ks, id_w1);
+              tc::umma_f16_ss<true>(d_w2, xb, dsc_ehi + 32 * ks, id_w2);
+              tc::umma_f16_ss<true>(d_b1, xa, dsc_one, id_b1);
+            }
+            tc::umma_f16_ss<true>(d_w1, xa, dsc_flo + 64 * ks, id_w1);
+            tc::umma_f16_ss<true>(d_w2, xb, dsc_elo + 32 * ks, id_w2);
+          }
           tc::umma_commit(&a_free[st]);
           tc::umma_commit(x_free);
         }
@@ -338,23 +371,24 @@ render_wgrad_pipe(const nfi_render_params p, const nfi_render_grads g,
     // ================================ ACTIVATION (forward and reverse) ================================
     asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(Cfg::kActRegs));
     unsigned char* const xrow = base + Cfg::kSmX;
-    // Accumulator row of this thread (TMEM lane gt): rows 0..63 hold dpre_j x [F (cols 0..31) |
-    // . | 1 (col 48)], rows 64..127 hold H_j x dOut (cols 32..47).  `first`: the row buffer is
-    // written, not added to; `final`: the total goes to the global gradients instead.
+    // Accumulator row of this thread (TMEM lane gt), hidden unit j = gt % 64 (rows 64.. are the
+    // products of the lo halves): columns 0..31 dW1[j][.], 32..47 dW2[.][j], 48 db1[j].
+    // `first`: the row buffer is written, not added to; `final`: the total goes to the global
+    // gradients instead.
     float* const myrow = acc_ws + ((size_t)blockIdx.x * 128 + gt) * 64;
     const int nout_w = 1 + (p.n_attention > 0 ? p.n_attention : 3);
     auto flush = [&](bool first, bool final) {
       const uint32_t dacc = tmem_base + kWgAccCol + lane_addr;
+      const int j = gt & (kHid - 1);
 #pragma unroll 1
       for (int c = 0; c < 4; ++c) {
         float v16[16];
-        tc::tmem_ld16(dacc + 16 * c, v16);
-        const bool mine = (gt < kHid) ? (c != 2) : (c == 2);
-        if (!mine) continue;
+        tc::tmem_ld16(dacc + 16 * c, v16);  // (c == 3: only column 48 is an accumulator)
         float4* row4 = reinterpret_cast<float4*>(myrow + 16 * c);
         if (!first) {
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
+            if (c == 3 && q > 0) break;
             const float4 o = row4[q];
             v16[4 * q] += o.x;
             v16[4 * q + 1] += o.y;
@@ -364,18 +398,23 @@ render_wgrad_pipe(const nfi_render_params p, const nfi_render_grads g,
         }
         if (!final) {
 #pragma unroll
-          for (int q = 0; q < 4; ++q)
+          for (int q = 0; q < 4; ++q) {
+            if (c == 3 && q > 0) break;
             row4[q] = make_float4(v16[4 * q], v16[4 * q + 1], v16[4 * q + 2], v16[4 * q + 3]);
-        } else if (gt < kHid) {
-          if (c < 2 && g.grad_w1) {
-#pragma unroll
-            for (int i = 0; i < 16; ++i) atomicAdd(g.grad_w1 + gt * kC + 16 * c + i, v16[i]);
           }
-          if (c == 3 && g.grad_b1) atomicAdd(g.grad_b1 + gt, v16[0]);
-        } else if (g.grad_w2) {
+        } else if (c < 2) {
+          if (g.grad_w1) {
 #pragma unroll
-          for (int i = 0; i < 16; ++i)
-            if (i < nout_w) atomicAdd(g.grad_w2 + i * kHid + (gt - kHid), v16[i]);
+            for (int i = 0; i < 16; ++i) atomicAdd(g.grad_w1 + j * kC + 16 * c + i, v16[i]);
+          }
+        } else if (c == 2) {
+          if (g.grad_w2) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i)
+              if (i < nout_w) atomicAdd(g.grad_w2 + i * kHid + j, v16[i]);
+          }
+        } else if (g.grad_b1) {
+          atomicAdd(g.grad_b1 + j, v16[0]);
         }
       }
     };
@@ -398,7 +437,7 @@ render_wgrad_pipe(const nfi_render_params p, const nfi_render_grads g,
       if (lane == 0) mbar_arrive(&h_ready[sl]);
     };
     // dpre = dH * sigmoid(pre),  sigmoid(pre) = 1 - exp(-softplus(pre)); dpre and H go to the
-    // X tile in bf16 (row = point = this thread, two MN-major atoms of 64 columns)
+    // X tiles as bf16 hi / lo pairs (row = point = this thread, MN-major atoms of 64 columns)
     auto act_bwd = [&](uint32_t m) {
       const uint32_t sl = m % kWgSlots, v = m / kWgSlots;
       const uint32_t d = tmem_base + sl * kWgSlotCols + lane_addr;
@@ -423,16 +462,27 @@ render_wgrad_pipe(const nfi_render_params p, const nfi_render_grads g,
           dp[i] = __uint_as_float(r3[i]) * sg;
           hh[i] = h;
         }
-        // columns 16c .. 16c+15 of dpre (atom 0) and of H (atom 1): two 16-byte chunks each
+        // columns 16c .. 16c+15 of dpre_hi / dpre_lo (tiles 0, 1) and H_hi / H_lo (tiles 2, 3):
+        // two 16-byte chunks of this point's 128-byte row in each
 #pragma unroll
         for (int q = 0; q < 2; ++q) {
           const uint32_t off = tc::sw128_offset(gt, 2 * c + q);
-          *reinterpret_cast<uint4*>(xrow + off) =
-              make_uint4(tc::bf16x2_rn(dp[8 * q + 0], dp[8 * q + 1]), tc::bf16x2_rn(dp[8 * q + 2], dp[8 * q + 3]),
-                         tc::bf16x2_rn(dp[8 * q + 4], dp[8 * q + 5]), tc::bf16x2_rn(dp[8 * q + 6], dp[8 * q + 7]));
-          *reinterpret_cast<uint4*>(xrow + 16384 + off) =
-              make_uint4(tc::bf16x2_rn(hh[8 * q + 0], hh[8 * q + 1]), tc::bf16x2_rn(hh[8 * q + 2], hh[8 * q + 3]),
-                         tc::bf16x2_rn(hh[8 * q + 4], hh[8 * q + 5]), tc::bf16x2_rn(hh[8 * q + 6], hh[8 * q + 7]));
+          uint32_t dh[4], dl[4], hh2[4], hl[4];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const float a0 = dp[8 * q + 2 * i], a1 = dp[8 * q + 2 * i + 1];
+            dh[i] = tc::bf16x2_rn(a0, a1);
+            dl[i] = tc::bf16x2_rn(a0 - __uint_as_float(dh[i] << 16),
+                                  a1 - __uint_as_float(dh[i] & 0xFFFF0000u));
+            const float b0 = hh[8 * q + 2 * i], b1v = hh[8 * q + 2 * i + 1];
+            hh2[i] = tc::bf16x2_rn(b0, b1v);
+            hl[i] = tc::bf16x2_rn(b0 - __uint_as_float(hh2[i] << 16),
+                                  b1v - __uint_as_float(hh2[i] & 0xFFFF0000u));
+          }
+          *reinterpret_cast<uint4*>(xrow + off) = make_uint4(dh[0], dh[1], dh[2], dh[3]);
+          *reinterpret_cast<uint4*>(xrow + 16384 + off) = make_uint4(dl[0], dl[1], dl[2], dl[3]);
+          *reinterpret_cast<uint4*>(xrow + 32768 + off) = make_uint4(hh2[0], hh2[1], hh2[2], hh2[3]);
+          *reinterpret_cast<uint4*>(xrow + 49152 + off) = make_uint4(hl[0], hl[1], hl[2], hl[3]);
         }
       }
       tc::tc_fence_before();
@@ -600,9 +650,9 @@ render_wgrad_pipe(const nfi_render_params p, const nfi_render_grads g,
         }
 #pragma unroll
         for (int o = 0; o < NOUT_PAD; ++o) acc_b2[o] += dOut[o];
-        // ---- hand dOut to the tensor core: hi/lo into TMEM (MMA3), bf16 into columns 32..47 of
-        //      the step's Y tile (its previous user, step m - 3, is done: the producers waited
-        //      for that before gathering this step into the stage)
+        // ---- hand dOut to the tensor core: TF32 hi/lo into TMEM (MMA3), a bf16 hi/lo pair into
+        //      the two [128][16] SWIZZLE_32B tiles the dW2 products read (once the previous
+        //      step's chain has read them)
         {
           float hi[16], lo[16];
 #pragma unroll
@@ -612,12 +662,22 @@ render_wgrad_pipe(const nfi_render_params p, const nfi_render_grads g,
           }
           tc::tmem_st16(d + 128, hi);
           tc::tmem_st16(d + 144, lo);
-          unsigned char* const yt = base + Cfg::kSmY + (m % NS) * 16384;
+          NFI_STEP_WAIT(x_free, (m & 1) ^ 1);
+          unsigned char* const et = base + Cfg::kSmE;
 #pragma unroll
-          for (int q = 0; q < 2; ++q)
-            *reinterpret_cast<uint4*>(yt + tc::sw128_offset(gt, 4 + q)) = make_uint4(
-                tc::bf16x2_rn(dOut[8 * q + 0], dOut[8 * q + 1]), tc::bf16x2_rn(dOut[8 * q + 2], dOut[8 * q + 3]),
-                tc::bf16x2_rn(dOut[8 * q + 4], dOut[8 * q + 5]), tc::bf16x2_rn(dOut[8 * q + 6], dOut[8 * q + 7]));
+          for (int q = 0; q < 2; ++q) {
+            uint32_t eh[4], el[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const float a0 = dOut[8 * q + 2 * i], a1 = dOut[8 * q + 2 * i + 1];
+              eh[i] = tc::bf16x2_rn(a0, a1);
+              el[i] = tc::bf16x2_rn(a0 - __uint_as_float(eh[i] << 16),
+                                    a1 - __uint_as_float(eh[i] & 0xFFFF0000u));
+            }
+            const uint32_t off = tc::sw32_offset(gt, q);
+            *reinterpret_cast<uint4*>(et + off) = make_uint4(eh[0], eh[1], eh[2], eh[3]);
+            *reinterpret_cast<uint4*>(et + 4096 + off) = make_uint4(el[0], el[1], el[2], el[3]);
+          }
           tc::tmem_wait_st();
           tc::tc_fence_before();
           tc::fence_async_smem();

@@ -71,11 +71,6 @@ def test_backward_at_benchmark_geometry(cuda_lib, case, mode, wgrad):
     for n, a, b in zip(names + cam_names, got, gref):
         err = Hh.rel_l2(a.double(), b)
         tol = 2e-4 if mode == 1 else (5e-3 if n == 'beta' else 1e-3)
-        if mode != 1 and n in ('w1', 'b1', 'w2'):
-            # render_wgrad_pipe: ONE bf16 per operand of the weight-gradient GEMM (measured
-            # 9e-4 .. 1.2e-3 / 1e-4 .. 7e-4 / 2e-4 .. 4e-4, nfi_wgrad_pipe.cuh header; the fp32
-            # SIMT kernel, mode 1 above, is at 3e-5)
-            tol = 3e-3
         assert err < tol, (n, err)
 
 
