@@ -112,6 +112,18 @@ __device__ __forceinline__ TileCoord tile_coord(int tile, int tiles_x, int tiles
 constexpr int kPipeSlots = 3;
 constexpr int kPipeSlotCols = 160;  // [0,64) D1 then H_lo, [64,128) H_hi, [128,144) D2
 constexpr int kPipeStageBytes = 32768;
+// NFI_L1_BF16: layer 1 of the forward kernel on bf16 hi/lo pairs (operands exact to 2^-17
+// instead of 3xTF32's 2^-22, as nfi_wgrad_pipe.cuh and the synthesis convolutions): the A stage
+// shrinks from 32 KB to 16 KB (two [128][32 bf16] SWIZZLE_64B tiles: half the stores of the
+// gather, 64 KB of shared memory back to the L1), six K16 MMAs instead of twelve K8.
+// Measured (profiles/r2_ab_forward_bf16_l1.txt): 8.52 vs 8.69 ms, 1.9 % -- and the importance-
+// resampled depths move from <= 2e-5 to > 2e-5 of the oracle's (the coarse densities feed an
+// inverse CDF), which costs the gradient tests their margin.  Not worth it: off by default; the
+// weight-gradient kernel, which resamples nothing, uses the bf16 form (nfi_wgrad_pipe.cuh).
+#ifndef NFI_L1_BF16
+#define NFI_L1_BF16 0
+#endif
+constexpr int kFwdStageBytes = NFI_L1_BF16 ? 16384 : 32768;
 
 // scratch per CTA: the tc_scratch layout plus NES parked extras per coarse sample
 __host__ __device__ inline size_t pipe_scratch_floats(int S, int nes) {
@@ -123,7 +135,7 @@ struct PipeCfg {
   static constexpr int kThreadsTotal = 384 + 128 * P;
   static constexpr int kStages = P + 1;  // one spare: a set never waits for its own MMA
   static constexpr int kSmA = 25600;
-  static constexpr int kSmPal = kSmA + kStages * kPipeStageBytes;
+  static constexpr int kSmPal = kSmA + kStages * kFwdStageBytes;
   static constexpr int kSmFrac = kSmPal + 48 * 4;  // s / S for s < 128 (one IEEE division each)
   static constexpr int kSmBars = kSmFrac + 128 * 4;
   // full[P], a_free[P], d1_full[3], h_ready[3], d2_full[3], slot_free[3], cw_ready, zf_ready,
@@ -539,6 +551,22 @@ render_forward_pipe(const nfi_render_params p, const unsigned char* __restrict__
     tc::tma_bulk_g2s(base, wimg, kWiBytes, wbar);
   }
   tc::mbar_wait(wbar, 0);
+#if NFI_L1_BF16
+  // layer 1's weights (x log2 e, as the image has them in TF32) as a bf16 hi / lo pair over the
+  // image's W1 region: [64 rows = hidden unit][32 k] K-major SWIZZLE_64B, 4 KB each
+  __syncthreads();
+  for (int i = tid; i < kHid * kC; i += Cfg::kThreadsTotal) {
+    const int j = i / kC, c = i % kC;
+    const float w = p.w1[i] * kLog2e;
+    const uint32_t hi = tc::bf16x2_rn(w, 0.f) & 0xFFFFu;
+    const uint32_t lo = tc::bf16x2_rn(w - __uint_as_float(hi << 16), 0.f) & 0xFFFFu;
+    const uint32_t off = tc::sw64_offset(j, c >> 3) + (c & 7) * 2;
+    *reinterpret_cast<unsigned short*>(base + kWiW1Hi + off) = (unsigned short)hi;
+    *reinterpret_cast<unsigned short*>(base + kWiW1Hi + 4096 + off) = (unsigned short)lo;
+  }
+  tc::fence_async_smem();
+  __syncthreads();
+#endif
 
   const uint32_t base_s = tc::smem_u32(base);
   const int tiles_x = (p.width + kTileW - 1) / kTileW;
@@ -651,7 +679,7 @@ render_forward_pipe(const nfi_render_params p, const unsigned char* __restrict__
         float nxt = fetch(s);
         for (; s < S; s += P) {
           const uint32_t st = (n + (uint32_t)s) % NS, u = (n + (uint32_t)s) / NS;
-          unsigned char* const stage = base + Cfg::kSmA + st * kPipeStageBytes;
+          unsigned char* const stage = base + Cfg::kSmA + st * kFwdStageBytes;
           const float cur = nxt;
           nxt = fetch(s + P);
           if (DBG && dbg_time) tprev = clock64();
@@ -675,7 +703,11 @@ render_forward_pipe(const nfi_render_params p, const unsigned char* __restrict__
             tp.o[2] &= 0x7FFu;
           }
           if (!dbg_skip_gather) {
+#if NFI_L1_BF16
+            gather_to_tiles_lean<true>(planes_b, R, tp, stage, stage + 8192, 32 * wig, lane);
+#else
             gather_to_tiles_lean(planes_b, R, tp, stage, stage + 16384, 32 * wig, lane);
+#endif
           }
           NFI_T(2)
           tc::fence_async_smem();
@@ -694,9 +726,16 @@ render_forward_pipe(const nfi_render_params p, const unsigned char* __restrict__
     asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(Cfg::kAuxRegs));
     if (wig == 0) {
       // layer 1: full[set] + slot_free[slot] -> 12 MMAs -> d1_full[slot], a_free[set]
+#if NFI_L1_BF16
+      constexpr uint32_t idesc1 = tc::umma_idesc_bf16(128, 64, false, false);
+      const uint64_t dsc_w1_hi = tc::umma_desc(base_s + kWiW1Hi, 4, 16, 512);
+      const uint64_t dsc_w1_lo = tc::umma_desc(base_s + kWiW1Hi + 4096, 4, 16, 512);
+      const uint64_t dsc_a0 = tc::umma_desc(base_s + Cfg::kSmA, 4, 16, 512);
+#else
       const uint64_t dsc_w1_hi = tc::umma_desc_sw128(base_s + kWiW1Hi);
       const uint64_t dsc_w1_lo = tc::umma_desc_sw128(base_s + kWiW1Lo);
       const uint64_t dsc_a0 = tc::umma_desc_sw128(base_s + Cfg::kSmA);
+#endif
       uint32_t st = 0, u = 0, sl = 0, v = 0;
       for (uint32_t m = 0; m < total_steps; ++m) {
         if (DBG && dbg_time && tprev == 0) tprev = clock64();
@@ -706,9 +745,21 @@ render_forward_pipe(const nfi_render_params p, const unsigned char* __restrict__
         NFI_T(1)
         if (elect_one()) {
           tc::tc_fence_after();
-          const uint64_t dsc_a = dsc_a0 + (uint64_t)st * (kPipeStageBytes >> 4);
+          const uint64_t dsc_a = dsc_a0 + (uint64_t)st * (kFwdStageBytes >> 4);
+#if NFI_L1_BF16
+          // D1 = F_lo W1_hi + F_hi W1_lo + F_hi W1_hi, K = 32 = two K16 steps of 32 bytes
+          const uint32_t d1 = tmem_base + sl * kPipeSlotCols;
+          const uint64_t a_lo = dsc_a + (8192 >> 4);
+          tc::umma_f16_ss<false>(d1, a_lo, dsc_w1_hi, idesc1);
+          tc::umma_f16_ss<true>(d1, a_lo + 2, dsc_w1_hi + 2, idesc1);
+          tc::umma_f16_ss<true>(d1, dsc_a, dsc_w1_lo, idesc1);
+          tc::umma_f16_ss<true>(d1, dsc_a + 2, dsc_w1_lo + 2, idesc1);
+          tc::umma_f16_ss<true>(d1, dsc_a, dsc_w1_hi, idesc1);
+          tc::umma_f16_ss<true>(d1, dsc_a + 2, dsc_w1_hi + 2, idesc1);
+#else
           tc::issue_layer1_d(tmem_base + sl * kPipeSlotCols, dsc_a, dsc_a + (16384 >> 4),
                              dsc_w1_hi, dsc_w1_lo);
+#endif
           tc::umma_commit(&d1_full[sl]);
           tc::umma_commit(&a_free[st]);
         }

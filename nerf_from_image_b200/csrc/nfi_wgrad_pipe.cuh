@@ -76,52 +76,6 @@ static_assert((WgCfg::kSmA & 1023) == 0 && (WgCfg::kSmX & 1023) == 0 && (WgCfg::
                   (WgCfg::kSmW1 & 1023) == 0 && (WgCfg::kSmOnes & 1023) == 0,
               "swizzled tiles are 1024-byte aligned");
 
-namespace tc {
-// two floats -> packed bf16 pair (round-to-nearest-even), `lo` in the low half (lower address)
-__device__ __forceinline__ uint32_t bf16x2_rn(float lo, float hi) {
-  uint32_t y;
-  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(y) : "f"(hi), "f"(lo));
-  return y;
-}
-// Shared-memory matrix descriptors for 16-bit operands.  `layout`: 2 = SWIZZLE_128B (128-byte
-// rows), 4 = SWIZZLE_64B (64-byte rows), 6 = SWIZZLE_32B (32-byte rows).  K-major: rows = M / N,
-// `sbo` = bytes between 8-row groups.  MN-major: rows = K, a row holds 64 / 32 / 16 elements of
-// M / N; `lbo` = bytes between such atoms along M / N, `sbo` = bytes between 8-row K groups (a
-// K16 instruction reads two of them).
-__device__ __forceinline__ uint64_t umma_desc(uint32_t smem_addr, uint32_t layout, uint32_t lbo,
-                                              uint32_t sbo) {
-  uint64_t d = 0;
-  d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
-  d |= (uint64_t)((lbo >> 4) & 0x3FFF) << 16;
-  d |= (uint64_t)((sbo >> 4) & 0x3FFF) << 32;
-  d |= (uint64_t)1 << 46;
-  d |= (uint64_t)layout << 61;
-  return d;
-}
-// Instruction descriptor, kind::f16 with bf16 operands, fp32 accumulate:
-//   [4,6) c_format=1 (F32)  [7,10) a_format=1 (BF16)  [10,13) b_format=1
-//   [15] A MN-major  [16] B MN-major  [17,23) N>>3  [24,29) M>>4
-__host__ __device__ constexpr uint32_t umma_idesc_bf16(int M, int N, bool a_mn, bool b_mn) {
-  return (1u << 4) | (1u << 7) | (1u << 10) | ((a_mn ? 1u : 0u) << 15) | ((b_mn ? 1u : 0u) << 16) |
-         ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
-}
-template <bool ACC>
-__device__ __forceinline__ void umma_f16_ss(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc,
-                                            uint32_t idesc) {
-  if (ACC)
-    asm volatile(
-        "{\n.reg .pred p;\nsetp.eq.u32 p, 0, 0;\n"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}\n" ::"r"(d_tmem),
-        "l"(a_desc), "l"(b_desc), "r"(idesc)
-        : "memory");
-  else
-    asm volatile(
-        "{\n.reg .pred p;\nsetp.ne.u32 p, 0, 0;\n"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}\n" ::"r"(d_tmem),
-        "l"(a_desc), "l"(b_desc), "r"(idesc)
-        : "memory");
-}
-}  // namespace tc
 
 template <int NOUT_PAD>
 __global__ void __launch_bounds__(WgCfg::kThreadsTotal, 1)
