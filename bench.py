@@ -742,8 +742,8 @@ class Bench:
         return {'value': gb * H * W / (ms_b * 1e-3), 'unit': UNIT, 'ms_per_step': ms_b,
                 'what': 'fused_render forward + backward through the autograd.Function (grads to '
                         'planes, palette, tform_cam2world%s)' % (
-                            '; decoder weights, beta, alpha too (+ their all-reduce)' if weights
-                            else '; decoder frozen')}
+                            '; decoder weights (render_wgrad_pipe, tcgen05), beta, alpha too (+ their '
+                            'all-reduce)' if weights else '; decoder frozen')}
 
     def cpu_baseline_and_parity(self, cfg, H, W, S):
         kind = reference_kind()
@@ -839,7 +839,9 @@ class Bench:
             'forward_only': {'value': gb * H * W / (ms_f * 1e-3), 'unit': UNIT, 'ms_per_step': ms_f},
             'images_per_gpu': B,
             'tiles_per_gpu': tiles, 'waves_of_148_ctas': tiles / 148.0,
-            'what': res['what'], 'gpu_launches': 4 * steps,
+            # per step: weight image + render_forward_pipe, weight images + render_backward_pipe,
+            # with decoder gradients also weight images + render_wgrad_pipe
+            'what': res['what'], 'gpu_launches': (5 if inv else 8) * steps,
         }
         print(json.dumps(line))
 

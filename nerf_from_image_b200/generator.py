@@ -64,6 +64,19 @@ def resolve_palette(g, ws, request_model_outputs, model_inputs):
     return attention_values, w_synthesis
 
 
+def view_conditioning(g, viewdir):
+    """--use_viewdir (generator.py:189-253,468-469): the ViewDirectionMapper trunk evaluated on the
+    unit view directions [B,H,W,1,3] by the reference module itself -> the 'triplane' entries
+    ``render.extract_view`` reads: per-ray features [B,H,W,32] and the effective weights of the
+    mapper's output layer."""
+    closure = g.viewdir_mapper(viewdir)
+    x = dict(zip(closure.__code__.co_freevars,
+                 (c.cell_contents for c in closure.__closure__)))['x']
+    out = g.viewdir_mapper.output
+    return dict(view_features=x.squeeze(-2), w3=out.weight * out.weight_gain,
+                b3=out.bias * out.bias_gain)
+
+
 def decoder_weights(g):
     """EFFECTIVE decoder weights (EqualizedLinear gains applied, differentiably)."""
     l1, l2 = g.decoder.net[0], g.decoder.net[2]
@@ -88,11 +101,9 @@ class FusedGeneratorFront:
         if not self.supports(request_model_outputs, model_inputs):
             raise _lib.NfiError('FusedGeneratorFront: outside its envelope (no_grad, outputs '
                                 'within %r)' % (SUPPORTED_OUTPUTS,))
-        if g.use_viewdir and viewdir is not None:
-            raise NotImplementedError('view-direction-conditioned models (--use_viewdir) keep the '
-                                      'reference front-end: render() routes them there')
         ws, batch = resolve_ws(g, c)
         attention_values, w_synthesis = resolve_palette(g, ws, request_model_outputs, model_inputs)
+        view = view_conditioning(g, viewdir) if (g.use_viewdir and viewdir is not None) else {}
         # ---- planes (generator.py:471-477), channel-last
         noise_mode = 'const' if model_inputs.get('freeze_noise') else 'random'
         planes_cl = self.synthesis(w_synthesis, noise_mode=noise_mode)
@@ -105,7 +116,7 @@ class FusedGeneratorFront:
         out['triplane'] = dict(
             planes=planes_cl, planes_layout='channel_last', palette=attention_values,
             w1=w1, b1=b1, w2=w2, b2=b2,
-            beta=getattr(g, 'beta', None), alpha=getattr(g, 'alpha', None))
+            beta=getattr(g, 'beta', None), alpha=getattr(g, 'alpha', None), **view)
         return out
 
 
@@ -132,9 +143,8 @@ class HeadsGeneratorFront:
         import math
         from .heads import regulariser_heads
         g = self.g
-        if g.use_viewdir and viewdir is not None:
-            raise NotImplementedError('view-direction-conditioned models (--use_viewdir) keep the '
-                                      'reference front-end: render() routes them there')
+        # (the heads read the distance row of the decoder only: nothing view-dependent, 520-585)
+        view = view_conditioning(g, viewdir) if (g.use_viewdir and viewdir is not None) else {}
         ws, batch = resolve_ws(g, c)
         if 'path_length' in request_model_outputs:
             assert torch.is_grad_enabled()
@@ -161,5 +171,6 @@ class HeadsGeneratorFront:
         if 'sampler' in request_model_outputs:
             out['triplane'] = dict(planes=planes, planes_layout='channel_first',
                                    palette=attention_values, w1=w1, b1=b1, w2=w2, b2=b2,
-                                   beta=getattr(g, 'beta', None), alpha=getattr(g, 'alpha', None))
+                                   beta=getattr(g, 'beta', None), alpha=getattr(g, 'alpha', None),
+                                   **view)
         return out

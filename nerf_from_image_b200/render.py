@@ -209,12 +209,12 @@ def render(target_model,
     requests = ['sampler'] + list(extra_model_outputs)
     front = _FRONTS.get(id(target_model))
     hfront = _HEAD_FRONTS.get(id(target_model))
-    if viewdirs is None and front is not None and front.supports(requests, extra_model_inputs):
+    if front is not None and front.supports(requests, extra_model_inputs):
         # plane producer on sm_100a too (generator.FusedGeneratorFront; no_grad calls only)
-        model_outputs = front(None, model_input, requests, extra_model_inputs)
-    elif viewdirs is None and hfront is not None and hfront.supports(requests, extra_model_inputs):
+        model_outputs = front(viewdirs, model_input, requests, extra_model_inputs)
+    elif hfront is not None and hfront.supports(requests, extra_model_inputs):
         # regulariser heads on the fused point evaluator (generator.HeadsGeneratorFront)
-        model_outputs = hfront(None, model_input, requests, extra_model_inputs)
+        model_outputs = hfront(viewdirs, model_input, requests, extra_model_inputs)
     else:
         model_outputs = target_model(viewdirs, model_input, requests, extra_model_inputs)
     sampler = model_outputs.pop('triplane', None) or model_outputs['sampler']

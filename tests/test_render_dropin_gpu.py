@@ -112,6 +112,33 @@ def test_render_with_viewdir_equals_the_reference_on_cuda(cuda_lib, kw):
     assert _rel(grads[1], grads[0]) < 5e-3
 
 
+def test_viewdir_with_the_fused_front_ends(cuda_lib):
+    """--use_viewdir together with enable_fused_synthesis (planes from the tcgen05 synthesis
+    kernels, mapper trunk by the reference module) and enable_fused_heads (regulariser outputs)."""
+    R, g, cams, ws, ref_render = _setup('p3d_car', use_viewdir=True)
+    a = (g, H, W, cams['c2w'], cams['focal'], cams['center'], cams['bbox'], ws, S)
+    try:
+        R.enable_fused_synthesis(g)
+        with torch.no_grad():
+            torch.manual_seed(31)
+            ref = ref_render(*a)
+            torch.manual_seed(31)
+            got = R.render(*a)
+        assert _rel(got[0], ref[0]) < 2e-3 and _rel(got[2], ref[2]) < 2e-3   # bf16-pair synthesis
+        R.enable_fused_heads(g)
+        heads = ['sdf_eikonal_loss', 'entropy_loss']
+        torch.manual_seed(32)
+        ref = ref_render(*a, extra_model_outputs=heads)
+        torch.manual_seed(32)
+        got = R.render(*a, extra_model_outputs=heads)
+        assert _rel(got[0], ref[0]) < 1e-3
+        for k in heads:
+            assert _rel(got[5][k], ref[5][k]) < 1e-3, k
+    finally:
+        R.enable_fused_synthesis(g, False)
+        R.enable_fused_heads(g, False)
+
+
 def test_inversion_gradients_flow_to_the_latents_like_the_reference(cuda_lib):
     """One inversion-style step (run.py:2256-2317): loss on rgb and mask, gradients w.r.t. the
     per-image latents (through the reference's synthesis autograd on both sides) and the pose."""
