@@ -718,10 +718,13 @@ class Bench:
                 'api': 'nfi_render_forward_host (C ABI): planes H2D every step -- PCIe-bound'}
 
     def fwd_bwd(self, sc, cams, nt, nu, cfg, H, W, S, gb, weights=False, steps=None):
-        """Forward + backward through the autograd.Function (grads to planes, palette, pose;
-        with `weights` also the decoder, beta, alpha)."""
+        """Forward + backward through the autograd.Function: the inversion step (grads to planes,
+        palette, pose; decoder frozen: run.py:628-629,2256-2317) or, with `weights`, the GAN
+        generator step (grads to planes, palette, decoder, beta, alpha; the cameras are sampled
+        data there, run.py:1007-1044)."""
         leaves = {k: sc[k].detach().clone().requires_grad_() for k in ('planes', 'palette')}
-        leaves['c2w'] = cams['c2w'].detach().clone().requires_grad_()
+        if not weights:
+            leaves['c2w'] = cams['c2w'].detach().clone().requires_grad_()
         if weights:
             for k in ('w1', 'b1', 'w2', 'b2', 'beta', 'alpha'):
                 leaves[k] = sc[k].detach().clone().requires_grad_()
@@ -741,9 +744,10 @@ class Bench:
         torch.cuda.empty_cache()
         return {'value': gb * H * W / (ms_b * 1e-3), 'unit': UNIT, 'ms_per_step': ms_b,
                 'what': 'fused_render forward + backward through the autograd.Function (grads to '
-                        'planes, palette, tform_cam2world%s)' % (
-                            '; decoder weights (render_wgrad_pipe, tcgen05), beta, alpha too (+ their '
-                            'all-reduce)' if weights else '; decoder frozen')}
+                        'planes, palette, %s)' % (
+                            'decoder weights (render_wgrad_pipe, tcgen05), beta, alpha (+ their '
+                            'all-reduce); cameras are data' if weights
+                            else 'tform_cam2world; decoder frozen')}
 
     def cpu_baseline_and_parity(self, cfg, H, W, S):
         kind = reference_kind()

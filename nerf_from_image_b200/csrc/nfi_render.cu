@@ -517,6 +517,7 @@ int nfi_render_backward(const nfi_render_params* params, const nfi_render_grads*
     NFI_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
     size_t grid = num_ctas(&p);
     if (grid > (size_t)sms) grid = sms;
+    if (grid > kMaxPersistentCtas) grid = kMaxPersistentCtas;  // (the wgrad workspace is sized for it)
     nfi_render_grads g1 = g;
     g1.grad_w1 = g1.grad_b1 = g1.grad_w2 = g1.grad_b2 = nullptr;
     const bool others = g1.grad_planes || g1.grad_palette || g1.grad_beta || g1.grad_alpha ||

@@ -126,6 +126,7 @@ def test_viewdir_with_the_fused_front_ends(cuda_lib):
             got = R.render(*a)
         assert _rel(got[0], ref[0]) < 2e-3 and _rel(got[2], ref[2]) < 2e-3   # bf16-pair synthesis
         R.enable_fused_heads(g)
+        g.train()                                   # generator.py:517: the eikonal head is a training loss
         heads = ['sdf_eikonal_loss', 'entropy_loss']
         torch.manual_seed(32)
         ref = ref_render(*a, extra_model_outputs=heads)
@@ -135,6 +136,7 @@ def test_viewdir_with_the_fused_front_ends(cuda_lib):
         for k in heads:
             assert _rel(got[5][k], ref[5][k]) < 1e-3, k
     finally:
+        g.eval()
         R.enable_fused_synthesis(g, False)
         R.enable_fused_heads(g, False)
 
