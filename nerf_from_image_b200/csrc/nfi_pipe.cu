@@ -81,12 +81,13 @@ int bwd_np(const nfi_render_params& p, const nfi_render_grads& g, const unsigned
              : run_bwd<NP, 0, false>(p, g, wimg, grid, st, err, err_len);
 }
 
-template <int NP>
+template <int NP, bool PLANES>
 int run_wgrad(const nfi_render_params& p, const nfi_render_grads& g, const unsigned char* wimg,
               unsigned grid, cudaStream_t st, char* err, size_t err_len) {
-  auto k = render_wgrad_pipe<NP>;
-  NFI_PCUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, WgCfg::kSmBytes));
-  k<<<grid, WgCfg::kThreadsTotal, WgCfg::kSmBytes, st>>>(
+  using Cfg = WgCfgT<PLANES>;
+  auto k = render_wgrad_pipe<NP, PLANES>;
+  NFI_PCUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmBytes));
+  k<<<grid, Cfg::kThreadsTotal, Cfg::kSmBytes, st>>>(
       p, g, wimg, reinterpret_cast<float*>(const_cast<unsigned char*>(wimg) + 65536));
   NFI_PCUDA(cudaGetLastError());
   return 0;
@@ -133,7 +134,7 @@ int launch_pipe_backward(const nfi_render_params& p, const nfi_render_grads& g, 
 
 // decoder-weight gradients on tcgen05 (nfi_wgrad_pipe.cuh): both weight images + render_wgrad_pipe
 int launch_pipe_wgrad(const nfi_render_params& p, const nfi_render_grads& g, int nout_pad,
-                      unsigned char* wimg, unsigned grid, cudaStream_t st, char* err,
+                      unsigned char* wimg, unsigned grid, bool planes, cudaStream_t st, char* err,
                       size_t err_len) {
   const int nout = 1 + (p.n_attention > 0 ? p.n_attention : 3);
   if (launch_pipe_weight_image(p, wimg, st)) {
@@ -142,9 +143,14 @@ int launch_pipe_wgrad(const nfi_render_params& p, const nfi_render_grads& g, int
   }
   prep_weight_image_bwd<<<1, 256, 0, st>>>(p.w1, p.w2, nout, wimg + 32768);
   NFI_PCUDA(cudaGetLastError());
-  if (nout_pad == 4) return run_wgrad<4>(p, g, wimg, grid, st, err, err_len);
-  if (nout_pad == 12) return run_wgrad<12>(p, g, wimg, grid, st, err, err_len);
-  return run_wgrad<16>(p, g, wimg, grid, st, err, err_len);
+  if (planes) {
+    if (nout_pad == 4) return run_wgrad<4, true>(p, g, wimg, grid, st, err, err_len);
+    if (nout_pad == 12) return run_wgrad<12, true>(p, g, wimg, grid, st, err, err_len);
+    return run_wgrad<16, true>(p, g, wimg, grid, st, err, err_len);
+  }
+  if (nout_pad == 4) return run_wgrad<4, false>(p, g, wimg, grid, st, err, err_len);
+  if (nout_pad == 12) return run_wgrad<12, false>(p, g, wimg, grid, st, err, err_len);
+  return run_wgrad<16, false>(p, g, wimg, grid, st, err, err_len);
 }
 
 }  // namespace nfi

@@ -21,8 +21,10 @@ int launch_pipe_backward(const nfi_render_params& p, const nfi_render_grads& g, 
 // (workspace at `wimg`: the two weight images, then one accumulator row buffer per CTA:
 // pipe_wgrad_workspace_bytes(grid) in all)
 size_t pipe_wgrad_workspace_bytes(unsigned grid);
+// `planes`: ONE sweep for the whole generator step -- the kernel also produces grad_planes /
+// grad_palette / grad_beta / grad_alpha of `g` (no pose gradient)
 int launch_pipe_wgrad(const nfi_render_params& p, const nfi_render_grads& g, int nout_pad,
-                      unsigned char* wimg, unsigned grid, cudaStream_t st, char* err,
+                      unsigned char* wimg, unsigned grid, bool planes, cudaStream_t st, char* err,
                       size_t err_len);
 // the pipelined kernels' weight image (log2 e folded into layer 1 and the colour rows of
 // layer 2, padded logits at -1e30)

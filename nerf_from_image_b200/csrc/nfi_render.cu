@@ -522,14 +522,17 @@ int nfi_render_backward(const nfi_render_params* params, const nfi_render_grads*
     g1.grad_w1 = g1.grad_b1 = g1.grad_w2 = g1.grad_b2 = nullptr;
     const bool others = g1.grad_planes || g1.grad_palette || g1.grad_beta || g1.grad_alpha ||
                         g1.grad_origins;
-    if (others || !wgrad) {
+    // The generator step (decoder gradients, cameras are data): ONE sweep, render_wgrad_pipe with
+    // the plane scatter folded in.  With a pose gradient too: render_backward_pipe beside it.
+    const bool one_sweep = wgrad && others && !g.grad_origins && !(p.mlp_mode & 0x2000);
+    if ((others && !one_sweep) || !wgrad) {
       if (int rc = nfi::launch_pipe_backward(p, g1, nout_pad_of(params), (unsigned char*)p.workspace,
                                              (unsigned)grid, st, g_err, sizeof(g_err)))
         return rc;
     }
     if (wgrad)
       return nfi::launch_pipe_wgrad(p, g, nout_pad_of(params), (unsigned char*)p.workspace,
-                                    (unsigned)grid, st, g_err, sizeof(g_err));
+                                    (unsigned)grid, one_sweep, st, g_err, sizeof(g_err));
     return 0;
   }
   return nfi::launch_backward(*params, *grads, st, g_err, sizeof(g_err));

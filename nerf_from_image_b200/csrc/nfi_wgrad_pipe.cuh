@@ -48,40 +48,51 @@ constexpr int kWgStages = 3;
 constexpr int kWgFlush = 16;
 constexpr size_t kWgAccBytesPerCta = 128 * 64 * sizeof(float);
 
-struct WgCfg {
+// PLANES: the kernel also forms dL/d(texel features) (MMA4) and scatters it into the plane
+// gradient, and accumulates the palette / beta / alpha gradients -- i.e. it is the WHOLE backward
+// of the GAN generator step in one sweep (no pose gradient: cameras are data there).
+template <bool PLANES>
+struct WgCfgT {
   static constexpr int P = 2;
   static constexpr int kThreadsTotal = 384 + 128 * P;
   static constexpr int kStageBytes = 16384;                           // F_hi | F_lo, 8 KB each
-  static constexpr int kSmWb = 25600;                                 // W2^T hi / lo (16 KB)
-  static constexpr int kSmW1 = kSmWb + 16384;                         // 41 * 1024: W1 bf16 hi | lo
-  static constexpr int kSmA = kSmW1 + 8192;                           // 49 * 1024
-  static constexpr int kSmX = kSmA + kWgStages * kStageBytes;         // 97 * 1024: 4 x 16 KB
-  static constexpr int kSmE = kSmX + 65536;                           // 161 * 1024: dOut hi | lo
-  static constexpr int kSmOnes = kSmE + 8192;                         // 169 * 1024: 1 KB of 1.0
-  static constexpr int kSmPal = kSmOnes + 1024;
+  static constexpr int kWbBytes = PLANES ? 32768 : 16384;             // W2^T hi/lo (+ W1^T/3 hi/lo)
+  static constexpr int kSmWb = 25600;
+  static constexpr int kSmW1 = kSmWb + kWbBytes;                      // W1 bf16 hi | lo (8 KB)
+  static constexpr int kSmA = kSmW1 + 8192;
+  static constexpr int kSmX = kSmA + kWgStages * kStageBytes;         // 4 x 16 KB
+  static constexpr int kSmE = kSmX + 65536;                           // dOut hi | lo
+  static constexpr int kSmOnes = kSmE + 8192;                         // 1 KB of 1.0
+  static constexpr int kStageWarp = 32 * 36 * 4;                      // per-warp scatter staging
+  static constexpr int kSmStage = kSmOnes + 1024;
+  static constexpr int kSmPal = kSmStage + (PLANES ? P * 4 * kStageWarp : 0);
   static constexpr int kSmFrac = kSmPal + 48 * 4;
   static constexpr int kSmBars = kSmFrac + 128 * 4;
-  // full[3], a_free[3], per slot: d1_full, h_ready, d2_full, dout_ready, d3_full, slot_free;
-  // x_ready, x_free; weights x2
-  static constexpr int kNumBars = 2 * kWgStages + 6 * kWgSlots + 2 + 2;
+  // full[3], a_free[3], per slot: d1_full, h_ready, d2_full, dout_ready, d3_full, slot_free,
+  // dpre_ready, d4_full; x_ready, x_free; weights x2
+  static constexpr int kNumBars = 2 * kWgStages + 8 * kWgSlots + 2 + 2;
   static constexpr int kSmTmemPtr = kSmBars + kNumBars * 8;
   static constexpr int kSmBytes = kSmTmemPtr + 16;
-  // 640 x 96 = 61440 = 256 x 96 + 128 x (128 + 136 + 24)
-  static constexpr int kActRegs = 128;
+  // 640 x 96 = 61440 = 256 x 96 + 128 x (128 + 136 + 24) = 256 x 112 + 128 x (96 + 136 + 24)
+  static constexpr int kProdRegs = PLANES ? 112 : 96;
+  static constexpr int kActRegs = PLANES ? 96 : 128;
   static constexpr int kShadeRegs = 136;
   static constexpr int kAuxRegs = 24;
 };
-static_assert(WgCfg::kSmBytes <= 227 * 1024, "shared memory budget");
-static_assert((WgCfg::kSmA & 1023) == 0 && (WgCfg::kSmX & 1023) == 0 && (WgCfg::kSmE & 1023) == 0 &&
-                  (WgCfg::kSmW1 & 1023) == 0 && (WgCfg::kSmOnes & 1023) == 0,
+using WgCfg = WgCfgT<false>;
+static_assert(WgCfgT<true>::kSmBytes <= 227 * 1024, "shared memory budget");
+static_assert((WgCfgT<false>::kSmA & 1023) == 0 && (WgCfgT<false>::kSmX & 1023) == 0 &&
+                  (WgCfgT<false>::kSmE & 1023) == 0 && (WgCfgT<false>::kSmW1 & 1023) == 0 &&
+                  (WgCfgT<true>::kSmA & 1023) == 0 && (WgCfgT<true>::kSmX & 1023) == 0 &&
+                  (WgCfgT<true>::kSmE & 1023) == 0 && (WgCfgT<true>::kSmW1 & 1023) == 0,
               "swizzled tiles are 1024-byte aligned");
 
 
-template <int NOUT_PAD>
-__global__ void __launch_bounds__(WgCfg::kThreadsTotal, 1)
+template <int NOUT_PAD, bool PLANES = false>
+__global__ void __launch_bounds__(WgCfgT<PLANES>::kThreadsTotal, 1)
 render_wgrad_pipe(const nfi_render_params p, const nfi_render_grads g,
                   const unsigned char* __restrict__ wimg, float* __restrict__ acc_ws) {
-  using Cfg = WgCfg;
+  using Cfg = WgCfgT<PLANES>;
   constexpr int P = Cfg::P;
   constexpr int NA = NOUT_PAD - 1;
   constexpr int NS = kWgStages;
@@ -105,7 +116,9 @@ render_wgrad_pipe(const nfi_render_params p, const nfi_render_grads g,
   uint64_t* dout_ready = d2_full + kWgSlots;  // [2] 4 warps (dOut in TMEM and in the E tiles)
   uint64_t* d3_full = dout_ready + kWgSlots;  // [2] commit
   uint64_t* slot_free = d3_full + kWgSlots;   // [2] 4 warps (D3 / H read)
-  uint64_t* x_ready = slot_free + kWgSlots;   // X tile written (4 warps)
+  uint64_t* dpre_ready = slot_free + kWgSlots;  // [2] 4 warps (PLANES: dpre hi/lo in TMEM)
+  uint64_t* d4_full = dpre_ready + kWgSlots;    // [2] commit (PLANES)
+  uint64_t* x_ready = d4_full + kWgSlots;     // X tile written (4 warps)
   uint64_t* x_free = x_ready + 1;             // X and E tiles read by the dW MMAs (commit)
   uint64_t* wbar = x_free + 1;                // [2] weight images landed
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(base + Cfg::kSmTmemPtr);
@@ -142,6 +155,8 @@ render_wgrad_pipe(const nfi_render_params p, const nfi_render_grads g,
       tc::mbar_init(&dout_ready[i], kWarps);
       tc::mbar_init(&d3_full[i], 1);
       tc::mbar_init(&slot_free[i], kWarps);
+      tc::mbar_init(&dpre_ready[i], kWarps);
+      tc::mbar_init(&d4_full[i], 1);
     }
     tc::mbar_init(x_ready, kWarps);
     tc::mbar_init(x_free, 1);
@@ -157,8 +172,8 @@ render_wgrad_pipe(const nfi_render_params p, const nfi_render_grads g,
   if (tid == 0) {
     tc::mbar_expect_tx(&wbar[0], kWiBytes);
     tc::tma_bulk_g2s(base, wimg, kWiBytes, &wbar[0]);
-    tc::mbar_expect_tx(&wbar[1], 16384);
-    tc::tma_bulk_g2s(base + Cfg::kSmWb, wimg + 32768, 16384, &wbar[1]);  // W2^T hi | lo
+    tc::mbar_expect_tx(&wbar[1], Cfg::kWbBytes);
+    tc::tma_bulk_g2s(base + Cfg::kSmWb, wimg + 32768, Cfg::kWbBytes, &wbar[1]);  // W2^T (| W1^T / 3)
   }
   tc::mbar_wait(&wbar[0], 0);
   tc::mbar_wait(&wbar[1], 0);
@@ -176,8 +191,12 @@ render_wgrad_pipe(const nfi_render_params p, const nfi_render_grads g,
   const uint32_t lane_addr = (uint32_t)(32 * wig) << 16;
 
   if (wg >= 3) {
-    // ================================ PRODUCERS (gather only) ================================
+    // ================================ PRODUCERS (gather; PLANES: also the scatter) ================
+    if (PLANES) asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(Cfg::kProdRegs));
     const int set = wg - 3;
+    float* Dw = reinterpret_cast<float*>(base + Cfg::kSmStage + (set * 4 + wig) * Cfg::kStageWarp);
+    const int q = lane >> 3, kq = lane & 7;
+    const uint32_t row_units = (uint32_t)R * 8u;
     uint32_t n0 = 0;  // ring position of the tile's first step
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, n0 += (uint32_t)n_total) {
       const TileCoord tcd = tile_coord(tile, tiles_x, tiles_y);
@@ -191,10 +210,13 @@ render_wgrad_pipe(const nfi_render_params p, const nfi_render_grads g,
       setup_ray(p, b, py, px, r);
       const unsigned char* planes_b =
           reinterpret_cast<const unsigned char*>(p.planes) + (size_t)b * 3 * plane_bytes;
+      float* gplanes_b = (PLANES && g.grad_planes)
+                             ? g.grad_planes + (size_t)b * 3 * (plane_bytes >> 2) : nullptr;
       MergeWalk mw;
       mw.init(p, r, ray, frac);
       int walked = 0;
-      for (int i = set; i < n_total; i += P) {
+      ByteTaps cur, nxt;  // taps of the (up to) two steps this set has between "gathered" and "scattered"
+      auto gather_step = [&](int i, ByteTaps& tp) {
         float z = 0.f;
         while (walked <= i) {
           z = mw.pop();
@@ -202,7 +224,6 @@ render_wgrad_pipe(const nfi_render_params p, const nfi_render_grads g,
         }
         const float x0 = (r.ox + r.dx * z) * inv_range, x1 = (r.oy + r.dy * z) * inv_range,
                     x2 = (r.oz + r.dz * z) * inv_range;
-        ByteTaps tp;
         byte_taps(x0, x1, R, 0u, tp.o[0], tp.fx[0], tp.fy[0]);
         byte_taps(x0, x2, R, plane_bytes >> 4, tp.o[1], tp.fx[1], tp.fy[1]);
         byte_taps(x1, x2, R, plane_bytes >> 3, tp.o[2], tp.fx[2], tp.fy[2]);
@@ -214,6 +235,64 @@ render_wgrad_pipe(const nfi_render_params p, const nfi_render_grads g,
         tc::fence_async_smem();
         __syncwarp();
         if (lane == 0) mbar_arrive(&full[st]);
+      };
+      if constexpr (!PLANES) {
+        for (int i = set; i < n_total; i += P) gather_step(i, cur);
+      } else {
+        if (set < n_total) gather_step(set, cur);
+        for (int i = set; i < n_total; i += P) {
+          if (i + P < n_total) gather_step(i + P, nxt);
+          // ---- scatter step i: D4 -> plane gradient (as render_backward_pipe, no pose gradient)
+          const uint32_t m = n0 + (uint32_t)i;
+          const uint32_t sl = m % kWgSlots, v = m / kWgSlots;
+          const uint32_t d4 = tmem_base + sl * kWgSlotCols + lane_addr;
+          NFI_STEP_WAIT(&d4_full[sl], v & 1);
+          tc::tc_fence_after();
+          {
+            uint32_t ra[16], rb[16];
+            tc::tmem_ld16_nowait(d4, ra);
+            tc::tmem_ld16_nowait(d4 + 16, rb);
+            tc::tmem_wait_ld();
+            tc::tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&slot_free[sl]);
+#pragma unroll
+            for (int c4 = 0; c4 < 4; ++c4) {
+              *reinterpret_cast<float4*>(Dw + lane * 36 + 4 * c4) =
+                  make_float4(__uint_as_float(ra[4 * c4]), __uint_as_float(ra[4 * c4 + 1]),
+                              __uint_as_float(ra[4 * c4 + 2]), __uint_as_float(ra[4 * c4 + 3]));
+              *reinterpret_cast<float4*>(Dw + lane * 36 + 16 + 4 * c4) =
+                  make_float4(__uint_as_float(rb[4 * c4]), __uint_as_float(rb[4 * c4 + 1]),
+                              __uint_as_float(rb[4 * c4 + 2]), __uint_as_float(rb[4 * c4 + 3]));
+            }
+          }
+          __syncwarp();
+          if (gplanes_b != nullptr) {
+#pragma unroll 1
+            for (int gq = 0; gq < 8; ++gq) {
+              const int src = 4 * gq + q;
+              const float4 d4v = *reinterpret_cast<const float4*>(Dw + src * 36 + 4 * kq);
+#pragma unroll
+              for (int pl = 0; pl < 3; ++pl) {
+                const uint32_t a00 = __shfl_sync(kFull, cur.o[pl], src) | (uint32_t)kq;
+                const float fx = __shfl_sync(kFull, cur.fx[pl], src);
+                const float fy = __shfl_sync(kFull, cur.fy[pl], src);
+                const float gx0 = 1.f - fx, gy0 = 1.f - fy;
+                const float w00 = gx0 * gy0, w01 = fx * gy0, w10 = gx0 * fy, w11 = fx * fy;
+                float* gp = gplanes_b;
+                red_add_v4(gp + (size_t)a00 * 4, d4v.x * w00, d4v.y * w00, d4v.z * w00, d4v.w * w00);
+                red_add_v4(gp + (size_t)(a00 + 8u) * 4, d4v.x * w01, d4v.y * w01, d4v.z * w01,
+                           d4v.w * w01);
+                red_add_v4(gp + (size_t)(a00 + row_units) * 4, d4v.x * w10, d4v.y * w10,
+                           d4v.z * w10, d4v.w * w10);
+                red_add_v4(gp + (size_t)(a00 + row_units + 8u) * 4, d4v.x * w11, d4v.y * w11,
+                           d4v.z * w11, d4v.w * w11);
+              }
+            }
+          }
+          __syncwarp();
+          cur = nxt;
+        }
       }
     }
   } else if (wg == 2) {
@@ -287,8 +366,20 @@ render_wgrad_pipe(const nfi_render_params p, const nfi_render_grads g,
       const uint64_t dsc_elo = tc::umma_desc(base_s + Cfg::kSmE + 4096, 6, 16, 256);
       const uint64_t dsc_one = tc::umma_desc(base_s + Cfg::kSmOnes, 6, 16, 256);  // K-major [8][16]
       const uint32_t d_w1 = tmem_base + kWgAccCol, d_w2 = d_w1 + 32, d_b1 = d_w1 + 48;
+      const uint64_t w1t_hi = tc::umma_desc_sw128(base_s + Cfg::kSmWb + kWbW1tHi);
+      const uint64_t w1t_lo = tc::umma_desc_sw128(base_s + Cfg::kSmWb + kWbW1tLo);
       uint32_t st = 0, u = 0, sl = 0, v = 0;
       for (uint32_t m = 0; m < total_steps; ++m) {
+        if constexpr (PLANES) {  // MMA4: D4 = dpre (W1 / 3) over D1 / H_lo, 3xTF32 as render_backward_pipe
+          NFI_STEP_WAIT(&dpre_ready[sl], v & 1);
+          if (elect_one()) {
+            tc::tc_fence_after();
+            const uint32_t d = tmem_base + sl * kWgSlotCols;
+            issue_mma4(d, d + 64, d + 160, w1t_hi, w1t_lo);
+            tc::umma_commit(&d4_full[sl]);
+          }
+          __syncwarp();
+        }
         NFI_STEP_WAIT(&full[st], u & 1);
         NFI_STEP_WAIT(&dout_ready[sl], v & 1);
         NFI_STEP_WAIT(x_ready, m & 1);
@@ -416,6 +507,16 @@ render_wgrad_pipe(const nfi_render_params p, const nfi_render_grads g,
           dp[i] = __uint_as_float(r3[i]) * sg;
           hh[i] = h;
         }
+        if constexpr (PLANES) {  // dpre as a TF32 pair for MMA4: hi over H_hi, lo over D3
+          float thi[16], tlo[16];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            thi[i] = tc::tf32_hi(dp[i]);
+            tlo[i] = dp[i] - thi[i];
+          }
+          tc::tmem_st16(d + 160 + 16 * c, tlo);
+          tc::tmem_st16(d + 64 + 16 * c, thi);
+        }
         // columns 16c .. 16c+15 of dpre_hi / dpre_lo (tiles 0, 1) and H_hi / H_lo (tiles 2, 3):
         // two 16-byte chunks of this point's 128-byte row in each
 #pragma unroll
@@ -439,12 +540,14 @@ render_wgrad_pipe(const nfi_render_params p, const nfi_render_grads g,
           *reinterpret_cast<uint4*>(xrow + 49152 + off) = make_uint4(hl[0], hl[1], hl[2], hl[3]);
         }
       }
+      if constexpr (PLANES) tc::tmem_wait_st();
       tc::tc_fence_before();
       tc::fence_async_smem();
       __syncwarp();
       if (lane == 0) {
         mbar_arrive(x_ready);
-        mbar_arrive(&slot_free[sl]);
+        if constexpr (PLANES) mbar_arrive(&dpre_ready[sl]);  // (the slot is freed by the scatter)
+        else mbar_arrive(&slot_free[sl]);
       }
     };
     if (total_steps > 0) act_fwd(0);
@@ -506,6 +609,10 @@ render_wgrad_pipe(const nfi_render_params p, const nfi_render_grads g,
         o_b -= bg;
       }
       const float total = (g_r * o_r + g_g * o_g + g_b * o_b) + g_m * out_m;
+      float accP[PLANES ? NA : 1];  // PLANES: palette / beta / alpha gradients of this ray
+#pragma unroll
+      for (int a = 0; a < (PLANES ? NA : 1); ++a) accP[a] = 0.f;
+      float acc_beta = 0.f, acc_alpha = 0.f;
 
       MergeWalk mw;
       mw.init(p, r, ray, frac);
@@ -528,11 +635,11 @@ render_wgrad_pipe(const nfi_render_params p, const nfi_render_grads g,
 #pragma unroll
         for (int o = 0; o < NOUT_PAD; ++o) out[o] = o16[o] + b2s[o];
         // density (models/generator.py:629-636) and its derivative wrt out[0]
-        float sigma, dsig_dout0;
+        float sigma, dsig_dout0, nd = 0.f, e_sdf = 0.f, sg = 0.f;
         if (fc.use_sdf) {
-          const float nd = -out[0];
-          const float e_sdf = tc::ex2_approx(-fabsf(nd) * (fc.inv_beta * kLog2e));
-          const float sg = (nd > 0.f) ? 1.f : ((nd < 0.f) ? -1.f : 0.f);
+          nd = -out[0];
+          e_sdf = tc::ex2_approx(-fabsf(nd) * (fc.inv_beta * kLog2e));
+          sg = (nd > 0.f) ? 1.f : ((nd < 0.f) ? -1.f : 0.f);
           sigma = fc.inv_alpha * ((0.5f + 0.5f * sg * (1.f - e_sdf)) * keep);
           // analytic derivative also AT the zero crossing (see nfi_backward_pipe.cuh)
           dsig_dout0 = -(fc.inv_alpha * keep) * 0.5f * e_sdf * fc.inv_beta;
@@ -583,6 +690,11 @@ render_wgrad_pipe(const nfi_render_params p, const nfi_render_grads g,
 #pragma unroll
         for (int o = 0; o < 16; ++o) dOut[o] = 0.f;
         dOut[0] = dsig * dsig_dout0;
+        if (PLANES && fc.use_sdf) {
+          acc_beta = fmaf(dsig, fc.inv_alpha * keep * (-0.5f * sg * e_sdf * fabsf(nd) * fc.inv_beta *
+                                                       fc.inv_beta), acc_beta);
+          acc_alpha = fmaf(dsig, -sigma * fc.inv_alpha, acc_alpha);
+        }
         const float wr = w * g_r, wg2 = w * g_g, wb = w * g_b;
         if (fc.A > 0) {
           float dp[NA];
@@ -592,6 +704,7 @@ render_wgrad_pipe(const nfi_render_params p, const nfi_render_grads g,
             const float vv = wr * pal[3 * q + 0] + wg2 * pal[3 * q + 1] + wb * pal[3 * q + 2];
             dp[q] = vv;
             dot = fmaf(probs[q], vv, dot);
+            if (PLANES) accP[q] = fmaf(w, probs[q], accP[q]);
           }
 #pragma unroll
           for (int q = 0; q < NA; ++q) dOut[1 + q] = probs[q] * (dp[q] - dot);
@@ -639,6 +752,28 @@ render_wgrad_pipe(const nfi_render_params p, const nfi_render_grads g,
           if (lane == 0) mbar_arrive(&dout_ready[sl]);
         }
         z = zn;
+      }
+      if constexpr (PLANES) {  // per-tile write-out, as render_backward_pipe
+        if (g.grad_palette != nullptr && p.n_attention > 0) {
+#pragma unroll
+          for (int a = 0; a < NA; ++a) {
+            const float pr = warp_sum(accP[a] * g_r), pg = warp_sum(accP[a] * g_g),
+                        pb = warp_sum(accP[a] * g_b);
+            if (lane == 0 && a < p.n_attention) {
+              float* gp = g.grad_palette + ((size_t)b * p.n_attention + a) * 3;
+              atomicAdd(gp + 0, pr);
+              atomicAdd(gp + 1, pg);
+              atomicAdd(gp + 2, pb);
+            }
+          }
+        }
+        if (p.use_sdf) {
+          const float sb = warp_sum(acc_beta), sa = warp_sum(acc_alpha);
+          if (lane == 0) {
+            if (g.grad_beta) atomicAdd(g.grad_beta, sb);
+            if (g.grad_alpha) atomicAdd(g.grad_alpha, sa);
+          }
+        }
       }
     }
     if (g.grad_b2 != nullptr) {
