@@ -477,6 +477,19 @@ class Bench:
             'hbm_achieved_gbs': hbm_bytes_launch / (k_ms * 1e-3) / 1e9 if k_ms > 0 else 0.0,
             'hbm_peak_gbs': pk['hbm_gbs'], 'peak_source': pk['source'],
         }
+        if fwd_bwd is not None:
+            # the backward sweep re-runs the two layers and adds dL/dH = dOut W2 (2 x 11 x 64) and
+            # dL/dF = dpre W1 (2 x 64 x 32) per point: 5,504 FLOPs on top of the recompute's 5,564
+            bwd_flops = float(B * H * W) * (2 * S) * (FLOPS_PER_POINT + 5504.0)
+            step_s = fwd_bwd['ms_per_step'] * 1e-3
+            ach = (flops_launch + bwd_flops) / step_s / 1e12
+            fwd_bwd['roofline'] = {
+                'bound': 'tensor', 'achieved': ach, 'peak': pk['tflops'], 'unit': 'TFLOP/s',
+                'frac': ach / pk['tflops'],
+                'algorithmic_flops_per_step': flops_launch + bwd_flops,
+                'what': 'render_forward_pipe + render_backward_pipe (pose gradients on) of one '
+                        'inversion step; the backward is bound by its three line-rate passes per '
+                        'point -- gather, red.global.add.v4 scatter, pose re-read (DESIGN.md 8.2)'}
         cpu_baseline = parity = eager = None
         if world == 1 and not a.no_cpu_baseline:
             cpu_baseline, parity = self.cpu_baseline_and_parity(cfg, H, W, S)

@@ -220,9 +220,11 @@ NFI_API int nfi_decoder_forward(const float *features, int64_t n_points, const f
 
 /* autograd of the above: recomputes the samples.
  * With params->workspace >= 64 KiB, no semantics output and S <= 128, S % 4 == 0 the four GEMMs of
- * a sample step run on tcgen05 (render_backward_pipe); decoder-weight gradients (grad_w1 / b1 /
- * w2 / b2) then come from a second tcgen05 kernel (render_wgrad_pipe), which needs
- * params->workspace >= NFI_BACKWARD_WORKSPACE_BYTES; otherwise the fp32 SIMT kernel is used. */
+ * a sample step run on tcgen05 (render_backward_pipe).  Decoder-weight gradients (grad_w1 / b1 /
+ * w2 / b2) come from render_wgrad_pipe (MN-major bf16-pair GEMMs on tcgen05), which needs
+ * params->workspace >= NFI_BACKWARD_WORKSPACE_BYTES: without pose gradients (the GAN generator
+ * step) it is the WHOLE backward in one sweep, with them it runs beside render_backward_pipe.
+ * Everything outside that envelope: the fp32 SIMT kernel. */
 #define NFI_BACKWARD_WORKSPACE_BYTES (65536 + 160 * 32768)
 NFI_API int nfi_render_backward(const nfi_render_params *params, const nfi_render_grads *grads,
                         void *stream);

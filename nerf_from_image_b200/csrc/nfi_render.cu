@@ -524,6 +524,7 @@ int nfi_render_backward(const nfi_render_params* params, const nfi_render_grads*
                         g1.grad_origins;
     // The generator step (decoder gradients, cameras are data): ONE sweep, render_wgrad_pipe with
     // the plane scatter folded in.  With a pose gradient too: render_backward_pipe beside it.
+    // (mlp_mode bit 0x2000: timing experiments, tools/time_wgrad.py -- two sweeps anyway)
     const bool one_sweep = wgrad && others && !g.grad_origins && !(p.mlp_mode & 0x2000);
     if ((others && !one_sweep) || !wgrad) {
       if (int rc = nfi::launch_pipe_backward(p, g1, nout_pad_of(params), (unsigned char*)p.workspace,
