@@ -157,6 +157,13 @@ typedef struct nfi_render_params {
   const float *view_features; /* [B,H,W,32] or NULL */
   const float *w3;            /* [A,32] ([3,32] when A == 0): EFFECTIVE weight of mapper.output */
   const float *b3;            /* [A] ([3]) */
+  /* ---- row tile (ABI 5): render rows [row_offset, row_offset + height) of images that are
+   * full_height rows tall (full_height == 0: the whole image, height rows).  Every buffer of
+   * this struct then has `height` rows; only the pixel -> ray mapping (lib/nerf_utils.py:36-39)
+   * sees the offset.  This is how one image's rays are split over GPUs when there are fewer
+   * images than GPUs (parallel.render_row_sharded). */
+  int32_t row_offset;
+  int32_t full_height;
 } nfi_render_params;
 
 /* Upstream gradients in, parameter gradients out (all device pointers).

@@ -55,6 +55,7 @@ class RenderParams(ctypes.Structure):
         ('peer_rank', ctypes.c_int32 * 7), ('peer_epoch', ctypes.c_uint32),
         ('peer_done', ctypes.c_void_p),
         ('view_features', ctypes.c_void_p), ('w3', ctypes.c_void_p), ('b3', ctypes.c_void_p),
+        ('row_offset', ctypes.c_int32), ('full_height', ctypes.c_int32),
     ]
 
 

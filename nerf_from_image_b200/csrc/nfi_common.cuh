@@ -46,7 +46,8 @@ __device__ __forceinline__ void tile_pixel(int tile_x, int tile_y, int warp, int
 __device__ __forceinline__ void setup_ray(const nfi_render_params& p, int b, int py, int px,
                                           Ray& r) {
   float ii = (float)px / (float)p.width;
-  float jj = (float)py / (float)p.height;
+  // (row tiles: py counts from row_offset of a full_height-row image, nfi_render.h)
+  float jj = (float)(py + p.row_offset) / (float)(p.full_height > 0 ? p.full_height : p.height);
   const float* M = p.c2w + b * 16;
   float rx, ry, rz;  // un-normalised direction
   if (p.focal != nullptr) {

@@ -59,6 +59,9 @@ int check_params(const nfi_render_params* p) {
     return fail("planes / decoder weights / tform_cam2world must be given");
   if (p->n_attention > 0 && !p->palette) return fail("palette missing (attention_values > 0)");
   if (p->use_sdf && (!p->beta || !p->alpha)) return fail("use_sdf needs beta and alpha");
+  if (p->row_offset < 0 || p->full_height < 0 ||
+      (p->full_height > 0 && p->row_offset + p->height > p->full_height))
+    return fail("row tile outside the image (row_offset + height > full_height)");
   if (p->view_features && (!p->w3 || !p->b3))
     return fail("view_features given without w3 / b3 (ViewDirectionMapper.output)");
   if (p->noise_mode == NFI_NOISE_EXPLICIT) {

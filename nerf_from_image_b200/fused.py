@@ -78,7 +78,7 @@ def planes_from_channel_last(planes_cl):
 
 def _make_params(cfg, planes_cl, w1, b1, w2, b2, palette, beta, alpha, c2w,
                  focal, center, bbox, height, width, S, noise_t, noise_u,
-                 extra_mode, view_feat=None, w3=None, b3=None):
+                 extra_mode, view_feat=None, w3=None, b3=None, rows=None):
     p = _lib.RenderParams()
     B, _, R, _, _ = planes_cl.shape
     p.batch, p.height, p.width, p.num_samples = B, height, width, S
@@ -98,6 +98,8 @@ def _make_params(cfg, planes_cl, w1, b1, w2, b2, palette, beta, alpha, c2w,
     p.c2w, p.focal, p.center, p.bbox = _ptr(c2w), _ptr(focal), _ptr(center), _ptr(bbox)
     p.noise_t, p.noise_u = _ptr(noise_t), _ptr(noise_u)
     p.view_features, p.w3, p.b3 = _ptr(view_feat), _ptr(w3), _ptr(b3)
+    if rows is not None:
+        p.row_offset, p.full_height = int(rows[0]), int(rows[1])
     return p
 
 
@@ -161,7 +163,8 @@ class FusedTriplaneRender(torch.autograd.Function):
     def forward(ctx, planes, w1, b1, w2, b2, palette, beta, alpha, c2w, focal,
                 center, bbox, cfg, height, width, S, noise_t, noise_u,
                 extra_mode, cam_grad, compute_normals=False, out=None,
-                planes_layout='channel_first', peers=None, view_feat=None, w3=None, b3=None):
+                planes_layout='channel_first', peers=None, view_feat=None, w3=None, b3=None,
+                rows=None):
         channel_last = planes_layout == 'channel_last'
         _check_shapes(cfg, planes, w1, b1, w2, b2, palette, c2w, focal, center,
                       bbox, height, width, S, noise_t, noise_u, channel_last, view_feat, w3, b3)
@@ -220,7 +223,7 @@ class FusedTriplaneRender(torch.autograd.Function):
                              t['palette'], t['beta'], t['alpha'], t['c2w'],
                              t['focal'], t['center'], t['bbox'], height, width,
                              S, t['noise_t'], t['noise_u'], extra_mode,
-                             t['view_feat'], t['w3'], t['b3'])
+                             t['view_feat'], t['w3'], t['b3'], rows)
             p.rgb, p.depth, p.mask, p.extra = _ptr(rgb), _ptr(depth), _ptr(mask), _ptr(extra)
             p.z_fine = _ptr(z_fine)
             if normals is not None:
@@ -263,6 +266,7 @@ class FusedTriplaneRender(torch.autograd.Function):
             ctx.cfg, ctx.dims, ctx.extra_mode = cfg, (height, width, S), extra_mode
             ctx.cam_grad = cam_grad
             ctx.channel_last = channel_last
+            ctx.rows = rows
             # caller-owned outputs are slices of buffers an in-place all-gather completes
             # afterwards (parallel.py); it rewrites this rank's slice with the values it
             # already holds, so those are saved as aliases with their own version counter
@@ -331,7 +335,7 @@ class FusedTriplaneRender(torch.autograd.Function):
                              t['palette'], t['beta'], t['alpha'], t['c2w'],
                              t['focal'], t['center'], t['bbox'], height, width,
                              S, t['noise_t'], t['noise_u'], ctx.extra_mode,
-                             t['view_feat'], t['w3'], t['b3'])
+                             t['view_feat'], t['w3'], t['b3'], ctx.rows)
             p.rgb, p.depth, p.mask = _ptr(rgb), _ptr(mask), _ptr(mask)  # unused
             p.extra = _ptr(extra)
             p.z_fine = _ptr(z_fine)
@@ -357,7 +361,7 @@ class FusedTriplaneRender(torch.autograd.Function):
                     focal_l = leaf(t['focal'], n_focal)
                     center_l = leaf(t['center'], n_center)
                     bbox_l = leaf(t['bbox'], n_bbox)
-                    o, d = unit_rays(height, width, c2w_l, focal_l, center_l, bbox_l)
+                    o, d = unit_rays(height, width, c2w_l, focal_l, center_l, bbox_l, ctx.rows)
                     leaves = [x for x, n in ((c2w_l, n_c2w), (focal_l, n_focal),
                                              (center_l, n_center), (bbox_l, n_bbox))
                               if x is not None and n]
@@ -377,14 +381,14 @@ class FusedTriplaneRender(torch.autograd.Function):
                     gbbox = res.pop(0)
         return (gplanes, gw1, gb1, gw2, gb2, gpal, gbeta, galpha, gc2w, gfocal,
                 gcenter, gbbox, None, None, None, None, None, None, None, None, None, None,
-                None, None, gvf, gw3, gb3)
+                None, None, gvf, gw3, gb3, None)
 
 
 def fused_render(planes, w1, b1, w2, b2, palette, beta, alpha, c2w, focal,
                  center, bbox, cfg, height, width, num_samples, noise_t=None,
                  noise_u=None, extra_mode=_lib.EXTRA_NONE, cam_grad=True,
                  compute_normals=False, out=None, planes_layout='channel_first', peers=None,
-                 view=None):
+                 view=None, rows=None):
     """Functional form; returns (rgb, depth, mask, extra|None), with
     ``compute_normals`` (rgb, depth, mask, extra|None, normals).  ``out=(rgb, depth,
     mask)`` makes the kernel write into caller-owned tensors (see parallel.py).
@@ -395,6 +399,8 @@ def fused_render(planes, w1, b1, w2, b2, palette, beta, alpha, c2w, focal,
     ranks' buffers; the kernel stores its tiles there too (parallel.PeerExchange).
     ``view``: (view_features [B,H,W,32], w3 [A,32], b3 [A]) switches on the view-direction
     conditioning of the CARLA models (--use_viewdir; fp32 SIMT kernels).
+    ``rows``: (row_offset, full_height) renders rows [row_offset, row_offset + height) of images
+    full_height rows tall; every per-ray tensor (noise, outputs) then has ``height`` rows.
 
     The kernels compute in fp32 like the reference's render (run.py:59-60).  Under
     autocast (BASELINE config 4 trains the synthesis network in bf16) the field tensors
@@ -409,7 +415,7 @@ def fused_render(planes, w1, b1, w2, b2, palette, beta, alpha, c2w, focal,
     rgb, depth, mask, extra, normals = FusedTriplaneRender.apply(
         planes, w1, b1, w2, b2, palette, beta, alpha, c2w, focal, center, bbox,
         cfg, height, width, num_samples, noise_t, noise_u, extra_mode, cam_grad,
-        compute_normals, out, planes_layout, peers, view_feat, w3, b3)
+        compute_normals, out, planes_layout, peers, view_feat, w3, b3, rows)
     extra = extra if extra_mode != _lib.EXTRA_NONE else None
     if compute_normals:
         return rgb, depth, mask, extra, normals

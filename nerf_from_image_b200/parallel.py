@@ -1,4 +1,5 @@
-"""Multi-GPU: one process per GPU, rays sharded by image, one all-gather.
+"""Multi-GPU: one process per GPU, rays sharded by image (or, with fewer images than GPUs, by
+row tiles of each image: ``render_row_sharded``), one all-gather.
 
 The reference scales with nn.DataParallel: scatter on the batch dimension,
 replicate the module, gather the outputs on GPU 0 (run.py:636-644).  The render
@@ -156,6 +157,62 @@ def render_sharded(render_fn, batch_inputs, batch, gather=True, group=None, inpl
     if world == 1 or not gather:
         return rgb, depth, mask
     return all_gather_outputs(rgb, depth, mask, batch, group)
+
+
+def row_range(height, world_size, rank, align=8):
+    """Contiguous rows [r0, r1) of an image for ``rank`` when ONE image's rays are split over the
+    GPUs (fewer images than GPUs: SURVEY.md section 8e).  Shards are multiples of ``align`` rows
+    (the kernels' tile height), the remainder goes to the lowest ranks; a rank may get none."""
+    if not (0 <= rank < world_size):
+        raise ValueError('rank %d outside world of %d' % (rank, world_size))
+    blocks = -(-height // align)
+    base, rem = divmod(blocks, world_size)
+    b0 = rank * base + min(rank, rem)
+    b1 = b0 + base + (1 if rank < rem else 0)
+    return min(b0 * align, height), min(b1 * align, height)
+
+
+def slice_rows(noise_t, noise_u, batch, height, width, r0, r1):
+    """The two noise tensors of render() restricted to rows [r0, r1): noise_t [B,H,W,S] ->
+    [B,h,W,S], noise_u [B*H*W,S] -> [B*h*W,S]."""
+    nt = None if noise_t is None else noise_t[:, r0:r1].contiguous()
+    nu = None
+    if noise_u is not None:
+        S = noise_u.shape[-1]
+        nu = noise_u.view(batch, height, width, S)[:, r0:r1].reshape(-1, S).contiguous()
+    return nt, nu
+
+
+def render_row_sharded(render_fn, height, group=None, align=8):
+    """Splits every image's ROWS over the ranks: ``render_fn(r0, r1)`` renders rows [r0, r1) of
+    the whole batch (``fused_render(..., height=r1 - r0, rows=(r0, height))``) and returns
+    (rgb [B,h,W,3], depth [B,h,W], mask [B,h,W]); every rank gets the full images back (one
+    all-gather of the padded packed tiles, then trim + concatenate along the rows)."""
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    rank = dist.get_rank(group) if dist.is_initialized() else 0
+    r0, r1 = row_range(height, world, rank, align)
+    if world == 1:
+        return tuple(render_fn(r0, r1)[:3])
+    ranges = [row_range(height, world, r, align) for r in range(world)]
+    longest = max(b - a for a, b in ranges)
+    if r1 > r0:
+        packed = pack_outputs(*render_fn(r0, r1)[:3])            # [B,h,W,5]
+        shape = (packed.shape[0], longest) + tuple(packed.shape[2:])
+    else:  # nothing to render on this rank: it still takes part in the exchange
+        shape = None
+    # every rank must know the tile shape: ranks without rows learn it from rank 0
+    meta = [shape]
+    dist.broadcast_object_list(meta, src=0, group=group)
+    shape = shape or meta[0]
+    dev = packed.device if r1 > r0 else torch.device(
+        'cuda', torch.cuda.current_device()) if dist.get_backend(group) == 'nccl' else 'cpu'
+    tile = torch.zeros(shape, device=dev, dtype=torch.float32)
+    if r1 > r0:
+        tile[:, :r1 - r0] = packed
+    out = [torch.empty_like(tile) for _ in range(world)]
+    dist.all_gather(out, tile, group=group)
+    full = torch.cat([o[:, :b - a] for o, (a, b) in zip(out, ranges) if b > a], dim=1)
+    return unpack_outputs(full)
 
 
 class PeerExchange:

@@ -13,11 +13,14 @@ import torch
 import torch.nn.functional as F
 
 
-def unit_rays(height, width, c2w, focal, center, bbox):
+def unit_rays(height, width, c2w, focal, center, bbox, rows=None):
+    """``rows`` = (row_offset, full_height): the rays of rows [row_offset, row_offset + height)
+    of images full_height rows tall (parallel.render_row_sharded)."""
     B = c2w.shape[0]
     dev, dt = c2w.device, c2w.dtype
+    r0, hfull = rows if rows is not None else (0, height)
     u = (torch.arange(width, device=dev, dtype=dt) / width).view(1, 1, width)
-    v = (torch.arange(height, device=dev, dtype=dt) / height).view(1, height, 1)
+    v = ((torch.arange(height, device=dev, dtype=dt) + r0) / hfull).view(1, height, 1)
     u = u.expand(B, height, width)
     v = v.expand(B, height, width)
     rot = c2w[:, None, None, :3, :3]

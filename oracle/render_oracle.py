@@ -42,7 +42,7 @@ import torch.nn.functional as F
 # --------------------------------------------------------------------------
 def ray_bundle(height: int, width: int, focal: Optional[torch.Tensor],
                c2w: torch.Tensor, bbox: Optional[torch.Tensor],
-               center: Optional[torch.Tensor] = None):
+               center: Optional[torch.Tensor] = None, rows=None):
     """Ray origins / (unnormalised) directions, [B,H,W,3] each.
 
     Pixel (h, w) sits at (w/W, h/H): there is no half-pixel offset
@@ -51,8 +51,11 @@ def ray_bundle(height: int, width: int, focal: Optional[torch.Tensor],
     """
     dev = c2w.device
     # (dtype follows the cameras: the fp64 runs of tests/ use the oracle as ground truth)
+    # rows = (row_offset, full_height): rows [row_offset, row_offset + height) of a taller image
+    # (the row-tile split of the multi-GPU path; not a reference feature)
+    r0, hfull = rows if rows is not None else (0, height)
     u = (torch.arange(width, device=dev, dtype=c2w.dtype) / width).view(1, 1, width)
-    v = (torch.arange(height, device=dev, dtype=c2w.dtype) / height).view(1, height, 1)
+    v = ((torch.arange(height, device=dev, dtype=c2w.dtype) + r0) / hfull).view(1, height, 1)
     u = u.expand(1, height, width)
     v = v.expand(1, height, width)
     rot = c2w[:, None, None, :3, :3]
@@ -357,7 +360,8 @@ def render_oracle(planes, w1, b1, w2, b2, palette, beta, alpha,
                   white_background=False, use_sdf=True, fine_sampling=True,
                   compute_normals=False, compute_semantics=False,
                   compute_coords=False, force_no_cam_grad=False,
-                  global_near_far_fallback=True, view_features=None, w3=None, b3=None):
+                  global_near_far_fallback=True, view_features=None, w3=None, b3=None,
+                  rows=None):
     """run.py:176-350 with the planes / palette given instead of produced by
     ``target_model`` and with the two random draws passed in:
 
@@ -375,7 +379,7 @@ def render_oracle(planes, w1, b1, w2, b2, palette, beta, alpha,
     """
     B = planes.shape[0]
     S = num_samples
-    origins, dirs = ray_bundle(height, width, focal, c2w, bbox, center)
+    origins, dirs = ray_bundle(height, width, focal, c2w, bbox, center, rows)
     dirs = F.normalize(dirs, dim=-1)
     with torch.no_grad():
         near, far, _ = near_far_planes(origins, dirs, scene_range,

@@ -87,6 +87,46 @@ def test_sharded_render_equals_single_process(tmp_path, world, batch, inplace):
         assert torch.equal(mask, ref['mask'])
 
 
+def _row_worker(rank, world, port, out_dir):
+    os.environ['MASTER_ADDR'] = '127.0.0.1'
+    os.environ['MASTER_PORT'] = str(port)
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    torch.set_num_threads(1)
+    B, H, W, S = 1, 40, 8, 8            # ONE image, more ranks than images: rows are split
+    scene, cams = Hh.make_case('p3d_bbox', seed=5, batch=B, plane_res=16)
+    nt, nu = synthetic.make_noise(5, B, H, W, S)
+
+    def render_fn(r0, r1):
+        nt_, nu_ = parallel.slice_rows(nt, nu, B, H, W, r0, r1)
+        o = Hh.run_oracle(scene, cams, r1 - r0, W, S, nt_, nu_, rows=(r0, H),
+                          global_near_far_fallback=False)
+        return o['rgb'], o['depth'], o['mask']
+
+    rgb, depth, mask = parallel.render_row_sharded(render_fn, H)
+    torch.save((rgb, depth, mask), os.path.join(out_dir, 'r%d.pt' % rank))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize('world', [2, 3, 7])
+def test_row_sharded_render_equals_single_process(tmp_path, world):
+    """Fewer images than ranks: every image's rows are split over the ranks
+    in multiples of the 8-row tile height (40 rows: 24 + 16, 16 + 16 + 8, and five ranks of seven
+    with rows), gathered back along the rows."""
+    assert [parallel.row_range(40, 3, r) for r in range(3)] == [(0, 16), (16, 32), (32, 40)]
+    assert [parallel.row_range(40, 7, r) for r in range(7)] == [(0, 8), (8, 16), (16, 24), (24, 32),
+                                                                (32, 40), (40, 40), (40, 40)]
+    mp.spawn(_row_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    B, H, W, S = 1, 40, 8, 8
+    scene, cams = Hh.make_case('p3d_bbox', seed=5, batch=B, plane_res=16)
+    nt, nu = synthetic.make_noise(5, B, H, W, S)
+    ref = Hh.run_oracle(scene, cams, H, W, S, nt, nu, global_near_far_fallback=False)
+    for r in range(world):
+        rgb, depth, mask = torch.load(os.path.join(str(tmp_path), 'r%d.pt' % r))
+        assert torch.equal(rgb, ref['rgb']) and torch.equal(depth, ref['depth'])
+        assert torch.equal(mask, ref['mask'])
+
+
 def _grad_worker(rank, world, port, out_dir):
     os.environ['MASTER_ADDR'] = '127.0.0.1'
     os.environ['MASTER_PORT'] = str(port)
