@@ -7,6 +7,7 @@
 #include "nfi_backward.cuh"
 #include "nfi_backward_pipe.cuh"
 #include "nfi_forward_pipe.cuh"
+#include "nfi_normals_pipe.cuh"
 #include "nfi_pipe_launch.h"
 #include "nfi_wgrad_pipe.cuh"
 
@@ -151,6 +152,30 @@ int launch_pipe_wgrad(const nfi_render_params& p, const nfi_render_grads& g, int
   if (nout_pad == 4) return run_wgrad<4, false>(p, g, wimg, grid, st, err, err_len);
   if (nout_pad == 12) return run_wgrad<12, false>(p, g, wimg, grid, st, err, err_len);
   return run_wgrad<16, false>(p, g, wimg, grid, st, err, err_len);
+}
+
+// surface normals after render_forward_pipe (nfi_normals_pipe.cuh): `wimg` = the forward weight
+// image of that launch, `wimg_bwd` = 32 KiB for the backward image (W1^T / 3 is what is used)
+int launch_pipe_normals(const nfi_render_params& p, int nout_pad, const unsigned char* wimg,
+                        unsigned char* wimg_bwd, unsigned grid, cudaStream_t st, char* err,
+                        size_t err_len) {
+  const int nout = 1 + (p.n_attention > 0 ? p.n_attention : 3);
+  prep_weight_image_bwd<<<1, 256, 0, st>>>(p.w1, p.w2, nout, wimg_bwd);
+  NFI_PCUDA(cudaGetLastError());
+  NFI_PCUDA(cudaMemsetAsync(p.normals, 0,
+                            (size_t)p.batch * p.height * p.width * 3 * sizeof(float), st));
+  using Cfg = BwdCfg<2>;
+  constexpr int smem = Cfg::kSmBytes + (kBwdSlots * 128 + kHid) * (int)sizeof(float);
+#define NFI_NRM(NP)                                                                          \
+  do {                                                                                       \
+    auto k = render_normals_pipe<NP, 2>;                                                     \
+    NFI_PCUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));   \
+    k<<<grid, Cfg::kThreadsTotal, smem, st>>>(p, wimg, wimg_bwd);                            \
+  } while (0)
+  if (nout_pad == 4) NFI_NRM(4); else if (nout_pad == 12) NFI_NRM(12); else NFI_NRM(16);
+#undef NFI_NRM
+  NFI_PCUDA(cudaGetLastError());
+  return 0;
 }
 
 }  // namespace nfi

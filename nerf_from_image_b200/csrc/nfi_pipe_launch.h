@@ -26,6 +26,11 @@ size_t pipe_wgrad_workspace_bytes(unsigned grid);
 int launch_pipe_wgrad(const nfi_render_params& p, const nfi_render_grads& g, int nout_pad,
                       unsigned char* wimg, unsigned grid, bool planes, cudaStream_t st, char* err,
                       size_t err_len);
+// composited surface normals (params.normals, overwritten) after a render_forward_pipe launch of
+// the same params (z_fine and mask filled): render_normals_pipe
+int launch_pipe_normals(const nfi_render_params& p, int nout_pad, const unsigned char* wimg,
+                        unsigned char* wimg_bwd, unsigned grid, cudaStream_t st, char* err,
+                        size_t err_len);
 // the pipelined kernels' weight image (log2 e folded into layer 1 and the colour rows of
 // layer 2, padded logits at -1e30)
 int launch_pipe_weight_image(const nfi_render_params& p, unsigned char* wimg, cudaStream_t st);

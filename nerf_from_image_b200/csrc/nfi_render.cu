@@ -105,9 +105,13 @@ size_t num_tc_ctas(const nfi_render_params* p) {  // persistent grid: at most on
 // Can the tensor-core kernel take this configuration?
 bool tc_supported(const nfi_render_params* p) {
   if (p->view_features) return false;  // view-direction conditioning (CARLA): SIMT kernels
-  if (p->compute_normals && !(p->mlp_mode & 0x1000)) return false;  // evaluation-only: SIMT kernel
   const int mode = p->mlp_mode & 0xff;
   const bool pipe_mode = (mode == NFI_MLP_TC_PIPE || mode == NFI_MLP_AUTO || mode == NFI_MLP_TC_WARPSPEC);
+  // surface normals: a second pipelined kernel after the render (nfi_normals_pipe.cuh), which
+  // walks the merged samples and so needs the forward pass's fine depths; else the SIMT kernel
+  if (p->compute_normals && !(p->mlp_mode & 0x1000) &&
+      !(pipe_mode && (!p->fine_sampling || p->z_fine != nullptr) && p->n_peers == 0))
+    return false;
   // semantics: the pipelined kernel parks the coarse samples' probabilities; NOUT_PAD = 4 only
   // exists for palettes of <= 3 entries, kept on the SIMT kernel
   if (p->extra_mode == NFI_EXTRA_SEMANTICS && !(pipe_mode && p->n_attention > 3)) return false;
@@ -369,7 +373,8 @@ size_t nfi_render_workspace_bytes(const nfi_render_params* p) {
             sizeof(float);
     }
   }
-  return kWeightImageBytes + fwd + 256;
+  // (+ the backward weight image of the normals kernel, behind the scratch)
+  return kWeightImageBytes + fwd + 256 + (wants_normals(p) && tc_supported(p) ? 32768 : 0);
 }
 
 int nfi_planes_to_channel_last(const float* xy, const float* xz, const float* yz,
@@ -425,7 +430,20 @@ int nfi_render_forward(const nfi_render_params* params, void* stream) {
   if (p.n_peers < 0 || p.n_peers > NFI_MAX_PEERS) return fail("n_peers out of range");
   for (int q = 0; q < p.n_peers; ++q)
     if (!p.peer_rgb[q] || !p.peer_depth[q] || !p.peer_mask[q]) return fail("peer output pointer is NULL");
-  if (want_tc) return launch_fwd_tc(p, np, st);
+  if (want_tc) {
+    if (int rc = launch_fwd_tc(p, np, st)) return rc;
+    if (wants_normals(params)) {
+      int dev = 0, sms = 0;
+      NFI_CUDA(cudaGetDevice(&dev));
+      NFI_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+      size_t grid = num_ctas(&p);
+      if (grid > (size_t)sms) grid = sms;
+      unsigned char* ws = (unsigned char*)p.workspace;
+      const size_t off = (nfi_render_workspace_bytes(params) - 32768) & ~(size_t)255;
+      return nfi::launch_pipe_normals(p, np, ws, ws + off, (unsigned)grid, st, g_err, sizeof(g_err));
+    }
+    return 0;
+  }
   if (p.n_peers > 0) return fail("peer outputs (n_peers > 0) need the pipelined kernel");
   if (p.view_features) {
     nfi_render_params pv = p;  // SIMT scratch starts after the weight-image header

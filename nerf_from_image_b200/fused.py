@@ -217,7 +217,8 @@ class FusedTriplaneRender(torch.autograd.Function):
                 assert cfg.use_sdf
                 normals = torch.empty(B, height, width, 3, device=dev)
             z_fine = None
-            if needs_grad and cfg.fine_sampling:
+            if (needs_grad or compute_normals) and cfg.fine_sampling:
+                # the fine depths: kept for the backward pass, and read by the normals kernel
                 z_fine = torch.empty(B * height * width, S, device=dev)
             p = _make_params(cfg, planes_cl, t['w1'], t['b1'], t['w2'], t['b2'],
                              t['palette'], t['beta'], t['alpha'], t['c2w'],
