@@ -95,7 +95,8 @@ typedef struct nfi_render_params {
   int32_t noise_mode;    /* enum nfi_noise_mode */
   int32_t extra_mode;    /* enum nfi_extra_mode */
   int32_t compute_normals; /* analytic grad of the SDF, normalised, composited
-                              with detached weights (generator.py:614-623) */
+                              with detached weights (generator.py:614-623): a second
+                              pipelined kernel after the render (render_normals_pipe) */
   int32_t mlp_mode;      /* enum nfi_mlp_mode */
   /* ---- radiance field (models/generator.py:288-331,587-681) ---- */
   const float *planes; /* [B,3,R,R,32] channel-last, see nfi_planes_to_channel_last */
@@ -120,7 +121,8 @@ typedef struct nfi_render_params {
   float *mask;    /* [B,H,W]   */
   float *extra;   /* [B,H,W,3] or [B,H,W,A] or NULL (extra_mode) */
   float *normals; /* [B,H,W,3] or NULL */
-  float *z_fine;  /* [B*H*W,S] sorted fine depths, kept for the backward pass;
+  float *z_fine;  /* [B*H*W,S] sorted fine depths, kept for the backward pass and read by the
+                     pipelined normals kernel (compute_normals without it: fp32 SIMT kernel);
                      NULL = do not save */
   /* ---- scratch ---- */
   void *workspace;        /* >= nfi_render_workspace_bytes(params) */
