@@ -24,10 +24,16 @@
 // synthesis convolutions do): the gather writes the features as two [128][32 bf16] SWIZZLE_64B
 // tiles (16 KB per stage instead of 32) that are BOTH the K-major A operand of MMA1 and, rows = K,
 // the MN-major B operand of the dW1 products.  The rest of the chain is render_backward_pipe's
-// (MMA2 / MMA3 in 3xTF32, softplus and its reverse, reverse compositing); MMA4 and the scatter are
-// gone: plane / palette / pose gradients come from render_backward_pipe, launched beside this
-// kernel with the decoder as a constant.  TMEM: two slots of 224 columns
-//   [0,64) D1 -> H_lo   [64,128) H_hi   [128,144) D2 -> dOut_hi   [144,160) dOut_lo   [160,224) D3
+// (MMA2 / MMA3 in 3xTF32, softplus and its reverse, reverse compositing).  Two forms:
+//   PLANES = true  (the generator step: decoder AND planes / palette / beta / alpha gradients,
+//                   cameras are data): MMA4 and the scatter of render_backward_pipe are folded
+//                   in -- ONE sweep, 26.0 ms per 32 images at config 2 against 21.7 + 16.7 ms of
+//                   the two kernels (profiles/r2_time_wgrad.txt);
+//   PLANES = false (decoder gradients only, or a pose gradient is wanted too): this kernel beside
+//                   render_backward_pipe, which then sees the decoder as a constant.
+// TMEM: two slots of 224 columns
+//   [0,64) D1 -> H_lo (-> D4)   [64,128) H_hi (-> dpre_hi)   [128,144) D2 -> dOut_hi
+//   [144,160) dOut_lo   [160,224) D3 (-> dpre_lo)
 // and the accumulators at [448,504).
 #pragma once
 #include <cuda_bf16.h>
@@ -40,11 +46,12 @@ constexpr int kWgSlots = 2;
 constexpr int kWgSlotCols = 224;
 constexpr int kWgAccCol = 448;
 constexpr int kWgStages = 3;
-// The tensor core ADDS into a TMEM accumulator with truncation, a bias of about half an ulp of
-// the RUNNING sum per instruction: over the ~28,000 accumulating MMAs of a CTA at config 2 it
-// reached 1e-2 of columns whose terms cancel.  The chain is therefore cut every kWgFlush steps
-// (128 MMAs: 4e-6): the accumulator is added, in fp32 round-to-nearest, to a per-CTA row buffer
-// in global memory (L2-resident, single writer per element) and the next chain starts from zero.
+// The tensor core adds into a TMEM accumulator with truncation, a bias that grows with the length
+// of the chain (finding 3: 1.35e-4 after 4,608 terms in the synthesis
+// convolutions); a CTA of config 2 would chain 28,000 accumulating MMAs = 450,000 terms.  The
+// chain is therefore cut every kWgFlush steps (2,048 terms): the accumulator is added, in fp32
+// round-to-nearest, to a per-CTA row buffer in global memory (L2-resident, single writer per
+// element) and the next chain starts from zero.
 constexpr int kWgFlush = 16;
 constexpr size_t kWgAccBytesPerCta = 128 * 64 * sizeof(float);
 
