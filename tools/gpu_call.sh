@@ -35,6 +35,9 @@ for a in "$@"; do
              for f in weak strong nccl ncclstrong config3 config4; do echo "== $f n=$n"; cut -c1-700 gpurun_out/r2_bench_${f}_n$n.json; tail -3 gpurun_out/r2_bench_${f}_n$n.err | cut -c1-300; done;;
     cfg1) (timeout 300 python bench.py --config 3 | tail -1 > gpurun_out/r2_bench_config3_n1.json) 2> gpurun_out/r2_bench_config3_n1.err; (timeout 300 python bench.py --config 4 | tail -1 > gpurun_out/r2_bench_config4_n1.json) 2> gpurun_out/r2_bench_config4_n1.err; (timeout 600 python bench.py --config 5 | tail -1 > gpurun_out/r2_bench_config5_n1.json) 2> gpurun_out/r2_bench_config5_n1.err
           for f in config3 config4 config5; do echo "== $f"; cut -c1-1500 gpurun_out/r2_bench_${f}_n1.json; tail -3 gpurun_out/r2_bench_${f}_n1.err | cut -c1-300; done;;
+    ncu_normals) timeout 600 ncu --set full --clock-control none --import-source on -k regex:render_normals_pipe -s 2 -c 1 -f -o gpurun_out/r2_normals python tools/time_normals.py 32 > gpurun_out/r2_ncu_normals.log 2>&1
+             ncu -i gpurun_out/r2_normals.ncu-rep --page raw --csv > gpurun_out/r2_normals_raw.csv 2>/dev/null
+             rm -f gpurun_out/r2_normals.ncu-rep; tail -2 gpurun_out/r2_ncu_normals.log | cut -c1-200;;
     smoke) timeout 300 python __graft_entry__.py smoke 2>&1 | tail -3;;
     ncu_wgrad) timeout 600 ncu --set full --clock-control none --import-source on -k regex:render_wgrad_pipe -s 6 -c 1 -f -o gpurun_out/r2_wgrad python tools/time_wgrad.py 32 > gpurun_out/r2_ncu_wgrad.log 2>&1
              ncu -i gpurun_out/r2_wgrad.ncu-rep --page raw --csv > gpurun_out/r2_wgrad_raw.csv 2>/dev/null
