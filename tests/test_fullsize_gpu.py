@@ -178,3 +178,35 @@ def test_channel_last_planes_are_used_as_they_are(cuda_lib):
     assert gb.shape == pl.shape
     # (plane-gradient atomics are order-dependent: equal to rounding, not bitwise)
     assert Hh.rel_l2(gb.permute(0, 1, 4, 2, 3), ga) < 1e-5
+
+
+@pytest.mark.parametrize('case,A,kw', [('p3d_plain', 10, {}), ('chairs_white_center', 15, {}),
+                                       ('cub_ortho', 0, {}), ('p3d_bbox', 10, dict(use_sdf=False)),
+                                       ('p3d_plain', 3, dict(fine_sampling=False))])
+def test_generator_step_backward_in_one_sweep(cuda_lib, case, A, kw):
+    """The GAN generator step (run.py:1007-1044): gradients to the planes, the palette, beta /
+    alpha AND the decoder weights, cameras are data -- render_wgrad_pipe<PLANES>, the whole
+    backward in one tcgen05 sweep -- against the oracle's autograd in float64; every head variant
+    (palettes of 15 / 10 / 3 entries, direct colours, density model, no fine pass, white
+    background, orthographic cameras)."""
+    torch.backends.cuda.matmul.allow_tf32 = False
+    B, H, W, S = 2, 64, 64, 32
+    scene, cams = Hh.make_case(case, batch=B, plane_res=128, attention_values=A, device='cuda')
+    fine = kw.get('fine_sampling', True)
+    nt, nu = synthetic.make_noise(61, B, H, W, S, fine=fine, device='cuda')
+    use_sdf = kw.get('use_sdf', True)
+    names = ['planes', 'w1', 'b1', 'w2', 'b2'] + (['palette'] if A > 0 else []) + \
+        (['beta', 'alpha'] if use_sdf else [])
+    wr, wm = _weights((B, H, W, 3), (B, H, W), 'cuda')
+    dbl = lambda d: {k: (v.double() if torch.is_tensor(v) else v) for k, v in d.items()}
+    sc, cm = _leaves(dbl(scene), dbl(cams), names, [])
+    ref = Hh.run_oracle(sc, cm, H, W, S, nt.double(), nu.double() if nu is not None else None, **kw)
+    gref = torch.autograd.grad((ref['rgb'] * wr.double()).sum() + (ref['mask'] * wm.double()).sum(),
+                               [sc[n] for n in names])
+    sc2, cm2 = _leaves(scene, cams, names, [])
+    rgb, depth, mask, _ = Hh.run_cuda(sc2, cm2, H, W, S, nt, nu, mlp_mode=4, **kw)
+    assert Hh.rel_l2(rgb.detach(), ref['rgb'].detach().float()) < 2e-4
+    got = torch.autograd.grad((rgb * wr).sum() + (mask * wm).sum(), [sc2[n] for n in names])
+    for n, a, b in zip(names, got, gref):
+        err = Hh.rel_l2(a.double(), b)
+        assert err < (5e-3 if n == 'beta' else 1e-3), (n, err)
