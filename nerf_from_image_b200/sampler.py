@@ -76,8 +76,18 @@ class FusedSampler:
             scene_range = target_model.scene_range
         if use_sdf is None:
             use_sdf = bool(getattr(target_model, 'use_sdf', beta is not None))
-        return cls(planes, w1, b1, w2, b2, palette, beta if use_sdf else None,
-                   alpha if use_sdf else None, scene_range, use_sdf, bbox_debug)
+        view_conditioned = bool(getattr(target_model, 'use_viewdir', False))
+        if view_conditioned:
+            # --use_viewdir: the decoder emits 1 + 32 values and the colour needs the per-RAY
+            # view directions the reference closure captured (generator.py:242-251,662-663);
+            # the seam serves the geometry outputs of such a model (row 0 of layer 2)
+            n_col = palette.shape[1] if palette is not None else 3
+            w2 = torch.cat((w2[:1], torch.zeros(n_col, 64, device=w2.device, dtype=w2.dtype)))
+            b2 = torch.cat((b2[:1], torch.zeros(n_col, device=b2.device, dtype=b2.dtype)))
+        out = cls(planes, w1, b1, w2, b2, palette, beta if use_sdf else None,
+                  alpha if use_sdf else None, scene_range, use_sdf, bbox_debug)
+        out.view_conditioned = view_conditioned
+        return out
 
     def __call__(self, x_in, request_sampler_outputs=['sigma', 'rgb']):
         for output in request_sampler_outputs:
@@ -86,6 +96,12 @@ class FusedSampler:
             assert self.use_sdf  # generator.py:600
         if 'semantics' in request_sampler_outputs:
             assert self.attention_values > 0  # generator.py:673
+        if getattr(self, 'view_conditioned', False) and \
+                ('rgb' in request_sampler_outputs or 'semantics' in request_sampler_outputs):
+            raise NotImplementedError(
+                "colours of a view-direction-conditioned model (--use_viewdir) need the rays' view "
+                "directions: render() evaluates them; this seam offers 'sigma', 'sdf_distance', "
+                "'normals' and 'coords' for such models")
         if torch.is_grad_enabled() and (self._needs_grad or x_in.requires_grad):
             raise _lib.NfiError(
                 'the fused sampler is forward-only: call it under torch.no_grad(), or keep '

@@ -140,3 +140,28 @@ def test_errors(cuda_lib):
         Hh.run_cuda(bad, cams, H, W, S, nt, nu)
     with pytest.raises(AssertionError):          # 33 decoder rows are required with a view
         Hh.run_cuda(dict(scene, w2=scene['w2'][:11], b2=scene['b2'][:11]), cams, H, W, S, nt, nu)
+
+
+def test_sampler_seam_serves_the_geometry_of_a_view_conditioned_model(cuda_lib):
+    """FusedSampler.from_generator on a --use_viewdir model: 'sigma' / 'sdf_distance' / 'normals'
+    (row 0 of the 33-row decoder) as the oracle's sampler, colours refused (they need the rays)."""
+    import types
+    from nerf_from_image_b200.sampler import FusedSampler
+    from oracle import render_oracle as O
+    scene, cams = make('p3d_plain')
+    sc = Hh.to_device(scene, 'cuda')
+    g = torch.Generator().manual_seed(5)
+    x = ((torch.rand(2, 7, 9, 3, generator=g) * 2 - 1) * scene['scene_range'] * 0.9)
+    model = types.SimpleNamespace(use_viewdir=True, use_sdf=True, scene_range=scene['scene_range'])
+    field = dict(planes=sc['planes'], palette=sc['palette'], w1=sc['w1'], b1=sc['b1'], w2=sc['w2'],
+                 b2=sc['b2'], beta=sc['beta'], alpha=sc['alpha'])
+    fs = FusedSampler.from_generator(model, field)
+    with torch.no_grad():
+        got = fs(x.cuda(), ['sigma', 'sdf_distance', 'normals'])
+        with pytest.raises(NotImplementedError):
+            fs(x.cuda(), ['sigma', 'rgb'])
+    want = O.sampler(x, scene['planes'], scene['w1'], scene['b1'], scene['w2'][:11], scene['b2'][:11],
+                     scene['palette'], scene['beta'], scene['alpha'], scene['scene_range'],
+                     request=('sigma', 'sdf_distance', 'normals'))
+    for k in ('sigma', 'sdf_distance', 'normals'):
+        assert Hh.rel_l2(got[k].cpu().reshape(want[k].shape), want[k].detach()) < 1e-4, k
