@@ -101,3 +101,15 @@ def test_header_is_plain_c_and_links(tmp_path):
                                       _lib.RenderParams.workspace.offset,
                                       _lib.RenderParams.noise_seed.offset,
                                       _lib.SampleParams.points.offset]
+
+
+def test_backward_workspace_constant_matches_the_header():
+    """fused.py sizes the backward workspace (weight images + one accumulator row buffer per CTA of
+    render_wgrad_pipe) with _lib.BACKWARD_WORKSPACE_BYTES = NFI_BACKWARD_WORKSPACE_BYTES."""
+    import re
+    from nerf_from_image_b200 import _lib
+    m = re.search(r'#define NFI_BACKWARD_WORKSPACE_BYTES \((\d+) \+ (\d+) \* (\d+)\)', open(HEADER).read())
+    assert m, 'NFI_BACKWARD_WORKSPACE_BYTES missing from the header'
+    a, b, c = (int(x) for x in m.groups())
+    assert a + b * c == _lib.BACKWARD_WORKSPACE_BYTES
+    assert ('#define NFI_VIEW_FEATURES 32') in open(HEADER).read()
